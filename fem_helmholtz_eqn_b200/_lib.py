@@ -1,0 +1,123 @@
+"""ctypes binding of the C ABI in include/fem_helmholtz.h (libfemhelmholtz_b200.so).
+
+There is deliberately NO fallback: if the shared library is missing or no CUDA device is
+visible, every compute entry point raises.  PyTorch is used only for device memory, streams
+and (elsewhere) torch.distributed.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libfemhelmholtz_b200.so")
+
+FH_BC_NEUMANN, FH_BC_SOMMERFELD, FH_BC_DIRICHLET = 0, 1, 2
+FH_H_SCALAR, FH_H_NODAL = 0, 1
+BC_CODES = {"neumann": FH_BC_NEUMANN, "sommerfeld": FH_BC_SOMMERFELD, "dirichlet": FH_BC_DIRICHLET}
+
+
+class FHError(RuntimeError):
+    """A call into libfemhelmholtz_b200 failed (the message comes from fh_last_error())."""
+
+
+class Problem1d(C.Structure):
+    _fields_ = [
+        ("n_elem", C.c_int64), ("h", C.c_double), ("x", C.c_void_p), ("h_mode", C.c_int),
+        ("bc_left", C.c_int), ("bc_right", C.c_int),
+        ("g_left_re", C.c_double), ("g_left_im", C.c_double),
+        ("g_right_re", C.c_double), ("g_right_im", C.c_double),
+        ("cos_theta", C.c_double), ("gauss_xi", C.c_double), ("gauss_w", C.c_double),
+    ]
+
+
+_P = C.c_void_p
+_SIGNATURES = {
+    # name: (restype, argtypes)
+    "fh_last_error": (C.c_char_p, []),
+    "fh_abi_version": (C.c_int, []),
+    "fh_device_info": (C.c_int, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                 C.POINTER(C.c_size_t)]),
+    "fh_shape_functions_1d": (C.c_int, [C.c_double, _P, _P, _P]),
+    "fh_element_matrices_1d": (C.c_int, [C.c_double, C.c_double, C.c_double, _P, _P, _P]),
+    "fh_boundary_matrices_1d": (C.c_int, [C.c_double, C.c_double, _P, _P, _P]),
+    "fh_assemble_1d_c128": (C.c_int, [C.POINTER(Problem1d), _P, _P, C.c_int64, _P, _P, _P, _P, _P]),
+    "fh_tridiag_batched_max_n": (C.c_int64, []),
+    "fh_tridiag_solve_batched_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
+    "fh_tridiag_solve_batched_c128": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, _P,
+                                                C.c_size_t, _P]),
+    "fh_helmholtz1d_sweep_fused_c128": (C.c_int, [C.POINTER(Problem1d), _P, _P, C.c_int64, _P, _P, _P,
+                                                  C.c_size_t, _P]),
+    "fh_tridiag_solve_large_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "fh_tridiag_solve_large_c128": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P, _P, C.c_size_t, _P]),
+    "fh_tridiag_residual_c128": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, _P]),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    """Names every build of the library must export (checked by the CPU test-suite)."""
+    return sorted(_SIGNATURES)
+
+
+def load():
+    """Load the shared library (no GPU needed for this step)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C fem_helmholtz_eqn_b200/csrc`).  There is no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("fem_helmholtz_eqn_b200 needs a CUDA device (B200, sm_100a); "
+                           "there is no CPU fallback")
+    return load()
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().fh_last_error().decode("utf-8", "replace")
+        raise FHError(f"{what} failed with code {rc}: {msg}")
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (or NULL for None)."""
+    if t is None:
+        return C.c_void_p(0)
+    assert t.is_cuda and t.is_contiguous(), "expected a contiguous CUDA tensor"
+    return C.c_void_p(t.data_ptr())
+
+
+def device():
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def as_device(a, dtype):
+    """numpy / torch / scalar sequence -> contiguous CUDA tensor of `dtype` (H2D copy if needed)."""
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device(), dtype=dtype).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(device())
+
+
+def device_info():
+    lib = require_cuda()
+    sm, major, minor, smem = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
+    check(lib.fh_device_info(C.byref(sm), C.byref(major), C.byref(minor), C.byref(smem)), "fh_device_info")
+    return {"sm_count": sm.value, "cc": (major.value, minor.value), "smem_optin": smem.value}

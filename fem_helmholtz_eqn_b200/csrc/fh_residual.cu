@@ -1,0 +1,80 @@
+// Residual / parity metrics of a batch of tridiagonal systems, on device (gate G3):
+// out[s] = { ||b - A u||_2^2, ||u||_2^2, ||b||_2^2, ||A||_inf }.  One CTA per system (grid-stride),
+// coalesced streaming reads (96 B per row), fixed-shape tree reductions => deterministic results.
+#include "fh_common.cuh"
+
+namespace fh {
+
+constexpr int kResThreads = 256;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__global__ void __launch_bounds__(kResThreads)
+residual_kernel(const cplx *__restrict__ dl, const cplx *__restrict__ d, const cplx *__restrict__ du,
+                const cplx *__restrict__ b, const cplx *__restrict__ u, int64_t n, int64_t batch,
+                double *__restrict__ out) {
+    __shared__ double red[4][kResThreads / 32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int64_t s = blockIdx.x; s < batch; s += gridDim.x) {
+        const int64_t base = s * n;
+        double r2 = 0.0, u2 = 0.0, b2 = 0.0, amax = 0.0;
+        for (int64_t j = t; j < n; j += kResThreads) {
+            const cplx uj = u[base + j], bj = ldg_stream(b + base + j), dj = ldg_stream(d + base + j);
+            cplx r = nmsub(bj, dj, uj);
+            double rowsum = hypot(dj.re, dj.im);
+            if (j > 0) {
+                const cplx lj = ldg_stream(dl + base + j);
+                r = nmsub(r, lj, u[base + j - 1]);
+                rowsum += hypot(lj.re, lj.im);
+            }
+            if (j < n - 1) {
+                const cplx hj = ldg_stream(du + base + j);
+                r = nmsub(r, hj, u[base + j + 1]);
+                rowsum += hypot(hj.re, hj.im);
+            }
+            r2 += r.re * r.re + r.im * r.im;
+            u2 += uj.re * uj.re + uj.im * uj.im;
+            b2 += bj.re * bj.re + bj.im * bj.im;
+            amax = fmax(amax, rowsum);
+        }
+        r2 = warp_sum(r2), u2 = warp_sum(u2), b2 = warp_sum(b2), amax = warp_max(amax);
+        if (lane == 0) red[0][warp] = r2, red[1][warp] = u2, red[2][warp] = b2, red[3][warp] = amax;
+        __syncthreads();
+        if (warp == 0) {
+            const int nw = kResThreads / 32;
+            double v0 = lane < nw ? red[0][lane] : 0.0, v1 = lane < nw ? red[1][lane] : 0.0;
+            double v2 = lane < nw ? red[2][lane] : 0.0, v3 = lane < nw ? red[3][lane] : 0.0;
+            v0 = warp_sum(v0), v1 = warp_sum(v1), v2 = warp_sum(v2), v3 = warp_max(v3);
+            if (lane == 0) out[4 * s + 0] = v0, out[4 * s + 1] = v1, out[4 * s + 2] = v2, out[4 * s + 3] = v3;
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace fh
+
+extern "C" int fh_tridiag_residual_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c128 *du, const fh_c128 *b,
+                                        const fh_c128 *u, int64_t n, int64_t batch, double *out4,
+                                        fh_stream_t stream) {
+    using namespace fh;
+    FH_REQUIRE(n >= 0 && batch >= 0, "n and batch must be >= 0");
+    if (n == 0 || batch == 0) return FH_OK;
+    FH_REQUIRE(dl && d && du && b && u && out4, "NULL device pointer");
+    int64_t grid = 8ll * sm_count();
+    if (grid > batch) grid = batch;
+    if (grid < 1) grid = 1;
+    residual_kernel<<<(unsigned)grid, kResThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const cplx *>(dl), reinterpret_cast<const cplx *>(d), reinterpret_cast<const cplx *>(du),
+        reinterpret_cast<const cplx *>(b), reinterpret_cast<const cplx *>(u), n, batch, out4);
+    FH_LAUNCH_CHECK("residual_kernel");
+    return FH_OK;
+}

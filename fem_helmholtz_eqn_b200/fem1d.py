@@ -1,0 +1,309 @@
+"""1D P1 Helmholtz FEM on the GPU behind the reference notebook's own function names.
+
+Mirrors code cell 2 of the reference's ``notebooks/1D_soln.ipynb`` (``nb:N`` = raw JSON line):
+
+    create_mesh            nb:33-47      shape_functions      nb:55-67
+    element_matrices       nb:70-96      boundary_matrices    nb:99-131
+    assembly               nb:134-187    solve_helmholtz_fem  nb:190-205
+    analytical_solution    nb:208-219    compute_L2_error     nb:259-281
+
+Same names, argument order, defaults and return shapes.  What differs is where the work
+happens: assembly writes tridiagonal bands (the reference's dense ``A`` is tridiagonal) with a
+CUDA kernel, and the solve is a CUDA batched tridiagonal solver; both are reached through the
+C ABI of ``include/fem_helmholtz.h``.  There is no CPU fallback.
+
+Additions (keyword-only, defaults keep the reference behaviour): Dirichlet row replacement
+(``solvers/fem2d_dirichlet.py:20-27`` convention) via ``bc_left`` / ``bc_right``, a batched
+wavenumber sweep ``solve_helmholtz_sweep`` and the fused (bands never stored) variant.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import BC_CODES, FH_H_NODAL, FH_H_SCALAR, Problem1d, check, ptr, stream_ptr
+
+# nb:52: gauss_point, gauss_weight = np.polynomial.legendre.leggauss(1)
+gauss_point = np.array([0.0])
+gauss_weight = np.array([2.0])
+
+
+# ------------------------------------------------------------------------------------------------
+# mesh (L1 in SURVEY.md: problem data, produced on the host exactly as the reference does)
+# ------------------------------------------------------------------------------------------------
+def create_mesh(N, L=1.0):
+    """nb:33-47.  ``h`` is the scalar ``L / N``; connectivity is the canonical ``[i, i+1]``
+    (the GPU kernels treat it as implicit and never read it)."""
+    h = L / N
+    nodes = np.linspace(0, L, N + 1)
+    idx = np.arange(N)
+    elements = np.stack([idx, idx + 1], axis=1)
+    return h, nodes, elements
+
+
+# ------------------------------------------------------------------------------------------------
+# element routines (device, one thread: they exist for API parity and bit-parity tests)
+# ------------------------------------------------------------------------------------------------
+def shape_functions(xi):
+    """nb:55-67 -> (basis_fns[2], dbasis_dxi[2]) as numpy arrays."""
+    lib = _lib.require_cuda()
+    out = torch.empty(4, dtype=torch.float64, device=_lib.device())
+    check(lib.fh_shape_functions_1d(float(xi), ptr(out[:2]), ptr(out[2:]), stream_ptr()),
+          "fh_shape_functions_1d")
+    res = out.cpu().numpy()
+    return res[:2].copy(), res[2:].copy()
+
+
+def element_matrices(h, xi=gauss_point[0], w=gauss_weight[0]):
+    """nb:70-96 -> (Ke[2,2], Me[2,2]) as numpy arrays, bit-identical to the reference."""
+    lib = _lib.require_cuda()
+    out = torch.empty(8, dtype=torch.float64, device=_lib.device())
+    check(lib.fh_element_matrices_1d(float(h), float(xi), float(w), ptr(out[:4]), ptr(out[4:]),
+                                     stream_ptr()), "fh_element_matrices_1d")
+    res = out.cpu().numpy()
+    return res[:4].reshape(2, 2).copy(), res[4:].reshape(2, 2).copy()
+
+
+def boundary_matrices(h, k, theta=0.0):
+    """nb:99-131 -> (Ne[2], Se[2,2]) complex numpy arrays (``h`` is unused, as in the reference)."""
+    lib = _lib.require_cuda()
+    out = torch.empty(6, dtype=torch.complex128, device=_lib.device())
+    check(lib.fh_boundary_matrices_1d(float(k), float(np.cos(theta)), ptr(out[:2]), ptr(out[2:]),
+                                      stream_ptr()), "fh_boundary_matrices_1d")
+    res = out.cpu().numpy()
+    return res[:2].copy(), res[2:].reshape(2, 2).copy()
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers
+# ------------------------------------------------------------------------------------------------
+def _host_k_and_k2(k):
+    """Return (ks fp64[n_k], k2s fp64[n_k], scalar?) with k**2 evaluated on the host the way
+    nb:185 does (``k**2`` of a Python number goes through CPython's pow, of an array through numpy)."""
+    if isinstance(k, torch.Tensor):
+        k = k.detach().cpu().numpy()
+    if np.isscalar(k) or (isinstance(k, np.ndarray) and k.ndim == 0):
+        return np.array([float(k)]), np.array([float(k**2)]), True
+    if isinstance(k, np.ndarray):
+        ks = np.ascontiguousarray(k, dtype=np.float64).ravel()
+        return ks, ks**2, False
+    ks = list(k)
+    return (np.array([float(v) for v in ks], dtype=np.float64),
+            np.array([float(v**2) for v in ks], dtype=np.float64), False)
+
+
+def _problem(N, h, theta, bc_left, bc_right, g_left, g_right, nodes_dev):
+    if bc_left not in ("neumann", "dirichlet"):
+        raise ValueError(f"bc_left must be 'neumann' or 'dirichlet', got {bc_left!r}")
+    if bc_right not in ("sommerfeld", "dirichlet"):
+        raise ValueError(f"bc_right must be 'sommerfeld' or 'dirichlet', got {bc_right!r}")
+    gl, gr = complex(g_left), complex(g_right)
+    return Problem1d(
+        n_elem=int(N), h=float(h), x=(nodes_dev.data_ptr() if nodes_dev is not None else None),
+        h_mode=FH_H_NODAL if nodes_dev is not None else FH_H_SCALAR,
+        bc_left=BC_CODES[bc_left], bc_right=BC_CODES[bc_right],
+        g_left_re=gl.real, g_left_im=gl.imag, g_right_re=gr.real, g_right_im=gr.imag,
+        cos_theta=float(np.cos(theta)), gauss_xi=float(gauss_point[0]), gauss_w=float(gauss_weight[0]))
+
+
+def _check_elements(N, elements):
+    if elements is None:
+        return
+    shape = tuple(elements.shape)
+    if shape != (N, 2):
+        raise ValueError(f"elements must have shape ({N}, 2), got {shape}")
+    first, last = np.asarray(elements[0]).tolist(), np.asarray(elements[-1]).tolist()
+    if first != [0, 1] or last != [N - 1, N]:
+        raise ValueError("only the reference's canonical connectivity [[i, i+1]] is supported")
+
+
+def _raise_if_singular(status):
+    if status is not None and bool(torch.any(status != 0).item()):
+        bad = torch.nonzero(status).flatten()[:8].tolist()
+        raise np.linalg.LinAlgError(f"Singular matrix (zero pivot / non-finite solution) in systems {bad}")
+
+
+# ------------------------------------------------------------------------------------------------
+# the assembled operator
+# ------------------------------------------------------------------------------------------------
+class TridiagonalSystem:
+    """Device-resident ``A`` of ``assembly``: bands ``dl, d, du`` as complex128[batch, n] CUDA tensors
+    (``dl[:, 0]`` and ``du[:, n-1]`` are zero).  ``np.asarray(A)`` / ``A.to_dense()`` materialise the
+    reference's dense matrix, so ``np.linalg.solve(A, b)`` still works for small N."""
+
+    def __init__(self, dl, d, du, rhs=None, scalar=True):
+        self.dl, self.d, self.du, self.rhs = dl, d, du, rhs
+        self.batch, self.n = d.shape
+        self._scalar = scalar
+
+    @property
+    def shape(self):
+        return (self.n, self.n) if self._scalar else (self.batch, self.n, self.n)
+
+    dtype = np.dtype(np.complex128)
+
+    def bands(self, i=0):
+        """(dl, d, du) of system i as numpy arrays of length n (LAPACK gtsv style + padding)."""
+        return tuple(t[i].cpu().numpy() for t in (self.dl, self.d, self.du))
+
+    def to_dense(self, i=0):
+        dl, d, du = self.bands(i)
+        A = np.zeros((self.n, self.n), dtype=complex)
+        idx = np.arange(self.n)
+        A[idx, idx] = d
+        A[idx[1:], idx[:-1]] = dl[1:]
+        A[idx[:-1], idx[1:]] = du[:-1]
+        return A
+
+    def __array__(self, dtype=None, copy=None):
+        if self.batch != 1:
+            raise ValueError("np.asarray() of a batched system is ambiguous; use to_dense(i)")
+        A = self.to_dense(0)
+        return A.astype(dtype) if dtype is not None else A
+
+    def solve(self, b=None, check_singular=True):
+        """Solve every system of the batch on the GPU.  ``b``: None (use the assembled load),
+        numpy or torch, shape [n] or [batch, n].  Returns a CUDA tensor complex128[batch, n]."""
+        rhs = self.rhs if b is None else _lib.as_device(b, torch.complex128).reshape(self.batch, self.n)
+        u, status = solve_tridiagonal(self.dl, self.d, self.du, rhs)
+        if check_singular:
+            _raise_if_singular(status)
+        return u
+
+    def residual(self, u, b=None):
+        rhs = self.rhs if b is None else _lib.as_device(b, torch.complex128).reshape(self.batch, self.n)
+        return tridiagonal_residual(self.dl, self.d, self.du, rhs, u)
+
+
+# ------------------------------------------------------------------------------------------------
+# assembly + solve
+# ------------------------------------------------------------------------------------------------
+def assemble_bands(N, k, h, theta=0.0, *, bc_left="neumann", bc_right="sommerfeld", g_left=1.0,
+                   g_right=0.0, nodes=None, out=None):
+    """Device-side assembly (nb:134-187) for one or many wavenumbers.
+
+    Returns ``(dl, d, du, b)`` CUDA tensors complex128[n_k, N+1].  ``nodes`` (fp64[N+1]) switches to
+    per-element sizes ``x[e+1]-x[e]``; the default reproduces the reference's scalar ``h``.
+    ``out``: optional preallocated complex128[4, n_k, N+1] CUDA tensor."""
+    lib = _lib.require_cuda()
+    ks, k2s = k if isinstance(k, tuple) else _host_k_and_k2(k)[:2]  # tuple = (ks, k2s) already split
+    n_k, n = len(ks), int(N) + 1
+    dev = _lib.device()
+    ks_d, k2s_d = _lib.as_device(ks, torch.float64), _lib.as_device(k2s, torch.float64)
+    nodes_d = _lib.as_device(nodes, torch.float64) if nodes is not None else None
+    if nodes_d is not None and nodes_d.numel() != n:
+        raise ValueError(f"nodes must have {n} entries")
+    if out is None:
+        out = torch.empty((4, n_k, n), dtype=torch.complex128, device=dev)
+    assert out.shape == (4, n_k, n) and out.dtype == torch.complex128 and out.is_contiguous()
+    prob = _problem(N, h, theta, bc_left, bc_right, g_left, g_right, nodes_d)
+    check(lib.fh_assemble_1d_c128(C.byref(prob), ptr(ks_d), ptr(k2s_d), n_k, ptr(out[0]), ptr(out[1]),
+                                  ptr(out[2]), ptr(out[3]), stream_ptr()), "fh_assemble_1d_c128")
+    return out[0], out[1], out[2], out[3]
+
+
+def assembly(N: int, k, h: float, elements=None, theta=0.0, *, bc_left="neumann", bc_right="sommerfeld",
+             g_left=1.0, g_right=0.0, nodes=None):
+    """nb:134-187 -> ``(A, b)``.
+
+    ``A`` is a :class:`TridiagonalSystem` (device bands; ``np.asarray(A)`` is the reference's dense
+    matrix).  For a scalar ``k`` (the reference's call) ``b`` is a numpy complex128[N+1] array; for a
+    sequence of wavenumbers ``b`` is a CUDA tensor complex128[n_k, N+1]."""
+    _check_elements(int(N), elements)
+    _, _, scalar = _host_k_and_k2(k)
+    dl, d, du, b = assemble_bands(N, k, h, theta, bc_left=bc_left, bc_right=bc_right, g_left=g_left,
+                                  g_right=g_right, nodes=nodes)
+    A = TridiagonalSystem(dl, d, du, rhs=b, scalar=scalar)
+    return (A, b[0].cpu().numpy()) if scalar else (A, b)
+
+
+def solve_tridiagonal(dl, d, du, b, out=None):
+    """Batched tridiagonal solve on the GPU (replaces nb:204).  All arguments complex128[batch, n]
+    CUDA tensors (numpy accepted and uploaded).  Returns ``(u, status)``; ``status[i] != 0`` flags a
+    breakdown (the caller decides whether to raise)."""
+    lib = _lib.require_cuda()
+    dl, d, du, b = (_lib.as_device(t, torch.complex128) for t in (dl, d, du, b))
+    if d.dim() == 1:
+        dl, d, du, b = (t.reshape(1, -1) for t in (dl, d, du, b))
+    batch, n = d.shape
+    for t in (dl, du, b):
+        if tuple(t.shape) != (batch, n):
+            raise ValueError("dl, d, du, b must share the shape [batch, n]")
+    u = out if out is not None else torch.empty_like(d)
+    status = torch.empty(batch, dtype=torch.int32, device=d.device)
+    ws_bytes = lib.fh_tridiag_solve_batched_workspace_bytes(n, batch)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=d.device)
+    check(lib.fh_tridiag_solve_batched_c128(ptr(dl), ptr(d), ptr(du), ptr(b), ptr(u), n, batch, ptr(status),
+                                            ptr(ws), ws_bytes, stream_ptr()), "fh_tridiag_solve_batched_c128")
+    return u, status
+
+
+def tridiagonal_residual(dl, d, du, b, u):
+    """Device-side parity metrics per system: dict of numpy arrays ``backward`` (normwise backward
+    error ||b-Au|| / (||A||_inf ||u|| + ||b||)), ``relres`` (||b-Au||/||b||), ``r2, u2, b2, anorm``."""
+    lib = _lib.require_cuda()
+    dl, d, du, b, u = (_lib.as_device(t, torch.complex128) for t in (dl, d, du, b, u))
+    if d.dim() == 1:
+        dl, d, du, b, u = (t.reshape(1, -1) for t in (dl, d, du, b, u))
+    batch, n = d.shape
+    out = torch.empty((batch, 4), dtype=torch.float64, device=d.device)
+    check(lib.fh_tridiag_residual_c128(ptr(dl), ptr(d), ptr(du), ptr(b), ptr(u), n, batch, ptr(out),
+                                       stream_ptr()), "fh_tridiag_residual_c128")
+    o = out.cpu().numpy()
+    r, un, bn, an = np.sqrt(o[:, 0]), np.sqrt(o[:, 1]), np.sqrt(o[:, 2]), o[:, 3]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return {"backward": r / (an * un + bn), "relres": r / bn, "r2": o[:, 0], "u2": o[:, 1],
+                "b2": o[:, 2], "anorm": an}
+
+
+def solve_helmholtz_sweep(N, ks, L=1.0, theta=0.0, *, bc_left="neumann", bc_right="sommerfeld",
+                          g_left=1.0, g_right=0.0, fused=False, nodal_h=False, out=None,
+                          check_singular=True, return_status=False):
+    """Assemble and solve the 1D problem for every wavenumber in ``ks`` (the shape of the reference's
+    sweep loop nb:300-317 / nb:469-471, batched).  Returns ``(nodes, U)`` with ``U`` a CUDA tensor
+    complex128[n_k, N+1].
+
+    ``fused=False`` (default): staged pipeline, ``assembly`` writes the bands, the batched solver
+    reads them back -- the reference's structure.  ``fused=True``: one kernel generates the rows in
+    registers and only writes ``U``."""
+    lib = _lib.require_cuda()
+    h, nodes, _ = create_mesh(N, L)
+    ks_h, k2s_h, _ = _host_k_and_k2(ks)
+    n_k, n = len(ks_h), int(N) + 1
+    dev = _lib.device()
+    nodes_d = _lib.as_device(nodes, torch.float64) if nodal_h else None
+    if not fused:
+        dl, d, du, b = assemble_bands(N, (ks_h, k2s_h), h, theta, bc_left=bc_left, bc_right=bc_right, g_left=g_left, g_right=g_right,
+                                      nodes=nodes if nodal_h else None)
+        U, status = solve_tridiagonal(dl, d, du, b, out=out)
+    else:
+        ks_d, k2s_d = _lib.as_device(ks_h, torch.float64), _lib.as_device(k2s_h, torch.float64)
+        U = out if out is not None else torch.empty((n_k, n), dtype=torch.complex128, device=dev)
+        status = torch.empty(n_k, dtype=torch.int32, device=dev)
+        prob = _problem(N, h, theta, bc_left, bc_right, g_left, g_right, nodes_d)
+        check(lib.fh_helmholtz1d_sweep_fused_c128(C.byref(prob), ptr(ks_d), ptr(k2s_d), n_k, ptr(U),
+                                                  ptr(status), None, 0, stream_ptr()),
+              "fh_helmholtz1d_sweep_fused_c128")
+    if check_singular:
+        _raise_if_singular(status)
+    return (nodes, U, status) if return_status else (nodes, U)
+
+
+def solve_helmholtz_fem(N, k, order=0, L=1.0, *, theta=0.0, bc_left="neumann", bc_right="sommerfeld",
+                        g_left=1.0, g_right=0.0, fused=False):
+    """nb:190-205 -> ``(nodes, u)`` as numpy arrays (``order`` is accepted and ignored, as in the
+    reference).  create_mesh -> device assembly -> device solve -> one D2H copy of ``u``."""
+    nodes, U = solve_helmholtz_sweep(N, [k], L, theta, bc_left=bc_left, bc_right=bc_right,
+                                     g_left=g_left, g_right=g_right, fused=fused)
+    return nodes, U[0].cpu().numpy()
+
+
+def analytical_solution(x, k):
+    """nb:208-219: the continuum solution ``-exp(i k x)`` (verification helper, evaluated where ``x``
+    lives: numpy in -> numpy out, torch in -> torch out)."""
+    if isinstance(x, torch.Tensor):
+        return -torch.exp(1j * k * x.to(torch.complex128))
+    return -np.exp(1j * k * x)

@@ -1,0 +1,123 @@
+/*
+ * fem_helmholtz.h -- C ABI of the B200-native Helmholtz FEM hot path
+ * (libfemhelmholtz_b200.so, built from fem_helmholtz_eqn_b200/csrc/ for sm_100a).
+ *
+ * The reference (anishasahu/fem-helmholtz-eqn) has no FFI layer: its seam is a Python call
+ * surface.  Each entry point below names the reference interface it replaces
+ * (nb:N = raw JSON line N of notebooks/1D_soln.ipynb; other paths are under src/).
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers unless the name ends in _host.  The caller owns every
+ *     buffer; the library allocates nothing persistent.  Scratch space is passed in and sized by
+ *     the matching *_workspace_bytes() query.
+ *   - complex128 is stored as interleaved (re, im) doubles, identical to numpy.complex128 /
+ *     torch.complex128 / cuDoubleComplex.  Complex scalars cross the ABI as two doubles.
+ *   - Every call is asynchronous and ordered on `stream` (a cudaStream_t passed as void*).
+ *   - Return value: 0 = ok, < 0 = invalid argument (FH_E_*), > 0 = a cudaError_t.
+ *     fh_last_error() returns a thread-local description of the last failure.
+ *   - No exceptions cross the boundary; the library keeps no global mutable state besides the
+ *     thread-local error string and one-time per-device kernel attribute setup.
+ *   - Batched 1D arrays are batch-major: entry (system s, row j) lives at [s * n + j].
+ *     Tridiagonal bands use n entries per system: dl[s][0] and du[s][n-1] are ignored.
+ */
+#ifndef FEM_HELMHOLTZ_H
+#define FEM_HELMHOLTZ_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FH_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define FH_API __attribute__((visibility("default")))
+#else
+#define FH_API
+#endif
+
+typedef void *fh_stream_t;            /* cudaStream_t */
+typedef struct { double re, im; } fh_c128;
+
+enum { FH_OK = 0, FH_E_INVALID = -1, FH_E_UNSUPPORTED = -2, FH_E_WORKSPACE = -3 };
+
+/* Boundary rows of the 1D problem.
+ *   NEUMANN    (left)  : load b[0] += -i k cos(theta)                       nb:113-121, nb:174-176
+ *   SOMMERFELD (right) : A[N,N] += i k                                      nb:124-129, nb:179-182
+ *   DIRICHLET          : row replacement A[row]=0; A[row,row]=1; b[row]=g   solvers/fem2d_dirichlet.py:20-27 */
+enum { FH_BC_NEUMANN = 0, FH_BC_SOMMERFELD = 1, FH_BC_DIRICHLET = 2 };
+
+/* Element size: SCALAR = the reference's h = L/N for every element (nb:44, nb:158);
+ * NODAL = h_e = x[e+1] - x[e] from the node array (general meshes; extension). */
+enum { FH_H_SCALAR = 0, FH_H_NODAL = 1 };
+
+/* Description of one 1D Helmholtz problem family (shared by assembly and the fused solver). */
+typedef struct {
+    int64_t n_elem;            /* N; the system has n = N + 1 rows                                  */
+    double h;                  /* scalar element size (FH_H_SCALAR)                                  */
+    const double *x;           /* device fp64[N+1] node coordinates (FH_H_NODAL) or NULL             */
+    int h_mode;                /* FH_H_*                                                             */
+    int bc_left, bc_right;     /* FH_BC_*: left in {NEUMANN, DIRICHLET}, right in {SOMMERFELD, DIRICHLET} */
+    double g_left_re, g_left_im;   /* Dirichlet value at x = 0                                       */
+    double g_right_re, g_right_im; /* Dirichlet value at x = L                                       */
+    double cos_theta;          /* cos(incident angle), evaluated by the caller (nb:113)              */
+    double gauss_xi, gauss_w;  /* the 1-point rule the reference uses: leggauss(1) = (0, 2)  nb:52   */
+} fh_problem1d;
+
+FH_API const char *fh_last_error(void);
+FH_API int fh_abi_version(void);
+/* Device facts the host layer needs for grid sizing / the bench (SM count etc.). Host pointers. */
+FH_API int fh_device_info(int *sm_count_host, int *cc_major_host, int *cc_minor_host, size_t *smem_optin_host);
+
+/* ---- element routines (replace nb:55-67 shape_functions, nb:70-96 element_matrices,
+ *      nb:99-131 boundary_matrices); outputs are tiny device arrays, row-major -------------------- */
+FH_API int fh_shape_functions_1d(double xi, double *phi2, double *dphi2, fh_stream_t stream);
+FH_API int fh_element_matrices_1d(double h, double xi, double w, double *Ke4, double *Me4, fh_stream_t stream);
+FH_API int fh_boundary_matrices_1d(double k, double cos_theta, fh_c128 *Ne2, fh_c128 *Se4, fh_stream_t stream);
+
+/* ---- assembly (replaces nb:134-187 `assembly`): A = -K + k^2 M + S as tridiagonal bands ---------
+ * ks / k2s: device fp64[n_k]; k2s[i] must be the caller's k**2 (nb:185 evaluates it on the host).
+ * dl, d, du, b: device complex128[n_k][N+1].  Values are bit-identical to the reference's dense A. */
+FH_API int fh_assemble_1d_c128(const fh_problem1d *prob_host, const double *ks, const double *k2s,
+                        int64_t n_k, fh_c128 *dl, fh_c128 *d, fh_c128 *du, fh_c128 *b,
+                        fh_stream_t stream);
+
+/* ---- batched tridiagonal solve (replaces nb:204 `np.linalg.solve(A, b)` for tridiagonal A) ------
+ * Thread-chunk partition (8 rows per thread in registers) + parallel cyclic reduction of the
+ * per-thread interface rows in shared memory; a 2-CTA cluster solves one system when n > 2056.
+ * status[batch] (device int32, may be NULL): bit 0 set if the solution holds a non-finite value
+ * (zero pivot / singular system).  n <= fh_tridiag_batched_max_n() takes the cluster kernel, larger
+ * n is routed to the partitioned large-system solver using `workspace`. */
+FH_API int64_t fh_tridiag_batched_max_n(void);
+FH_API size_t fh_tridiag_solve_batched_workspace_bytes(int64_t n, int64_t batch);
+FH_API int fh_tridiag_solve_batched_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c128 *du,
+                                  const fh_c128 *b, fh_c128 *u, int64_t n, int64_t batch,
+                                  int32_t *status, void *workspace, size_t workspace_bytes,
+                                  fh_stream_t stream);
+
+/* ---- fused assemble+solve sweep (nb:190-205 `solve_helmholtz_fem` for many k at once): the bands
+ * are generated in registers and never stored; only u[n_k][N+1] is written. ----------------------- */
+FH_API int fh_helmholtz1d_sweep_fused_c128(const fh_problem1d *prob_host, const double *ks, const double *k2s,
+                                    int64_t n_k, fh_c128 *u, int32_t *status, void *workspace,
+                                    size_t workspace_bytes, fh_stream_t stream);
+
+/* ---- one very large system (single mesh of up to 2^31-2 rows per GPU): recursive partition ------
+ * levels: each level turns chunks of 16 rows into one interface row; the coarsest level is solved by
+ * the batched kernel; back-substitution re-reads the bands (2 passes over the data). */
+FH_API size_t fh_tridiag_solve_large_workspace_bytes(int64_t n);
+FH_API int fh_tridiag_solve_large_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c128 *du,
+                                const fh_c128 *b, fh_c128 *u, int64_t n, int32_t *status,
+                                void *workspace, size_t workspace_bytes, fh_stream_t stream);
+
+/* ---- residual / parity metrics on device -------------------------------------------------------
+ * out[s] = { ||b - A u||_2^2, ||u||_2^2, ||b||_2^2, ||A||_inf } for each system s (device fp64[batch][4]). */
+FH_API int fh_tridiag_residual_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c128 *du, const fh_c128 *b,
+                             const fh_c128 *u, int64_t n, int64_t batch, double *out4,
+                             fh_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FEM_HELMHOLTZ_H */

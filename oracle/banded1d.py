@@ -73,6 +73,10 @@ def to_dense(dl, d, du):
 
 def solve_bands(dl, d, du, b):
     """LAPACK zgtsv on copies; raises LinAlgError like np.linalg.solve would."""
+    if len(d) == 1:
+        if d[0] == 0:
+            raise np.linalg.LinAlgError("singular 1x1 system")
+        return np.asarray(b, dtype=complex) / d[0]
     _, _, _, x, info = lapack.zgtsv(dl[1:].copy(), d.copy(), du[:-1].copy(), b.copy())
     if info != 0:
         raise np.linalg.LinAlgError(f"zgtsv info={info}")

@@ -1,0 +1,93 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads without a GPU, exports every
+symbol include/fem_helmholtz.h declares, and the product refuses to run without CUDA."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+fh = pytest.importorskip("fem_helmholtz_eqn_b200")
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "fem_helmholtz.h")).read()
+    return sorted(set(re.findall(r"FH_API[^;(]*?\b(fh_\w+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    assert _declared_symbols() == fh._lib.exported_symbols()
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(fh._lib.LIB_PATH)
+    for name in _declared_symbols():
+        assert hasattr(lib, name), name
+    assert fh._lib.load().fh_abi_version() == 1
+    assert fh._lib.load().fh_tridiag_batched_max_n() == 4112
+
+
+def test_invalid_arguments_are_reported_without_gpu():
+    lib = fh._lib.load()
+    rc = lib.fh_assemble_1d_c128(None, None, None, 1, None, None, None, None, None)
+    assert rc == -1 and b"NULL" in lib.fh_last_error()
+    p = fh._lib.Problem1d(n_elem=0, h=0.1, h_mode=0, bc_left=0, bc_right=1)
+    rc = lib.fh_assemble_1d_c128(ctypes.byref(p), None, None, 1, None, None, None, None, None)
+    assert rc == -1 and b"n_elem" in lib.fh_last_error()
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fh.solve_helmholtz_fem(10, 1.0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fh.element_matrices(0.1)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "fem_helmholtz_eqn_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+                assert "oracle/" not in src or f.endswith(".md"), f
+
+
+def test_host_mesh_and_k2_logic():
+    h, nodes, elements = fh.create_mesh(100, 2.0)
+    assert h == 2.0 / 100 and nodes.shape == (101,) and elements.shape == (100, 2)
+    assert elements.dtype == np.int64 and elements[-1].tolist() == [99, 100]
+    from fem_helmholtz_eqn_b200.fem1d import _host_k_and_k2
+    ks, k2s, scalar = _host_k_and_k2(5)
+    assert scalar and ks[0] == 5.0 and k2s[0] == 25.0
+    ks, k2s, scalar = _host_k_and_k2([1.5, 2])
+    assert not scalar and k2s.tolist() == [1.5**2, 4.0]
+    ks, k2s, scalar = _host_k_and_k2(np.linspace(1, 1000, 7))
+    assert np.array_equal(k2s, np.linspace(1, 1000, 7) ** 2)
+
+
+def test_kernel_algorithm_model_matches_lapack():
+    """The numpy model of the CUDA kernel's algorithm (tests/models) agrees with zgtsv on the edge sizes
+    of the slot map; keeps the index maps / cluster coupling honest on machines without a GPU."""
+    from oracle import banded1d
+    from models.partition_pcr_model import solve
+    rng = np.random.default_rng(1)
+    for n in (1, 2, 9, 2048, 2050, 2056, 2057, 4097, 4112):
+        dl = rng.normal(size=n) + 1j * rng.normal(size=n)
+        du = rng.normal(size=n) + 1j * rng.normal(size=n)
+        d = 4 + rng.normal(size=n) + 1j * rng.normal(size=n)
+        b = rng.normal(size=n) + 1j * rng.normal(size=n)
+        dl[0] = 0
+        du[-1] = 0
+        u = solve(dl, d, du, b)
+        ref = banded1d.solve_bands(dl, d, du, b)
+        assert np.linalg.norm(u - ref) / np.linalg.norm(ref) < 1e-13, n
+    for N, k in ((999, 10.0), (4096, 1000.0)):
+        bands = banded1d.assemble_bands(N, k, 1.0 / N)
+        be, _ = banded1d.residual_metrics(*bands, solve(*bands))
+        assert be < 1e-14
