@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""Benchmark of the Helmholtz FEM hot path (BASELINE.json: "assembled+solved DOF/s and Helmholtz
+solves/s (k-sweep)").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch of synthetic input: the staged pipeline
+(band assembly kernel -> batched tridiagonal solve kernel) over the wavenumber sweep of BASELINE
+configs[2]: 65,536 wavenumbers x the 4,096-element mesh per GPU (k in [1, 1000], Neumann +
+Sommerfeld rows, complex128).  Multi-GPU: every rank takes its own contiguous slice of a sweep of
+N x 65,536 wavenumbers (independent systems, no data-path collective) -> weak scaling.
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput; `e2e` goes through the public
+host-to-host API (pinned H2D of k, D2H of every solution) and is the number to hold against the
+reference arm (`--impl reference`: the reference's dense NumPy algorithm on the host cores).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ELEM = 4096          # elements per mesh (BASELINE configs[2])
+N_K_PER_GPU = 65536    # wavenumbers per GPU
+K_MIN, K_MAX = 1.0, 1000.0
+BYTES_ASSEMBLY = 64    # per DOF: dl, d, du, b written (scalar-h mode)
+BYTES_SOLVE = 80       # per DOF: 4 bands read + u written
+METRIC = "assembled+solved DOF/s (k-sweep, staged assembly -> batched tridiagonal solve)"
+
+
+def measured_peak_gbs():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, reasons, smax, power = [], set(), None, 0.0
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax = float(r[1])
+                power = max(power, float(r[2]))
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": power}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (the only place besides tests/ and smoke() that may touch oracle/)
+# ------------------------------------------------------------------------------------------------
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_step(ks_sample):
+    """The reference's own algorithm (dense assembly + np.linalg.solve, oracle/ref1d.py restates nb:134-205)
+    on a bounded sample of the sweep.  Returns seconds."""
+    from oracle import ref1d
+    t0 = time.perf_counter()
+    for k in ks_sample:
+        ref1d.solve_helmholtz_fem(N_ELEM, float(k))
+    return time.perf_counter() - t0
+
+
+def cpu_banded_rate(n_systems=64):
+    """Banded restatement (vectorised bands + LAPACK zgtsv, 1 thread): DOF/s."""
+    import numpy as np
+    from oracle import banded1d
+    ks = np.linspace(K_MIN, K_MAX, n_systems)
+    t0 = time.perf_counter()
+    for k in ks:
+        banded1d.solve_bands(*banded1d.assemble_bands(N_ELEM, float(k), 1.0 / N_ELEM))
+    return n_systems * (N_ELEM + 1) / (time.perf_counter() - t0)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation on the host cores, same metric/config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    ks_all = np.linspace(K_MIN, K_MAX, N_K_PER_GPU)
+    per_step = 1  # one dense 4097x4097 assembly+solve per step (~5 s on 8 cores): bounded sample
+    pick = lambda i: ks_all[(i * 7919) % N_K_PER_GPU: (i * 7919) % N_K_PER_GPU + per_step]
+    for i in range(args.warmup):
+        cpu_reference_step(pick(i))
+    t = 0.0
+    for i in range(args.steps):
+        t += cpu_reference_step(pick(args.warmup + i))
+    dof = args.steps * per_step * (N_ELEM + 1)
+    value = dof / t
+    threads = cpu_threads()
+    sample = (f"{per_step} wavenumber(s) of the sweep per step at N={N_ELEM} (dense complex128 "
+              f"{N_ELEM + 1}^2 assembly + LAPACK zgesv, as nb:134-205); the full 65,536-k step would take "
+              f"~{N_K_PER_GPU * t / (args.steps * per_step) / 3600:.0f} h")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "DOF/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "complex128",
+        "data": "synthetic", "config": workload_config(args.gpus),
+        "solves_per_s": args.steps * per_step / t,
+        "cpu_baseline": {"value": value, "unit": "DOF/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(n_gpus):
+    return {"workload": "BASELINE configs[2]: wavenumber sweep, 65,536 k x 4,096-element 1D mesh per GPU "
+                        "(k in [1,1000], Neumann + Sommerfeld rows)",
+            "n_elem": N_ELEM, "n_k_per_gpu": N_K_PER_GPU, "n_k_total": N_K_PER_GPU * n_gpus,
+            "dof_per_step": N_K_PER_GPU * n_gpus * (N_ELEM + 1),
+            "pipeline": "staged: fh_assemble_1d_c128 -> fh_tridiag_solve_batched_c128",
+            "parallelism": f"k-sharded x{n_gpus}, no data-path collective",
+            "l2": "inputs larger than L2 (17.2 GB of bands + 4.3 GB of solutions per step; no flush needed)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import ctypes as C
+
+    import numpy as np
+    import torch
+
+    import fem_helmholtz_eqn_b200 as fh
+    from fem_helmholtz_eqn_b200 import fem1d
+    from fem_helmholtz_eqn_b200._lib import check, ptr, stream_ptr
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = fh._lib.require_cuda()
+    dev = torch.device("cuda", local_rank)
+
+    n, n_k = N_ELEM + 1, args.n_k
+    ks_global = np.linspace(K_MIN, K_MAX, n_k * world)
+    ks_h = ks_global[rank * n_k:(rank + 1) * n_k]
+    k2s_h = ks_h**2
+    ks_d = torch.from_numpy(ks_h).to(dev)
+    k2s_d = torch.from_numpy(k2s_h).to(dev)
+    bands = torch.empty((4, n_k, n), dtype=torch.complex128, device=dev)
+    U = torch.empty((n_k, n), dtype=torch.complex128, device=dev)
+    status = torch.zeros(n_k, dtype=torch.int32, device=dev)
+    prob = fem1d._problem(N_ELEM, 1.0 / N_ELEM, 0.0, "neumann", "sommerfeld", 1.0, 0.0, None)
+
+    def assemble():
+        check(lib.fh_assemble_1d_c128(C.byref(prob), ptr(ks_d), ptr(k2s_d), n_k, ptr(bands[0]), ptr(bands[1]),
+                                      ptr(bands[2]), ptr(bands[3]), stream_ptr()), "assemble")
+
+    def solve():
+        check(lib.fh_tridiag_solve_batched_c128(ptr(bands[0]), ptr(bands[1]), ptr(bands[2]), ptr(bands[3]),
+                                                ptr(U), n, n_k, ptr(status), None, 0, stream_ptr()), "solve")
+
+    def fused():
+        check(lib.fh_helmholtz1d_sweep_fused_c128(C.byref(prob), ptr(ks_d), ptr(k2s_d), n_k, ptr(U), ptr(status),
+                                                  None, 0, stream_ptr()), "fused")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        assemble()
+        solve()
+    barrier()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        t_begin.record()
+        for s in range(args.steps):
+            ev[s][0].record()
+            assemble()
+            ev[s][1].record()
+            solve()
+            ev[s][2].record()
+        t_end.record()
+        barrier()
+    total_ms = t_begin.elapsed_time(t_end)
+    asm_ms = [e[0].elapsed_time(e[1]) for e in ev]
+    sol_ms = [e[1].elapsed_time(e[2]) for e in ev]
+    assert int(status.abs().sum()) == 0, "solver flagged a breakdown"
+
+    # parity inside the bench: device-side backward error of what the timed steps produced
+    res = fh.tridiagonal_residual(bands[0], bands[1], bands[2], bands[3], U)
+    backward_max = float(res["backward"].max())
+
+    # fused variant (bands never stored), reported separately
+    for _ in range(2):
+        fused()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        fused()
+    f1.record()
+    barrier()
+    fused_ms = f0.elapsed_time(f1) / args.steps
+
+    # end-to-end through the public host-to-host API
+    e2e = None
+    if not args.no_e2e:
+        del bands
+        torch.cuda.empty_cache()
+        plan = fem1d.HostSweepPlan(N_ELEM, n_k)
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        fem1d.solve_helmholtz_sweep_host(N_ELEM, ks_h, plan=plan)  # warm-up (page-locks, first touch)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            _, U_host = fem1d.solve_helmholtz_sweep_host(N_ELEM, ks_h, plan=plan)
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        e2e = {"seconds": e2e_s, "h2d": plan.h2d_bytes, "d2h": plan.d2h_bytes, "steps": e2e_steps}
+
+    # max over ranks
+    vals = torch.tensor([total_ms, e2e["seconds"] if e2e else 0.0, fused_ms,
+                         statistics.mean(sol_ms), statistics.mean(asm_ms)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    total_ms, e2e_s, fused_ms, sol_mean, asm_mean = vals.tolist()
+
+    if rank == 0:
+        dof_rank = n_k * n
+        dof_all = dof_rank * world
+        ms_per_step = total_ms / args.steps
+        value = dof_all / (ms_per_step * 1e-3)
+        peak, peak_kind = measured_peak_gbs()
+        achieved = BYTES_SOLVE * dof_rank / (sol_mean * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["solve_bytes_per_launch"]
+        except Exception:
+            pass
+        out = {
+            "metric": METRIC, "value": value, "unit": "DOF/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "complex128", "data": "synthetic", "config": workload_config(world),
+            "solves_per_s": n_k * world / (ms_per_step * 1e-3),
+            "roofline": {"bound": "hbm", "kernel": "tridiag_batched_kernel<2, BandSource>",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured"
+                         else "fallback 6.65 TB/s (B200_PROFILING.md)",
+                         "algorithmic_bytes_per_launch": BYTES_SOLVE * dof_rank, "traffic": traffic,
+                         "launch_ms": sol_mean},
+            "stages": {"assembly_ms": asm_mean, "solve_ms": sol_mean,
+                       "assembly_gbs": BYTES_ASSEMBLY * dof_rank / (asm_mean * 1e-3) / 1e9,
+                       "assembly_frac": BYTES_ASSEMBLY * dof_rank / (asm_mean * 1e-3) / 1e9 / peak,
+                       "staged_gbs": (BYTES_ASSEMBLY + BYTES_SOLVE) * dof_rank / (ms_per_step * 1e-3) / 1e9,
+                       "staged_frac": (BYTES_ASSEMBLY + BYTES_SOLVE) * dof_rank / (ms_per_step * 1e-3) / 1e9 / peak},
+            "fused": {"ms_per_step": fused_ms, "value": dof_all / (fused_ms * 1e-3), "unit": "DOF/s",
+                      "bytes_per_dof": 16},
+            "parity": {"backward_error_max": backward_max, "bar": 1e-10},
+            "gpu_launches": 2 * args.steps,
+            "clocks": clocks.summary(),
+        }
+        if e2e:
+            out["e2e"] = {"value": dof_all / e2e_s, "unit": "DOF/s", "h2d_bytes_per_step": e2e["h2d"],
+                          "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": 1e3 * e2e_s, "steps": e2e["steps"],
+                          "api": "fem1d.solve_helmholtz_sweep_host (pinned H2D of k, k^2; D2H of every solution)"}
+        if world == 1 and not args.no_cpu:
+            ks_cpu = ks_h[[0, n_k // 2, n_k - 1]]
+            cpu_reference_step(ks_cpu[:1])  # warm the BLAS threads
+            t = cpu_reference_step(ks_cpu)
+            out["cpu_baseline"] = {
+                "value": len(ks_cpu) * n / t, "unit": "DOF/s", "cores": cpu_threads(), "kind": "port",
+                "sample": f"{len(ks_cpu)} of the {n_k} wavenumbers (k = first, middle, last) at N={N_ELEM}: the "
+                          f"reference's dense assembly + np.linalg.solve (oracle/ref1d.py), {t:.1f} s",
+                "banded_zgtsv_dof_per_s_1thread": cpu_banded_rate()}
+        print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n-k", dest="n_k", type=int, default=N_K_PER_GPU, help="wavenumbers per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

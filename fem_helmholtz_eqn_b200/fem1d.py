@@ -307,3 +307,78 @@ def analytical_solution(x, k):
     if isinstance(x, torch.Tensor):
         return -torch.exp(1j * k * x.to(torch.complex128))
     return -np.exp(1j * k * x)
+
+
+class HostSweepPlan:
+    """Reusable buffers for :func:`solve_helmholtz_sweep_host`: a pinned host array for the result, and two
+    sets of device buffers so that chunk i+1 is assembled+solved while chunk i is copied back.  (Pinning
+    gigabytes of host memory costs about a second, so a caller that sweeps repeatedly keeps the plan.)"""
+
+    def __init__(self, N, n_k, chunk=None):
+        _lib.require_cuda()
+        self.N, self.n, self.n_k = int(N), int(N) + 1, int(n_k)
+        if chunk is None:  # ~256 MB of solution per chunk keeps both the copy engine and the SMs busy
+            chunk = max(1, min(self.n_k, (256 << 20) // (16 * self.n)))
+        self.chunk = int(chunk)
+        dev = _lib.device()
+        self.U_host = torch.empty((self.n_k, self.n), dtype=torch.complex128).pin_memory()
+        self.k_host = torch.empty((2, self.n_k), dtype=torch.float64).pin_memory()
+        self.k_dev = torch.empty((2, self.n_k), dtype=torch.float64, device=dev)
+        self.bands = [torch.empty((4, self.chunk, self.n), dtype=torch.complex128, device=dev) for _ in range(2)]
+        self.U_dev = [torch.empty((self.chunk, self.n), dtype=torch.complex128, device=dev) for _ in range(2)]
+        self.status = torch.zeros(self.n_k, dtype=torch.int32, device=dev)
+        self.copy_stream = torch.cuda.Stream()
+        self.h2d_bytes = self.k_host.numel() * 8
+        self.d2h_bytes = self.U_host.numel() * 16 + self.n_k * 4
+
+
+def solve_helmholtz_sweep_host(N, ks, L=1.0, theta=0.0, *, plan=None, fused=False, check_singular=True,
+                               **bc):
+    """Host-to-host wavenumber sweep: ``ks`` (numpy / list) in, ``(nodes, U)`` out with ``U`` a numpy
+    complex128[n_k, N+1] array (a view of the plan's pinned buffer).  Per call: one pinned H2D copy of
+    (k, k**2), chunked assemble+solve on the compute stream, and D2H copies of the finished chunks on a
+    second stream, overlapped with the next chunk's kernels."""
+    lib = _lib.require_cuda()
+    h, nodes, _ = create_mesh(N, L)
+    ks_h, k2s_h, _ = _host_k_and_k2(ks)
+    n_k = len(ks_h)
+    if plan is None:
+        plan = HostSweepPlan(N, n_k)
+    assert plan.N == int(N) and plan.n_k == n_k, "plan was built for another sweep shape"
+    prob = _problem(N, h, theta, bc.get("bc_left", "neumann"), bc.get("bc_right", "sommerfeld"),
+                    bc.get("g_left", 1.0), bc.get("g_right", 0.0), None)
+    main = torch.cuda.current_stream()
+    plan.k_host[0].copy_(torch.from_numpy(ks_h))
+    plan.k_host[1].copy_(torch.from_numpy(k2s_h))
+    plan.k_dev.copy_(plan.k_host, non_blocking=True)
+    done = [None, None]
+    for c, lo in enumerate(range(0, n_k, plan.chunk)):
+        hi = min(n_k, lo + plan.chunk)
+        m, slot = hi - lo, c & 1
+        if done[slot] is not None:
+            main.wait_event(done[slot])  # the copy engine has drained this slot's previous chunk
+        ks_d, k2s_d = plan.k_dev[0, lo:hi], plan.k_dev[1, lo:hi]
+        U, st = plan.U_dev[slot][:m], plan.status[lo:hi]
+        if fused:
+            check(lib.fh_helmholtz1d_sweep_fused_c128(C.byref(prob), ptr(ks_d), ptr(k2s_d), m, ptr(U), ptr(st),
+                                                      None, 0, stream_ptr()), "fh_helmholtz1d_sweep_fused_c128")
+        else:
+            B = plan.bands[slot]
+            dl, d, du, b = (B[i, :m] for i in range(4))
+            check(lib.fh_assemble_1d_c128(C.byref(prob), ptr(ks_d), ptr(k2s_d), m, ptr(dl), ptr(d), ptr(du),
+                                          ptr(b), stream_ptr()), "fh_assemble_1d_c128")
+            check(lib.fh_tridiag_solve_batched_c128(ptr(dl), ptr(d), ptr(du), ptr(b), ptr(U), plan.n, m, ptr(st),
+                                                    None, 0, stream_ptr()), "fh_tridiag_solve_batched_c128")
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(plan.copy_stream):
+            plan.copy_stream.wait_event(ready)
+            plan.U_host[lo:hi].copy_(U, non_blocking=True)
+            done[slot] = torch.cuda.Event()
+            done[slot].record(plan.copy_stream)
+    main.wait_stream(plan.copy_stream)
+    status_host = plan.status.cpu()  # synchronises: everything above has finished
+    if check_singular and bool(torch.any(status_host != 0)):
+        bad = torch.nonzero(status_host).flatten()[:8].tolist()
+        raise np.linalg.LinAlgError(f"Singular matrix (zero pivot / non-finite solution) in systems {bad}")
+    return nodes, plan.U_host.numpy()
