@@ -53,6 +53,17 @@ _SIGNATURES = {
                                                   C.c_size_t, _P]),
     "fh_tridiag_solve_large_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "fh_tridiag_solve_large_c128": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P, _P, C.c_size_t, _P]),
+    "fh_helmholtz1d_solve_large_fused_c128": (C.c_int, [C.POINTER(Problem1d), C.c_double, C.c_double, _P, _P, _P,
+                                                        C.c_size_t, _P]),
+    "fh_spike_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "fh_spike_reduce_c128": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, _P, C.c_size_t, _P, _P]),
+    "fh_helmholtz1d_spike_reduce_c128": (C.c_int, [C.POINTER(Problem1d), C.c_double, C.c_double, C.c_int64,
+                                                   C.c_int64, _P, C.c_size_t, _P, _P]),
+    "fh_spike_solve_interface_c128": (C.c_int, [_P, C.c_int, _P, _P, _P]),
+    "fh_spike_backsub_c128": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, _P, C.c_size_t, _P, _P, _P,
+                                        _P]),
+    "fh_helmholtz1d_spike_backsub_c128": (C.c_int, [C.POINTER(Problem1d), C.c_double, C.c_double, C.c_int64,
+                                                    C.c_int64, _P, C.c_size_t, _P, _P, _P, _P]),
     "fh_tridiag_residual_c128": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, _P]),
 }
 

@@ -379,11 +379,23 @@ static int launch_batched(const Source &src, cplx *u, int64_t n, int64_t batch, 
 
 }  // namespace fh
 
-// from fh_tridiag_large.cu
 namespace fh {
+// from fh_tridiag_large.cu
 int solve_large(const cplx *dl, const cplx *d, const cplx *du, const cplx *b, cplx *u, int64_t n,
                 int32_t *status, void *workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t solve_large_workspace_bytes(int64_t n);
+
+int batched_solve_bands(const cplx *dl, const cplx *d, const cplx *du, const cplx *b, cplx *u, int64_t n,
+                        int64_t batch, int32_t *status, cudaStream_t stream) {
+    if (n > kBatchedMaxN) {
+        set_error("batched kernel handles n <= %lld", (long long)kBatchedMaxN);
+        return FH_E_UNSUPPORTED;
+    }
+    BandSource src;
+    src.dl = dl, src.d = d, src.du = du, src.b = b;
+    if (n <= kStageRows) return launch_batched<1>(src, u, n, batch, status, stream);
+    return launch_batched<2>(src, u, n, batch, status, stream);
+}
 }  // namespace fh
 
 extern "C" {
@@ -413,13 +425,9 @@ int fh_tridiag_solve_batched_c128(const fh_c128 *dl, const fh_c128 *d, const fh_
         }
         return FH_OK;
     }
-    BandSource src;
-    src.dl = reinterpret_cast<const cplx *>(dl);
-    src.d = reinterpret_cast<const cplx *>(d);
-    src.du = reinterpret_cast<const cplx *>(du);
-    src.b = reinterpret_cast<const cplx *>(b);
-    if (n <= kStageRows) return launch_batched<1>(src, reinterpret_cast<cplx *>(u), n, batch, status, st);
-    return launch_batched<2>(src, reinterpret_cast<cplx *>(u), n, batch, status, st);
+    return batched_solve_bands(reinterpret_cast<const cplx *>(dl), reinterpret_cast<const cplx *>(d),
+                               reinterpret_cast<const cplx *>(du), reinterpret_cast<const cplx *>(b),
+                               reinterpret_cast<cplx *>(u), n, batch, status, st);
 }
 
 int fh_helmholtz1d_sweep_fused_c128(const fh_problem1d *prob_host, const double *ks, const double *k2s,

@@ -282,11 +282,19 @@ def solve_helmholtz_sweep(N, ks, L=1.0, theta=0.0, *, bc_left="neumann", bc_righ
     else:
         ks_d, k2s_d = _lib.as_device(ks_h, torch.float64), _lib.as_device(k2s_h, torch.float64)
         U = out if out is not None else torch.empty((n_k, n), dtype=torch.complex128, device=dev)
-        status = torch.empty(n_k, dtype=torch.int32, device=dev)
+        status = torch.zeros(n_k, dtype=torch.int32, device=dev)
         prob = _problem(N, h, theta, bc_left, bc_right, g_left, g_right, nodes_d)
-        check(lib.fh_helmholtz1d_sweep_fused_c128(C.byref(prob), ptr(ks_d), ptr(k2s_d), n_k, ptr(U),
-                                                  ptr(status), None, 0, stream_ptr()),
-              "fh_helmholtz1d_sweep_fused_c128")
+        if n <= lib.fh_tridiag_batched_max_n():
+            check(lib.fh_helmholtz1d_sweep_fused_c128(C.byref(prob), ptr(ks_d), ptr(k2s_d), n_k, ptr(U),
+                                                      ptr(status), None, 0, stream_ptr()),
+                  "fh_helmholtz1d_sweep_fused_c128")
+        else:  # long meshes: recursive partition with generated level-0 rows, one wavenumber at a time
+            ws_bytes = lib.fh_tridiag_solve_large_workspace_bytes(n)
+            ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+            for i in range(n_k):
+                check(lib.fh_helmholtz1d_solve_large_fused_c128(
+                    C.byref(prob), float(ks_h[i]), float(k2s_h[i]), ptr(U[i]), ptr(status[i:i + 1]), ptr(ws),
+                    ws_bytes, stream_ptr()), "fh_helmholtz1d_solve_large_fused_c128")
     if check_singular:
         _raise_if_singular(status)
     return (nodes, U, status) if return_status else (nodes, U)

@@ -104,12 +104,44 @@ FH_API int fh_helmholtz1d_sweep_fused_c128(const fh_problem1d *prob_host, const 
                                     size_t workspace_bytes, fh_stream_t stream);
 
 /* ---- one very large system (single mesh of up to 2^31-2 rows per GPU): recursive partition ------
- * levels: each level turns chunks of 16 rows into one interface row; the coarsest level is solved by
- * the batched kernel; back-substitution re-reads the bands (2 passes over the data). */
+ * every level turns each chunk of 16 rows into 2 interface rows (8x smaller system); the coarsest level
+ * (<= 4112 rows) is solved by the batched kernel; back-substitution re-reads the bands (2 passes). */
 FH_API size_t fh_tridiag_solve_large_workspace_bytes(int64_t n);
 FH_API int fh_tridiag_solve_large_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c128 *du,
                                 const fh_c128 *b, fh_c128 *u, int64_t n, int32_t *status,
                                 void *workspace, size_t workspace_bytes, fh_stream_t stream);
+
+/* Same solver with level-0 rows generated from the Helmholtz problem instead of read (bands never stored). */
+FH_API int fh_helmholtz1d_solve_large_fused_c128(const fh_problem1d *prob_host, double k, double k2, fh_c128 *u,
+                                          int32_t *status, void *workspace, size_t workspace_bytes,
+                                          fh_stream_t stream);
+
+/* ---- multi-GPU SPIKE-style partitioned solve (single mesh split into contiguous slabs, one per rank) ------
+ * Per rank:  1. *_spike_reduce   : slab [row_begin, row_begin+n_rows) -> its 2 interface rows,
+ *                                  iface8 = device complex128[4][2] = (dl, d, du, b) x (first row, last row);
+ *            2. all-gather iface8 over the ranks (NCCL, 128 B per rank) -> complex128[P][4][2];
+ *            3. fh_spike_solve_interface_c128 : every rank solves the 2P-row interface system redundantly,
+ *                                  x_iface = complex128[2P] (rank r owns entries 2r, 2r+1);
+ *            4. *_spike_backsub  : slab solution from its two interface values (x_first_last = &x_iface[2r]).
+ * open_first / open_last: the slab's first / last row keeps its coupling to the neighbouring rank.
+ * The workspace (fh_spike_workspace_bytes) must be the same, untouched buffer for steps 1 and 4. */
+FH_API size_t fh_spike_workspace_bytes(int64_t n_rows);
+FH_API int fh_spike_reduce_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c128 *du, const fh_c128 *b,
+                         int64_t n_rows, int open_first, int open_last, void *workspace,
+                         size_t workspace_bytes, fh_c128 *iface8, fh_stream_t stream);
+FH_API int fh_helmholtz1d_spike_reduce_c128(const fh_problem1d *prob_host, double k, double k2, int64_t row_begin,
+                                     int64_t n_rows, void *workspace, size_t workspace_bytes, fh_c128 *iface8,
+                                     fh_stream_t stream);
+FH_API int fh_spike_solve_interface_c128(const fh_c128 *iface_all, int n_ranks, fh_c128 *x_iface, int32_t *status,
+                                  fh_stream_t stream);
+FH_API int fh_spike_backsub_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c128 *du, const fh_c128 *b,
+                          int64_t n_rows, int open_first, int open_last, void *workspace,
+                          size_t workspace_bytes, const fh_c128 *x_first_last, fh_c128 *u, int32_t *status,
+                          fh_stream_t stream);
+FH_API int fh_helmholtz1d_spike_backsub_c128(const fh_problem1d *prob_host, double k, double k2, int64_t row_begin,
+                                      int64_t n_rows, void *workspace, size_t workspace_bytes,
+                                      const fh_c128 *x_first_last, fh_c128 *u, int32_t *status,
+                                      fh_stream_t stream);
 
 /* ---- residual / parity metrics on device -------------------------------------------------------
  * out[s] = { ||b - A u||_2^2, ||u||_2^2, ||b||_2^2, ||A||_inf } for each system s (device fp64[batch][4]). */

@@ -1,0 +1,187 @@
+"""GPU parity tests of the large-system solver (recursive partition) and the per-rank SPIKE pieces, all
+through the C ABI.  The ranks of the multi-GPU path are emulated one after the other on a single GPU (the
+collective itself is covered by tests/test_distributed_cpu.py); with >= 2 GPUs the NCCL path runs for real
+in test_nccl_partitioned (skipped otherwise)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import banded1d
+
+pytestmark = pytest.mark.gpu
+
+fh = pytest.importorskip("fem_helmholtz_eqn_b200")
+from fem_helmholtz_eqn_b200 import distributed as fh_dist  # noqa: E402
+from fem_helmholtz_eqn_b200._lib import check, ptr, stream_ptr  # noqa: E402
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _random_system(n, seed):
+    rng = np.random.default_rng(seed)
+    dl = rng.normal(size=n) + 1j * rng.normal(size=n)
+    du = rng.normal(size=n) + 1j * rng.normal(size=n)
+    d = 4.0 + rng.normal(size=n) + 1j * rng.normal(size=n)
+    b = rng.normal(size=n) + 1j * rng.normal(size=n)
+    dl[0] = 0.0
+    du[-1] = 0.0
+    return dl, d, du, b
+
+
+@pytest.mark.parametrize("n", [4113, 4129, 5000, 16385, 65537, 131089, 1_000_001, 1_048_577 + 1024])
+def test_large_solver_random_systems(n):
+    """Sizes straddling the tiling rule: one row into a new chunk (4113 = 257*16+1), one row into a new
+    tile (1024*k + 1), several levels."""
+    dl, d, du, b = _random_system(n, n)
+    u, status = fh.solve_tridiagonal(dl, d, du, b)
+    assert int(status.abs().sum()) == 0
+    u = _np(u)[0]
+    ref = banded1d.solve_bands(dl, d, du, b)
+    assert rel_err(u, ref) < 1e-13
+    assert banded1d.residual_metrics(dl, d, du, b, u)[0] < 1e-15
+
+
+def test_large_solver_batch_of_long_systems():
+    n, batch = 6000, 3
+    sys_ = [_random_system(n, s) for s in range(batch)]
+    dl, d, du, b = (np.stack([s[i] for s in sys_]) for i in range(4))
+    u, status = fh.solve_tridiagonal(dl, d, du, b)
+    for i in range(batch):
+        assert rel_err(_np(u)[i], banded1d.solve_bands(*sys_[i])) < 1e-13
+
+
+@pytest.mark.parametrize("N,k", [(16384, 1000.0), (1_000_000, 10.0), (1_000_000, 1000.0)])
+def test_helmholtz_large_mesh_staged_and_fused(N, k):
+    """BASELINE configs 2 and 5 (N = 1e6; k = 1000 with the Robin row): staged (bands stored) and fused
+    (rows generated) agree bit for bit; checked against LAPACK zgtsv on the oracle's bands, the exact
+    discrete solution, and by backward error."""
+    nodes, u = fh.solve_helmholtz_fem(N, k)
+    nodes_f, u_f = fh.solve_helmholtz_fem(N, k, fused=True)
+    assert np.array_equal(u, u_f)
+    bands = banded1d.assemble_bands(N, k, 1.0 / N)
+    be, _ = banded1d.residual_metrics(*bands, u)
+    assert be < 1e-14, be  # bar 1e-10; LAPACK reaches ~2e-17
+    ref = banded1d.solve_bands(*bands)
+    ex = banded1d.discrete_exact(N, k)
+    # forward error is conditioning-limited at this size (zgtsv itself is 5e-6 from exact at k=10):
+    # require we are no further from exact than 10x LAPACK
+    assert rel_err(u, ex) < max(1e-10, 10 * rel_err(ref, ex)), (rel_err(u, ex), rel_err(ref, ex))
+
+
+def _emulated_ranks_fused(N, k, world):
+    """The per-rank sequence of distributed.solve_partitioned, ranks run one after the other on one GPU."""
+    n = N + 1
+    ops = [fh_dist.CudaSlabOps(N, k) for _ in range(world)]
+    ifaces = [ops[r].reduce(*fh_dist.slab_range(n, world, r)) for r in range(world)]
+    iface_all = torch.stack(ifaces).contiguous()
+    parts = []
+    for r in range(world):
+        x = ops[r].solve_interface(iface_all)
+        parts.append(ops[r].backsub(x[2 * r:2 * r + 2]))
+        assert not ops[r].singular()
+    return _np(torch.cat(parts))
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+def test_spike_pieces_fused_emulated_ranks(world):
+    for N, k in ((4096 * 8 + 17, 250.0), (1_000_000, 1000.0)):
+        u = _emulated_ranks_fused(N, k, world)
+        bands = banded1d.assemble_bands(N, k, 1.0 / N)
+        assert banded1d.residual_metrics(*bands, u)[0] < 1e-14
+        ref = banded1d.solve_bands(*bands)
+        ex = banded1d.discrete_exact(N, k)
+        assert rel_err(u, ex) < max(1e-10, 10 * rel_err(ref, ex))
+
+
+@pytest.mark.parametrize("world", [2, 5])
+def test_spike_pieces_on_stored_bands(world):
+    lib = fh._lib.require_cuda()
+    n = 50_001
+    dl, d, du, b = _random_system(n, 7)
+    dev = [fh._lib.as_device(x, torch.complex128) for x in (dl, d, du, b)]
+    ifaces, wss, rngs = [], [], []
+    for r in range(world):
+        s, e = fh_dist.slab_range(n, world, r)
+        ws_bytes = lib.fh_spike_workspace_bytes(e - s)
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device="cuda")
+        iface = torch.empty((4, 2), dtype=torch.complex128, device="cuda")
+        check(lib.fh_spike_reduce_c128(*(ptr(x[s:e]) for x in dev), e - s, int(r > 0), int(r < world - 1), ptr(ws),
+                                       ws_bytes, ptr(iface), stream_ptr()), "fh_spike_reduce_c128")
+        ifaces.append(iface), wss.append((ws, ws_bytes)), rngs.append((s, e))
+    iface_all = torch.stack(ifaces).contiguous()
+    x = torch.empty(2 * world, dtype=torch.complex128, device="cuda")
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    check(lib.fh_spike_solve_interface_c128(ptr(iface_all), world, ptr(x), ptr(status), stream_ptr()), "iface")
+    u = torch.empty(n, dtype=torch.complex128, device="cuda")
+    for r, (s, e) in enumerate(rngs):
+        check(lib.fh_spike_backsub_c128(*(ptr(t[s:e]) for t in dev), e - s, int(r > 0), int(r < world - 1),
+                                        ptr(wss[r][0]), wss[r][1], ptr(x[2 * r:2 * r + 2]), ptr(u[s:e]), ptr(status),
+                                        stream_ptr()), "fh_spike_backsub_c128")
+    assert int(status[0]) == 0
+    assert rel_err(_np(u), banded1d.solve_bands(dl, d, du, b)) < 1e-13
+
+
+def test_partitioned_entry_point_single_process():
+    N, k = 200_000, 321.0
+    begin, end, u = fh_dist.solve_partitioned(N, k)
+    assert (begin, end) == (0, N + 1)
+    bands = banded1d.assemble_bands(N, k, 1.0 / N)
+    assert banded1d.residual_metrics(*bands, _np(u))[0] < 1e-14
+
+
+def test_config4_full_size_on_one_gpu():
+    """BASELINE config 4's mesh (N = 2^27) split into 8 slabs, ranks emulated on one GPU: the exact discrete
+    solution is a pure phase, so |u_j| = 1 everywhere, and the slab seams must match it."""
+    N, k, world = 2**27, 1000.0, 8
+    n = N + 1
+    h = 1.0 / N
+    theta = 2.0 * np.arctan(k * h / 2.0)
+    ops = [fh_dist.CudaSlabOps(N, k) for _ in range(world)]
+    iface_all = torch.stack([ops[r].reduce(*fh_dist.slab_range(n, world, r)) for r in range(world)]).contiguous()
+    worst = 0.0
+    for r in range(world):
+        s, e = fh_dist.slab_range(n, world, r)
+        x = ops[r].solve_interface(iface_all)
+        u = ops[r].backsub(x[2 * r:2 * r + 2])
+        assert not ops[r].singular()
+        assert float((u.abs() - 1.0).abs().max()) < 1e-5
+        idx = torch.tensor([0, (e - s) // 2, e - s - 1], device=u.device)
+        exact = -np.exp(1j * (s + _np(idx)) * theta)
+        worst = max(worst, float(np.abs(_np(u[idx]) - exact).max()))
+        del u
+    # cond(A)*eps at N = 2^27, kh = 7.5e-6 is ~1e-4: the forward error is reported, and gated
+    # only loosely; the tight gate for this size is the residual, checked slab by slab in the bench
+    assert worst < 1e-2, worst
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_nccl_partitioned_two_gpus(tmp_path):
+    import subprocess
+    import sys
+    script = tmp_path / "run.py"
+    script.write_text(
+        "import os, sys, numpy as np, torch, torch.distributed as dist\n"
+        "sys.path.insert(0, os.environ['FH_ROOT'])\n"
+        "from fem_helmholtz_eqn_b200 import distributed as D\n"
+        "from oracle import banded1d\n"
+        "r = int(os.environ['LOCAL_RANK']); torch.cuda.set_device(r)\n"
+        "dist.init_process_group('nccl', device_id=torch.device('cuda', r))\n"
+        "N, k = 1_000_000, 1000.0\n"
+        "_, _, u = D.solve_partitioned(N, k, gather=True)\n"
+        "bands = banded1d.assemble_bands(N, k, 1.0 / N)\n"
+        "be = banded1d.residual_metrics(*bands, u.cpu().numpy())[0]\n"
+        "assert be < 1e-14, be\n"
+        "lo, hi, U = D.sweep_sharded(4096, np.linspace(1, 1000, 64))\n"
+        "assert U.shape == (32, 4097)\n"
+        "dist.destroy_process_group(); print('rank', r, 'ok', be)\n")
+    import os
+    env = dict(os.environ, FH_ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29731", str(script)], env=env,
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
