@@ -18,20 +18,76 @@ __global__ void __launch_bounds__(kAsmThreads)
 assemble1d_kernel(Problem1d p, const double *__restrict__ ks, const double *__restrict__ k2s,
                   int64_t n_k, int64_t k_per_block, cplx *__restrict__ dl, cplx *__restrict__ d,
                   cplx *__restrict__ du, cplx *__restrict__ b) {
+    // The wavenumbers of the block's slab are staged in shared memory 256 at a time, so the store loop
+    // has no global-load latency on its critical path (v1 waited on two __ldg per row: 62% of HBM peak).
+    __shared__ double sk[2][kAsmThreads];
     const int64_t n = p.n_elem + 1;
     const int64_t j = static_cast<int64_t>(blockIdx.x) * kAsmThreads + threadIdx.x;
-    if (j >= n) return;
-    const RowGeom g = row_geom(p, j);
+    const bool live = j < n;
+    RowGeom g = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (live) g = row_geom(p, j);
     const int64_t k_begin = static_cast<int64_t>(blockIdx.y) * k_per_block;
     const int64_t k_end = min(n_k, k_begin + k_per_block);
-    for (int64_t s = k_begin; s < k_end; ++s) {
-        cplx vl, vd, vu, vb;
-        row_values(p, g, j, __ldg(ks + s), __ldg(k2s + s), vl, vd, vu, vb);
-        const int64_t o = s * n + j;
+    for (int64_t base = k_begin; base < k_end; base += kAsmThreads) {
+        const int cnt = (int)min((int64_t)kAsmThreads, k_end - base);
+        __syncthreads();
+        if (threadIdx.x < cnt) {
+            sk[0][threadIdx.x] = __ldg(ks + base + threadIdx.x);
+            sk[1][threadIdx.x] = __ldg(k2s + base + threadIdx.x);
+        }
+        __syncthreads();
+        if (!live) continue;
+        int64_t o = base * n + j;
+#pragma unroll 4
+        for (int i = 0; i < cnt; ++i, o += n) {
+            cplx vl, vd, vu, vb;
+            row_values(p, g, j, sk[0][i], sk[1][i], vl, vd, vu, vb);
+            stg_stream(dl + o, vl);
+            stg_stream(d + o, vd);
+            stg_stream(du + o, vu);
+            stg_stream(b + o, vb);
+        }
+    }
+}
+
+// Scalar-h fast path (the reference's only mode, nb:158: one element matrix for the whole mesh).  All
+// interior rows of a system hold the same three numbers, so the kernel is a structured fill: every CTA owns
+// a contiguous slab of wavenumbers and streams the four arrays front to back -- four long sequential
+// write streams per CTA instead of 4 KB pieces 64 KB apart (which held the row-tiled kernel to 4.2 TB/s,
+// against 7.4 TB/s for a plain fill on the same GPU; tools/write_bw_probe.py).
+__global__ void __launch_bounds__(kAsmThreads)
+assemble1d_scalar_kernel(Problem1d p, const double *__restrict__ ks, const double *__restrict__ k2s,
+                         int64_t n_k, int64_t k_per_block, cplx *__restrict__ dl, cplx *__restrict__ d,
+                         cplx *__restrict__ du, cplx *__restrict__ b) {
+    const int64_t n = p.n_elem + 1;
+    const int64_t k_begin = static_cast<int64_t>(blockIdx.x) * k_per_block;
+    const int64_t k_end = min(n_k, k_begin + k_per_block);
+    if (k_begin >= k_end) return;
+    const RowGeom g_first = row_geom(p, 0);
+    const RowGeom g_mid = row_geom(p, p.n_elem > 1 ? 1 : 0);
+    const RowGeom g_last = row_geom(p, p.n_elem);
+    // flat position inside the slab, advanced by blockDim per step; (s, j) follow incrementally
+    int64_t s = k_begin + threadIdx.x / n;
+    int64_t j = threadIdx.x % n;
+    int64_t o = k_begin * n + threadIdx.x;
+    const int64_t o_end = k_end * n;
+    int64_t s_cached = -1;
+    cplx il = czero(), id = czero(), iu = czero(), ib = czero();  // interior row of the cached wavenumber
+    double k = 0.0, k2 = 0.0;
+    for (; o < o_end; o += kAsmThreads) {
+        if (s != s_cached) {
+            k = __ldg(ks + s), k2 = __ldg(k2s + s);
+            row_values(p, g_mid, 1, k, k2, il, id, iu, ib);
+            s_cached = s;
+        }
+        cplx vl = il, vd = id, vu = iu, vb = ib;
+        if (j == 0 || j == p.n_elem) row_values(p, j == 0 ? g_first : g_last, j, k, k2, vl, vd, vu, vb);
         stg_stream(dl + o, vl);
         stg_stream(d + o, vd);
         stg_stream(du + o, vu);
         stg_stream(b + o, vb);
+        j += kAsmThreads;
+        while (j >= n) j -= n, ++s;
     }
 }
 
@@ -94,6 +150,18 @@ int fh_assemble_1d_c128(const fh_problem1d *prob_host, const double *ks, const d
     if (n_k == 0) return FH_OK;
     FH_REQUIRE(ks && k2s && dl && d && du && b, "NULL device pointer");
     const int64_t n = p.n_elem + 1;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (p.h_mode == FH_H_SCALAR && p.n_elem >= 2) {  // structured-fill fast path
+        int64_t slabs = 8ll * fh::sm_count();
+        if (slabs > n_k) slabs = n_k;
+        const int64_t per = (n_k + slabs - 1) / slabs;
+        slabs = (n_k + per - 1) / per;
+        fh::assemble1d_scalar_kernel<<<(unsigned)slabs, fh::kAsmThreads, 0, st>>>(
+            p, ks, k2s, n_k, per, reinterpret_cast<fh::cplx *>(dl), reinterpret_cast<fh::cplx *>(d),
+            reinterpret_cast<fh::cplx *>(du), reinterpret_cast<fh::cplx *>(b));
+        FH_LAUNCH_CHECK("assemble1d_scalar_kernel");
+        return FH_OK;
+    }
     const int64_t row_blocks = (n + fh::kAsmThreads - 1) / fh::kAsmThreads;
     FH_REQUIRE(row_blocks < (1ll << 31), "mesh too large for one launch");
     // Split the k range so that the grid covers every SM several times even for short meshes,
@@ -106,7 +174,7 @@ int fh_assemble_1d_c128(const fh_problem1d *prob_host, const double *ks, const d
     const int64_t k_per_block = (n_k + k_splits - 1) / k_splits;
     k_splits = (n_k + k_per_block - 1) / k_per_block;
     dim3 grid(static_cast<unsigned>(row_blocks), static_cast<unsigned>(k_splits));
-    fh::assemble1d_kernel<<<grid, fh::kAsmThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+    fh::assemble1d_kernel<<<grid, fh::kAsmThreads, 0, st>>>(
         p, ks, k2s, n_k, k_per_block, reinterpret_cast<fh::cplx *>(dl), reinterpret_cast<fh::cplx *>(d),
         reinterpret_cast<fh::cplx *>(du), reinterpret_cast<fh::cplx *>(b));
     FH_LAUNCH_CHECK("assemble1d_kernel");
