@@ -64,6 +64,20 @@ _SIGNATURES = {
                                         _P]),
     "fh_helmholtz1d_spike_backsub_c128": (C.c_int, [C.POINTER(Problem1d), C.c_double, C.c_double, C.c_int64,
                                                     C.c_int64, _P, C.c_size_t, _P, _P, _P, _P]),
+    "fh_q4_element_matrices_c128": (C.c_int, [_P, _P, C.c_int64, C.c_double, _P, _P, _P, _P]),
+    "fh_q4_edge_geometry": (C.c_int, [_P, _P, _P, C.c_int64, C.c_double, _P, _P, _P]),
+    "fh_q4_robin_edge_matrices_c128": (C.c_int, [_P, _P, C.c_int64, C.c_double, C.c_double, _P, _P, C.c_int, _P, _P]),
+    "fh_q4_neumann_edge_vectors_c128": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, C.c_int, _P, _P]),
+    "fh_q4_scatter_keys": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int, _P, _P]),
+    "fh_sorted_segments_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "fh_sorted_segments": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "fh_csr_from_keys": (C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P, _P]),
+    "fh_segment_sum_c128": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int64, _P, _P]),
+    "fh_q4_boundary_flags": (C.c_int, [_P, C.c_int64, C.c_double, C.c_double, C.c_int, _P, _P]),
+    "fh_csr_apply_dirichlet_c128": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_double, C.c_double,
+                                              C.c_double, C.c_double, _P]),
+    "fh_csr_to_dense_c128": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P]),
+    "fh_dense_lu_solve_c128": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P]),
     "fh_tridiag_residual_c128": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, _P]),
 }
 

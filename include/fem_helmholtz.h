@@ -149,6 +149,62 @@ FH_API int fh_tridiag_residual_c128(const fh_c128 *dl, const fh_c128 *d, const f
                              const fh_c128 *u, int64_t n, int64_t batch, double *out4,
                              fh_stream_t stream);
 
+/* =====================================================================================================
+ * 2D: bilinear quads on the annulus (src/solvers/base.py and the four fem2d*.py classes)
+ * nodes: device fp64[n_nodes][2]; elements: device int32[n_elements][4] (0-based, counter-clockwise).
+ * Gauss points / weights are HOST arrays taken from scipy.special.roots_legendre by the caller, so the
+ * kernels use the reference's exact constants.
+ * ===================================================================================================== */
+
+/* base.py:65-117 get_element_matrices for every element: Ke = complex128[n_elements][4][4]. */
+FH_API int fh_q4_element_matrices_c128(const double *nodes, const int32_t *elements, int64_t n_elements,
+                                double k_squared, const double *gauss_pts_host, const double *gauss_wts_host,
+                                fh_c128 *Ke, fh_stream_t stream);
+/* For each listed element: which of its edges (0,1) (1,2) (2,3) (3,0) have both ends on the circle of `radius`
+ * (np.isclose, fem2d.py:47-52) and the edge lengths.  on_edge: uint8[n_ids][4]; length: fp64[n_ids][4]. */
+FH_API int fh_q4_edge_geometry(const double *nodes, const int32_t *elements, const int32_t *elem_ids, int64_t n_ids,
+                        double radius, uint8_t *on_edge, double *length, fh_stream_t stream);
+/* fem2d.py:29-80 / fem2d_dirichlet_sommerfeld.py:26-78: Se = complex128[n_ids][4][4], coef = get_abc_coeff(). */
+FH_API int fh_q4_robin_edge_matrices_c128(const uint8_t *on_edge, const double *length, int64_t n_ids, double coef_re,
+                                   double coef_im, const double *gauss_pts_host, const double *gauss_wts_host,
+                                   int n_gauss, fh_c128 *Se, fh_stream_t stream);
+/* fem2d.py:82-137: Ne = complex128[n_ids][4]; g_vals = complex128[n_ids][4][n_gauss] holds the incident normal
+ * derivative (fem2d.py:12-27, Bessel functions, evaluated by the caller) at the edge Gauss points. */
+FH_API int fh_q4_neumann_edge_vectors_c128(const uint8_t *on_edge, const double *length, int64_t n_ids,
+                                    const fh_c128 *g_vals, const double *gauss_pts_host,
+                                    const double *gauss_wts_host, int n_gauss, fh_c128 *Ne, fh_stream_t stream);
+
+/* Deterministic scatter (the `+=` loops of *.assemble(), fem2d.py:139-171): keys of every contribution
+ * (matrix: 16 per element, key = row * n_nodes + col; vector: 4 per element, key = node), a stable sort that
+ * keeps element order inside equal keys, then one ordered sum per unique key. */
+FH_API int fh_q4_scatter_keys(const int32_t *elements, const int32_t *elem_ids /* NULL = all */, int64_t count,
+                       int64_t n_nodes, int matrix, int64_t *keys, fh_stream_t stream);
+FH_API size_t fh_sorted_segments_workspace_bytes(int64_t n_entries);
+FH_API int fh_sorted_segments(const int64_t *keys, int64_t n_entries, int32_t *perm, int64_t *ukeys, int64_t *seg,
+                       int64_t *n_unique_dev, void *workspace, size_t workspace_bytes, fh_stream_t stream);
+FH_API int fh_csr_from_keys(const int64_t *ukeys, const int64_t *n_unique_dev, int64_t n_rows, int64_t n_cols,
+                     int64_t *rowptr, int32_t *colidx, fh_stream_t stream);
+/* out[s] = (ordered sum of contributions with id < split) + (ordered sum of the rest): K += S, F += N. */
+FH_API int fh_segment_sum_c128(const fh_c128 *contrib, const int32_t *perm, const int64_t *seg,
+                        const int64_t *n_seg_dev, int64_t n_seg_max, int64_t split, fh_c128 *out,
+                        fh_stream_t stream);
+
+/* apply_boundary_conditions (fem2d_dirichlet.py:11-29 etc.): flags[i] |= bit where |r_i - radius| < tol;
+ * then row replacement A[row]=0, A[row,row]=1, F[row]=g for rows whose flag intersects `mask`
+ * (bit 1 = inner circle, bit 2 = outer circle). */
+FH_API int fh_q4_boundary_flags(const double *nodes, int64_t n_nodes, double radius, double tol, int bit, uint8_t *flags,
+                         fh_stream_t stream);
+FH_API int fh_csr_apply_dirichlet_c128(const int64_t *rowptr, const int32_t *colidx, fh_c128 *vals, fh_c128 *F,
+                                const uint8_t *flags, int64_t n, int mask, double g_inner_re, double g_inner_im,
+                                double g_outer_re, double g_outer_im, fh_stream_t stream);
+
+/* *.solve(): np.linalg.solve(K, F) (fem2d.py:176) -> dense LU with partial pivoting on the device.
+ * A (n x n, row-major) and b are overwritten; piv: int32[n]; status: int32[1], non-zero = singular. */
+FH_API int fh_csr_to_dense_c128(const int64_t *rowptr, const int32_t *colidx, const fh_c128 *vals, int64_t n,
+                         fh_c128 *A, fh_stream_t stream);
+FH_API int fh_dense_lu_solve_c128(fh_c128 *A, fh_c128 *b, fh_c128 *x, int64_t n, int32_t *piv, int32_t *status,
+                           fh_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -91,3 +91,24 @@ def test_kernel_algorithm_model_matches_lapack():
         bands = banded1d.assemble_bands(N, k, 1.0 / N)
         be, _ = banded1d.residual_metrics(*bands, solve(*bands))
         assert be < 1e-14
+
+
+def test_2d_host_objects_match_reference(golden2d):
+    """Mesh stand-in, boundary lists and ABC coefficients are host logic: check them against the golden file."""
+    from fem_helmholtz_eqn_b200.helmholtz import HelmHoltz, structured_annulus
+    g = golden2d
+    for mname, (n_r, n_t) in (("m0", (3, 12)), ("m1", (6, 24))):
+        ri, ro = g[f"{mname}_radii"]
+        nodes, elements = structured_annulus(n_r, n_t, ri, ro)
+        assert np.array_equal(nodes, g[f"{mname}_nodes"]) and np.array_equal(elements, g[f"{mname}_elements"])
+        eqn = HelmHoltz(inner_radius=float(ri), outer_radius=float(ro), n_theta=n_t, n_r=n_r, mesher="structured")
+        assert list(eqn.inner_boundary_element_indices) == g[f"{mname}_inner_el"].tolist()
+        assert list(eqn.outer_boundary_element_indices) == g[f"{mname}_outer_el"].tolist()
+        for order in range(4):
+            assert eqn.get_abc_coeff(5.0, order) == g[f"{mname}_abc{order}"]
+        with pytest.raises(ValueError):
+            eqn.get_abc_coeff(5.0, 4)
+    from fem_helmholtz_eqn_b200.utils import get_solver, solvers
+    assert list(g["solver_names"]) == solvers
+    with pytest.raises(AssertionError):
+        get_solver("nope", eqn)
