@@ -226,8 +226,10 @@ def run_gpu(args):
     for _ in range(args.warmup):
         assemble()
         solve()
+        fem1d.refine_flagged(bands[0], bands[1], bands[2], bands[3], U, status)
     barrier()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    refined = []
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
         t_begin.record()
@@ -237,12 +239,16 @@ def run_gpu(args):
             ev[s][1].record()
             solve()
             ev[s][2].record()
+            # systems whose unpivoted elimination met a small pivot get one refinement step (part of the step)
+            refined.append(fem1d.refine_flagged(bands[0], bands[1], bands[2], bands[3], U, status))
+            ev[s][3].record()
         t_end.record()
         barrier()
     total_ms = t_begin.elapsed_time(t_end)
     asm_ms = [e[0].elapsed_time(e[1]) for e in ev]
     sol_ms = [e[1].elapsed_time(e[2]) for e in ev]
-    assert int(status.abs().sum()) == 0, "solver flagged a breakdown"
+    ref_ms = [e[2].elapsed_time(e[3]) for e in ev]
+    assert int((status & 1).sum()) == 0, "solver flagged a breakdown"
 
     # parity inside the bench: device-side backward error of what the timed steps produced
     res = fh.tridiagonal_residual(bands[0], bands[1], bands[2], bands[3], U)
@@ -306,7 +312,8 @@ def run_gpu(args):
                          else "fallback 6.65 TB/s (B200_PROFILING.md)",
                          "algorithmic_bytes_per_launch": BYTES_SOLVE * dof_rank, "traffic": traffic,
                          "launch_ms": sol_mean},
-            "stages": {"assembly_ms": asm_mean, "solve_ms": sol_mean,
+            "stages": {"assembly_ms": asm_mean, "solve_ms": sol_mean, "refine_ms": statistics.mean(ref_ms),
+                       "refined_systems_per_step": statistics.mean(refined),
                        "assembly_gbs": BYTES_ASSEMBLY * dof_rank / (asm_mean * 1e-3) / 1e9,
                        "assembly_frac": BYTES_ASSEMBLY * dof_rank / (asm_mean * 1e-3) / 1e9 / peak,
                        "staged_gbs": (BYTES_ASSEMBLY + BYTES_SOLVE) * dof_rank / (ms_per_step * 1e-3) / 1e9,
@@ -314,7 +321,7 @@ def run_gpu(args):
             "fused": {"ms_per_step": fused_ms, "value": dof_all / (fused_ms * 1e-3), "unit": "DOF/s",
                       "bytes_per_dof": 16},
             "parity": {"backward_error_max": backward_max, "bar": 1e-10},
-            "gpu_launches": 2 * args.steps,
+            "gpu_launches": sum(2 + (2 if r else 0) for r in refined),
             "clocks": clocks.summary(),
         }
         if e2e:

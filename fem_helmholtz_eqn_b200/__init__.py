@@ -9,7 +9,7 @@ All numerical work happens in hand-written CUDA kernels reached through the C AB
 """
 from . import _lib  # noqa: F401
 from .fem1d import (TridiagonalSystem, analytical_solution, assemble_bands, assembly,  # noqa: F401
-                    boundary_matrices, create_mesh, element_matrices, gauss_point, gauss_weight,
+                    boundary_matrices, compute_L2_error, convergence_test, create_mesh, element_matrices, gauss_point, gauss_weight,
                     shape_functions, solve_helmholtz_fem, solve_helmholtz_sweep, solve_tridiagonal,
                     tridiagonal_residual)
 

@@ -60,7 +60,39 @@ residual_kernel(const cplx *__restrict__ dl, const cplx *__restrict__ d, const c
     }
 }
 
+// r = b - A u, element-wise (the right-hand side of one step of iterative refinement)
+__global__ void __launch_bounds__(kResThreads)
+residual_vector_kernel(const cplx *__restrict__ dl, const cplx *__restrict__ d, const cplx *__restrict__ du,
+                       const cplx *__restrict__ b, const cplx *__restrict__ u, int64_t n, int64_t total,
+                       cplx *__restrict__ r) {
+    for (int64_t o = (int64_t)blockIdx.x * kResThreads + threadIdx.x; o < total; o += (int64_t)gridDim.x * kResThreads) {
+        const int64_t j = o % n;
+        cplx v = nmsub(b[o], d[o], u[o]);
+        if (j > 0) v = nmsub(v, dl[o], u[o - 1]);
+        if (j < n - 1) v = nmsub(v, du[o], u[o + 1]);
+        r[o] = v;
+    }
+}
+
 }  // namespace fh
+
+extern "C" int fh_tridiag_residual_vector_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c128 *du, const fh_c128 *b,
+                                               const fh_c128 *u, int64_t n, int64_t batch, fh_c128 *r,
+                                               fh_stream_t stream) {
+    using namespace fh;
+    FH_REQUIRE(n >= 0 && batch >= 0, "n and batch must be >= 0");
+    if (n == 0 || batch == 0) return FH_OK;
+    FH_REQUIRE(dl && d && du && b && u && r, "NULL device pointer");
+    const int64_t total = n * batch;
+    int64_t grid = (total + kResThreads - 1) / kResThreads;
+    const int64_t cap = 16ll * sm_count();
+    if (grid > cap) grid = cap;
+    residual_vector_kernel<<<(unsigned)grid, kResThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const cplx *>(dl), reinterpret_cast<const cplx *>(d), reinterpret_cast<const cplx *>(du),
+        reinterpret_cast<const cplx *>(b), reinterpret_cast<const cplx *>(u), n, total, reinterpret_cast<cplx *>(r));
+    FH_LAUNCH_CHECK("residual_vector_kernel");
+    return FH_OK;
+}
 
 extern "C" int fh_tridiag_residual_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c128 *du, const fh_c128 *b,
                                         const fh_c128 *u, int64_t n, int64_t batch, double *out4,

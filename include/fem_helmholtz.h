@@ -88,7 +88,8 @@ FH_API int fh_assemble_1d_c128(const fh_problem1d *prob_host, const double *ks, 
  * Thread-chunk partition (8 rows per thread in registers) + parallel cyclic reduction of the
  * per-thread interface rows in shared memory; a 2-CTA cluster solves one system when n > 2056.
  * status[batch] (device int32, may be NULL): bit 0 set if the solution holds a non-finite value
- * (zero pivot / singular system).  n <= fh_tridiag_batched_max_n() takes the cluster kernel, larger
+ * (zero pivot / singular system); bit 1 set if the unpivoted elimination met a pivot below 1e-3 of its
+ * scale (backward error may exceed ~1e-13: refine that system, see fh_tridiag_residual_vector_c128).  n <= fh_tridiag_batched_max_n() takes the cluster kernel, larger
  * n is routed to the partitioned large-system solver using `workspace`. */
 FH_API int64_t fh_tridiag_batched_max_n(void);
 FH_API size_t fh_tridiag_solve_batched_workspace_bytes(int64_t n, int64_t batch);
@@ -148,6 +149,16 @@ FH_API int fh_helmholtz1d_spike_backsub_c128(const fh_problem1d *prob_host, doub
 FH_API int fh_tridiag_residual_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c128 *du, const fh_c128 *b,
                              const fh_c128 *u, int64_t n, int64_t batch, double *out4,
                              fh_stream_t stream);
+
+/* r = b - A u for every system (complex128[batch][n]): the right-hand side of one refinement step. */
+FH_API int fh_tridiag_residual_vector_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c128 *du, const fh_c128 *b,
+                                    const fh_c128 *u, int64_t n, int64_t batch, fh_c128 *r, fh_stream_t stream);
+
+/* ---- L2 error against the continuum solution -exp(ikx) (replaces nb:259-281 compute_L2_error, quirks kept:
+ * complex square without abs, weight h*w).  sum_out[s] = the complex sum BEFORE the final sqrt (nb:281). */
+FH_API int fh_l2_error_1d_c128(const double *nodes, const fh_c128 *u, const double *ks, int64_t n_elem, int64_t batch,
+                        const double *gauss_pts_host, const double *gauss_wts_host, int n_gauss, fh_c128 *sum_out,
+                        fh_stream_t stream);
 
 /* =====================================================================================================
  * 2D: bilinear quads on the annulus (src/solvers/base.py and the four fem2d*.py classes)
