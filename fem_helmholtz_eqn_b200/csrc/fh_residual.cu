@@ -6,6 +6,7 @@
 namespace fh {
 
 constexpr int kResThreads = 256;
+__device__ __forceinline__ double abs1c(cplx z) { return fabs(z.re) + fabs(z.im); }  // LAPACK's cabs1
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -108,5 +109,76 @@ extern "C" int fh_tridiag_residual_c128(const fh_c128 *dl, const fh_c128 *d, con
         reinterpret_cast<const cplx *>(dl), reinterpret_cast<const cplx *>(d), reinterpret_cast<const cplx *>(du),
         reinterpret_cast<const cplx *>(b), reinterpret_cast<const cplx *>(u), n, batch, out4);
     FH_LAUNCH_CHECK("residual_kernel");
+    return FH_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Pivoted fallback.  The fast solvers are unpivoted; a system on which they produce a non-finite value (an
+// exactly vanishing leading minor, e.g. k*h = 2 on the first element) is re-solved here the way LAPACK zgtsv
+// does it: Gaussian elimination with partial pivoting between adjacent rows, one thread per system, serial in
+// n.  It only ever sees the handful of systems the status flags name, so its speed does not matter; what
+// matters is that numpy.linalg.LinAlgError is raised for genuinely singular systems only, as the reference does.
+namespace fh {
+__global__ void pivoted_gtsv_kernel(const cplx *__restrict__ dl, const cplx *__restrict__ d, const cplx *__restrict__ du,
+                                    const cplx *__restrict__ b, cplx *__restrict__ u, int64_t n, int64_t batch,
+                                    cplx *__restrict__ work, int32_t *__restrict__ status) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= batch) return;
+    const cplx *L = dl + s * n, *D0 = d + s * n, *U0 = du + s * n, *B = b + s * n;
+    cplx *x = u + s * n;                 // right-hand side, then the solution
+    cplx *dd = work + (3 * s) * n;       // diagonal
+    cplx *u1 = dd + n, *u2 = u1 + n;     // first and second super-diagonal of the factor
+    for (int64_t i = 0; i < n; ++i) dd[i] = D0[i], u1[i] = i < n - 1 ? U0[i] : czero(), u2[i] = czero(), x[i] = B[i];
+    bool singular = false;
+    for (int64_t i = 0; i + 1 < n; ++i) {
+        const cplx sub = L[i + 1];
+        if (abs1c(dd[i]) >= abs1c(sub)) {  // no interchange
+            if (abs1c(dd[i]) == 0.0) { singular = true; break; }
+            const cplx m = sub * crecip(dd[i]);
+            dd[i + 1] = nmsub(dd[i + 1], m, u1[i]);
+            x[i + 1] = nmsub(x[i + 1], m, x[i]);
+        } else {                           // swap rows i and i+1
+            const cplx m = dd[i] * crecip(sub);
+            const cplx di1 = dd[i + 1], ui = u1[i], xi = x[i];
+            dd[i] = sub;
+            u1[i] = di1;
+            dd[i + 1] = nmsub(ui, m, di1);
+            if (i + 2 < n) {
+                u2[i] = u1[i + 1];
+                u1[i + 1] = -(m * u1[i + 1]);
+            }
+            x[i] = x[i + 1];
+            x[i + 1] = nmsub(xi, m, x[i + 1]);
+        }
+    }
+    if (!singular && abs1c(dd[n - 1]) == 0.0) singular = true;
+    if (!singular) {
+        x[n - 1] = x[n - 1] * crecip(dd[n - 1]);
+        if (n > 1) x[n - 2] = nmsub(x[n - 2], u1[n - 2], x[n - 1]) * crecip(dd[n - 2]);
+        for (int64_t i = n - 3; i >= 0; --i)
+            x[i] = nmsub(nmsub(x[i], u1[i], x[i + 1]), u2[i], x[i + 2]) * crecip(dd[i]);
+        for (int64_t i = 0; i < n && !singular; ++i) singular = !cfinite(x[i]);
+    }
+    if (status != nullptr) status[s] = singular ? 1 : 0;
+}
+}  // namespace fh
+
+extern "C" size_t fh_tridiag_solve_pivoted_workspace_bytes(int64_t n, int64_t batch) {
+    return sizeof(fh::cplx) * 3 * (size_t)n * (size_t)batch;
+}
+
+extern "C" int fh_tridiag_solve_pivoted_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c128 *du, const fh_c128 *b,
+                                             fh_c128 *u, int64_t n, int64_t batch, int32_t *status, void *workspace,
+                                             size_t workspace_bytes, fh_stream_t stream) {
+    using namespace fh;
+    FH_REQUIRE(n >= 0 && batch >= 0, "n and batch must be >= 0");
+    if (n == 0 || batch == 0) return FH_OK;
+    FH_REQUIRE(dl && d && du && b && u && workspace, "NULL device pointer");
+    FH_REQUIRE(workspace_bytes >= fh_tridiag_solve_pivoted_workspace_bytes(n, batch), "workspace too small");
+    pivoted_gtsv_kernel<<<(unsigned)((batch + 31) / 32), 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const cplx *>(dl), reinterpret_cast<const cplx *>(d), reinterpret_cast<const cplx *>(du),
+        reinterpret_cast<const cplx *>(b), reinterpret_cast<cplx *>(u), n, batch, reinterpret_cast<cplx *>(workspace),
+        status);
+    FH_LAUNCH_CHECK("pivoted_gtsv_kernel");
     return FH_OK;
 }

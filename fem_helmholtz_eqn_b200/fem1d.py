@@ -246,6 +246,29 @@ def refine_flagged(dl, d, du, b, u, status):
     return m
 
 
+def resolve_nonfinite(dl, d, du, b, u, status):
+    """Re-solve, with partial pivoting, the systems on which the unpivoted kernels produced a non-finite value
+    (``status & STATUS_NONFINITE``): a vanishing leading minor is harmless to LAPACK's zgesv, which the reference
+    uses, so it must be harmless here.  Afterwards the flag stays set only for systems that are singular to working
+    precision.  Returns the number of re-solved systems."""
+    lib = _lib.require_cuda()
+    idx = torch.nonzero((status & STATUS_NONFINITE) != 0).flatten()
+    m = int(idx.numel())
+    if m == 0:
+        return 0
+    n = d.shape[1]
+    sub = [t.index_select(0, idx).contiguous() for t in (dl, d, du, b)]
+    x = torch.empty_like(sub[3])
+    st = torch.zeros(m, dtype=torch.int32, device=d.device)
+    ws_bytes = lib.fh_tridiag_solve_pivoted_workspace_bytes(n, m)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=d.device)
+    check(lib.fh_tridiag_solve_pivoted_c128(*(ptr(t) for t in sub), ptr(x), n, m, ptr(st), ptr(ws), ws_bytes,
+                                            stream_ptr()), "fh_tridiag_solve_pivoted_c128")
+    u.index_copy_(0, idx, x)
+    status.index_copy_(0, idx, st)
+    return m
+
+
 def solve_tridiagonal(dl, d, du, b, out=None, refine=True):
     """Batched tridiagonal solve on the GPU (replaces nb:204).  All arguments complex128[batch, n]
     CUDA tensors (numpy accepted and uploaded).  Returns ``(u, status)``; ``status[i] & STATUS_NONFINITE`` flags a
@@ -265,6 +288,7 @@ def solve_tridiagonal(dl, d, du, b, out=None, refine=True):
     check(lib.fh_tridiag_solve_batched_c128(ptr(dl), ptr(d), ptr(du), ptr(b), ptr(u), n, batch, ptr(status),
                                             ptr(ws), ws_bytes, stream_ptr()), "fh_tridiag_solve_batched_c128")
     if refine:
+        resolve_nonfinite(dl, d, du, b, u, status)
         refine_flagged(dl, d, du, b, u, status)
     return u, status
 

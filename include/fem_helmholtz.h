@@ -150,6 +150,13 @@ FH_API int fh_tridiag_residual_c128(const fh_c128 *dl, const fh_c128 *d, const f
                              const fh_c128 *u, int64_t n, int64_t batch, double *out4,
                              fh_stream_t stream);
 
+/* Pivoted fallback (LAPACK zgtsv's algorithm, one thread per system): for the few systems on which the unpivoted
+ * solvers report a non-finite value.  status[s] = 1 only if the system is singular to working precision. */
+FH_API size_t fh_tridiag_solve_pivoted_workspace_bytes(int64_t n, int64_t batch);
+FH_API int fh_tridiag_solve_pivoted_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c128 *du, const fh_c128 *b,
+                                  fh_c128 *u, int64_t n, int64_t batch, int32_t *status, void *workspace,
+                                  size_t workspace_bytes, fh_stream_t stream);
+
 /* r = b - A u for every system (complex128[batch][n]): the right-hand side of one refinement step. */
 FH_API int fh_tridiag_residual_vector_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c128 *du, const fh_c128 *b,
                                     const fh_c128 *u, int64_t n, int64_t batch, fh_c128 *r, fh_stream_t stream);

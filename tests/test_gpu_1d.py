@@ -225,3 +225,24 @@ def test_l2_error_and_convergence_rates_match_notebook(golden1d, capsys):
     stored = json.load(open(os.path.join(GOLDEN, "versions.json")))["notebook_stored_stdout"]
     assert capsys.readouterr().out == stored
     assert np.allclose(np.array(list(rates.values())), g["conv_rates"], rtol=1e-7)
+
+
+def test_zero_pivot_is_resolved_by_the_pivoted_fallback():
+    """k*h = 2 makes the first diagonal entry exactly zero (-1/h + k^2 h/4): harmless for LAPACK's pivoted zgesv
+    that the reference calls, fatal for an unpivoted sweep.  The status flag routes such systems to the pivoted
+    device fallback, so the result still matches the reference and no LinAlgError is raised."""
+    for N, k in ((1, 2.0), (2, 4.0), (64, 128.0), (1000, 2000.0)):
+        dl, d, du, b = banded1d.assemble_bands(N, k, 1.0 / N)
+        assert d[0] == 0
+        nodes, u = fh.solve_helmholtz_fem(N, k)
+        assert rel_err(u, banded1d.solve_bands(dl, d, du, b)) < 1e-12, (N, k)
+    # mixed batch: only the flagged systems take the fallback
+    ks = [3.0, 128.0, 77.0]
+    _, U, status = fh.solve_helmholtz_sweep(64, ks, return_status=True)
+    assert _np(status).tolist() == [0, 0, 0]
+    for i, k in enumerate(ks):
+        assert rel_err(_np(U[i]), banded1d.solve_bands(*banded1d.assemble_bands(64, k, 1.0 / 64))) < 1e-11
+    # without the fallback the raw kernel reports it
+    bands = fh.assemble_bands(64, 128.0, 1.0 / 64)
+    _, st = fh.solve_tridiagonal(*bands, refine=False)
+    assert int(st[0]) & 1
