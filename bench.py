@@ -313,6 +313,8 @@ def run_gpu(args):
                          "algorithmic_bytes_per_launch": BYTES_SOLVE * dof_rank, "traffic": traffic,
                          "launch_ms": sol_mean},
             "stages": {"assembly_ms": asm_mean, "solve_ms": sol_mean, "refine_ms": statistics.mean(ref_ms),
+                       "solve_ms_per_step": [round(v, 3) for v in sol_ms],
+                       "refined_per_step": refined,
                        "refined_systems_per_step": statistics.mean(refined),
                        "assembly_gbs": BYTES_ASSEMBLY * dof_rank / (asm_mean * 1e-3) / 1e9,
                        "assembly_frac": BYTES_ASSEMBLY * dof_rank / (asm_mean * 1e-3) / 1e9 / peak,

@@ -6,9 +6,8 @@
 //      its interior couplings with a downward and an upward elimination sweep (pivots are kept as
 //      reciprocals), leaving  a_i x_left + b_i x_i + c_i x_last = d_i  (i < 7) and one interface
 //      row per thread;
-//   2. the 256 interface rows of a CTA (kept normalised: unit diagonal) are reduced to 32 rows by three
-//      levels of cyclic reduction in shared memory; the 32 survivors are solved by parallel cyclic
-//      reduction (PCR) inside one warp with shuffles; three back-substitution levels recover the rest;
+//   2. the 256 interface rows of a CTA are solved by parallel cyclic reduction (PCR) in shared
+//      memory, <= 8 levels, rows kept normalised (unit diagonal);
 //   3. back-substitution in registers; the solution is staged in shared memory and leaves with one
 //      TMA tensor store.
 //   A system of up to 2056 rows is handled by one CTA; up to 4112 rows by a 2-CTA cluster: rank 0
@@ -43,6 +42,7 @@ constexpr int kM = 8;                          // rows per thread (register chun
 constexpr int kSlots = kT * kM;                // 2048 body rows per CTA
 constexpr int kHeadMax = 8;                    // extra rows at the far end, eliminated serially
 constexpr int kStageRows = kSlots + kHeadMax;  // 2056
+constexpr int kLevelsMax = 8;                  // log2(kT)
 constexpr uint32_t kTileBytes = kSlots * sizeof(cplx);  // 32 KB per band tile
 
 struct __align__(1024) BatchedSmem {
@@ -118,13 +118,6 @@ __device__ __forceinline__ cplx frecip(cplx a) {
     const double s = fast_rcp(fma(a.re, a.re, a.im * a.im));
     return mk(a.re * s, -a.im * s);
 }
-__device__ __forceinline__ cplx shfl_up(cplx v, int d) {
-    return mk(__shfl_up_sync(0xffffffffu, v.re, d), __shfl_up_sync(0xffffffffu, v.im, d));
-}
-__device__ __forceinline__ cplx shfl_down(cplx v, int d) {
-    return mk(__shfl_down_sync(0xffffffffu, v.re, d), __shfl_down_sync(0xffffffffu, v.im, d));
-}
-
 // A-posteriori accuracy probe.  The elimination is unpivoted; what it can lose shows up as a defect of the
 // INTERFACE rows (row 7 of every chunk -- interior rows are satisfied by construction of the back-substitution;
 // checked against a numpy model: the largest componentwise row residual always sits on an interface row and
@@ -240,7 +233,7 @@ __device__ __forceinline__ void helm_row(const Source &src, const HelmState &st,
 template <int CLUSTER, class Source>
 __global__ void __launch_bounds__(kT, 1)
 tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ StoreMaps umaps,
-                       Source src, cplx *__restrict__ u, int64_t n, int64_t batch,
+                       Source src, cplx *__restrict__ u, int64_t n, int64_t batch, int levels,
                        int32_t *__restrict__ status) {
     extern __shared__ unsigned char smem_raw[];
     // the dynamic window is only guaranteed 16-byte aligned: round up to the 1024 B the swizzle needs
@@ -407,99 +400,60 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
             const cplx inv = frecip(rb);
             rA = rA * inv, rC = rC * inv, rD = rD * inv, rV = rV * inv;
         }
-        // ---- interface system (256 rows, unit diagonal): cyclic reduction 256 -> 32 rows in shared memory,
-        //      parallel cyclic reduction of the 32 survivors inside ONE warp with shuffles, back-substitution.
-        //      (v2 ran PCR over all 256 rows for 8 levels: 390 KB of shared-memory traffic per system, the
-        //      binding resource of that phase; this needs ~80 KB and one barrier less.)
-        cplx *SA = sm.pcr[0][0], *SC = sm.pcr[0][1], *SD = sm.pcr[0][2], *SV = sm.pcr[0][3], *XS = sm.pcr[1][0];
-        SA[t] = rA, SC[t] = rC, SD[t] = rD;
-        if (CLUSTER > 1) SV[t] = rV;
+        // ---- PCR over the CTA's 256 interface rows (unit diagonal) ------------------------------------
+        int cur = 0;
+        sm.pcr[0][0][t] = rA, sm.pcr[0][1][t] = rC, sm.pcr[0][2][t] = rD;
+        if (CLUSTER > 1) sm.pcr[0][3][t] = rV;
         __syncthreads();
-#pragma unroll
-        for (int s = 1; s <= 4; s <<= 1) {  // forward: rows r with (r + 1) % 2s == 0 absorb r - s and r + s
-            if (t < kT / (2 * s)) {
-                const int r = 2 * s * (t + 1) - 1, rm = r - s, rp = r + s;
-                const cplx A = SA[r], C = SC[r], D = SD[r];
-                const cplx Am = SA[rm], Cm = SC[rm], Dm = SD[rm];
-                cplx Ap = czero(), Cp = czero(), Dp = czero(), Vp = czero(), V = czero(), Vm = czero();
-                if (rp < kT) Ap = SA[rp], Cp = SC[rp], Dp = SD[rp];
-                if (CLUSTER > 1) {
-                    V = SV[r], Vm = SV[rm];
-                    if (rp < kT) Vp = SV[rp];
-                }
-                const cplx inv = frecip(nmsub(nmsub(cone(), A, Cm), C, Ap));
-                SA[r] = -((A * Am) * inv);
-                SC[r] = -((C * Cp) * inv);
-                SD[r] = nmsub(nmsub(D, A, Dm), C, Dp) * inv;
-                if (CLUSTER > 1) SV[r] = nmsub(nmsub(V, A, Vm), C, Vp) * inv;
+        for (int lv = 0, s = 1; lv < levels; ++lv, s <<= 1) {
+            const bool last = lv == levels - 1;
+            cplx Am = czero(), Cm = czero(), Dm = czero(), Vm = czero();
+            cplx Ap = czero(), Cp = czero(), Dp = czero(), Vp = czero();
+            if (t - s >= 0) {
+                Am = sm.pcr[cur][0][t - s], Cm = sm.pcr[cur][1][t - s], Dm = sm.pcr[cur][2][t - s];
+                if (CLUSTER > 1) Vm = sm.pcr[cur][3][t - s];
             }
+            if (t + s < kT) {
+                Ap = sm.pcr[cur][0][t + s], Cp = sm.pcr[cur][1][t + s], Dp = sm.pcr[cur][2][t + s];
+                if (CLUSTER > 1) Vp = sm.pcr[cur][3][t + s];
+            }
+            const cplx inv = frecip(nmsub(nmsub(cone(), rA, Cm), rC, Ap));
+            const cplx nD = nmsub(nmsub(rD, rA, Dm), rC, Dp) * inv;
+            cplx nV = czero();
+            if (CLUSTER > 1) nV = nmsub(nmsub(rV, rA, Vm), rC, Vp) * inv;
+            cur ^= 1;
+            if (!last) {  // the last level leaves no couplings: A and C are not needed any more
+                const cplx nA = -((rA * Am) * inv);
+                const cplx nC = -((rC * Cp) * inv);
+                rA = nA, rC = nC;
+                sm.pcr[cur][0][t] = rA, sm.pcr[cur][1][t] = rC;
+            }
+            rD = nD, rV = nV;
+            sm.pcr[cur][2][t] = rD;
+            if (CLUSTER > 1) sm.pcr[cur][3][t] = rV;
             __syncthreads();
         }
-        if (t < 32) {  // warp 0: PCR over the survivors r = 8 * lane + 7, neighbours by shuffle
-            const int r = 8 * t + 7;
-            cplx A = SA[r], C = SC[r], D = SD[r], V = CLUSTER > 1 ? SV[r] : czero();
-#pragma unroll
-            for (int s = 1; s < 32; s <<= 1) {
-                cplx Am = shfl_up(A, s), Cm = shfl_up(C, s), Dm = shfl_up(D, s);
-                cplx Ap = shfl_down(A, s), Cp = shfl_down(C, s), Dp = shfl_down(D, s);
-                cplx Vm = czero(), Vp = czero();
-                if (CLUSTER > 1) Vm = shfl_up(V, s), Vp = shfl_down(V, s);
-                if (t < s) Am = czero(), Cm = czero(), Dm = czero(), Vm = czero();
-                if (t + s > 31) Ap = czero(), Cp = czero(), Dp = czero(), Vp = czero();
-                const cplx inv = frecip(nmsub(nmsub(cone(), A, Cm), C, Ap));
-                const cplx nD = nmsub(nmsub(D, A, Dm), C, Dp) * inv;
-                if (CLUSTER > 1) V = nmsub(nmsub(V, A, Vm), C, Vp) * inv;
-                if (s < 16) {  // the last level leaves no couplings
-                    const cplx nA = -((A * Am) * inv), nC = -((C * Cp) * inv);
-                    A = nA, C = nC;
-                }
-                D = nD;
-            }
-            SD[r] = D;  // x_r = D - V * x_partner
-            if (CLUSTER > 1) {
-                SV[r] = V;
-                if (t == 31) {
-                    const uint32_t rbar = map_to_rank(&sm.xchg_bar[parity], rank ^ 1);
-                    st_async_remote(map_to_rank(&sm.xchg[parity][0], rank ^ 1), D, rbar);
-                    st_async_remote(map_to_rank(&sm.xchg[parity][1], rank ^ 1), V, rbar);
-                }
-            }
-        }
-        __syncthreads();
-        cplx x_partner = czero();
+        // now x_last(t) = rD - rV * x_partner
+        cplx X = rD, x_partner = czero();
         if (CLUSTER > 1) {
+            if (t == kT - 1) {
+                const uint32_t rbar = map_to_rank(&sm.xchg_bar[parity], rank ^ 1);
+                st_async_remote(map_to_rank(&sm.xchg[parity][0], rank ^ 1), rD, rbar);
+                st_async_remote(map_to_rank(&sm.xchg[parity][1], rank ^ 1), rV, rbar);
+            }
             mbar_wait(&sm.xchg_bar[parity], (it >> 1) & 1);
             const cplx Yp = sm.xchg[parity][0], Vp = sm.xchg[parity][1];
-            const cplx Ym = SD[kT - 1], Vm = SV[kT - 1];
+            const cplx Ym = sm.pcr[cur][2][kT - 1], Vm = sm.pcr[cur][3][kT - 1];
             // x_me = Ym - Vm x_p ; x_p = Yp - Vp x_me
             const cplx x_me = nmsub(Ym, Vm, Yp) * frecip(nmsub(cone(), Vm, Vp));
-            x_partner = nmsub(Yp, Vp, x_me);
+            const cplx x_p = nmsub(Yp, Vp, x_me);
+            X = nmsub(rD, rV, x_p);
+            x_partner = x_p;
         }
-        // right-hand side of row r with the partner unknown substituted
-        auto rhs = [&](int r) { return CLUSTER > 1 ? nmsub(SD[r], SV[r], x_partner) : SD[r]; };
-        if (t < 32) {  // stride 4: rows 8t+3 from the survivors 8t-1 and 8t+7 (whose values are published too)
-            const int r = 8 * t + 3;
-            const cplx xr = rhs(r + 4);
-            const cplx xm = t > 0 ? rhs(r - 4) : czero();
-            XS[r] = nmsub(nmsub(rhs(r), SA[r], xm), SC[r], xr);
-            XS[r + 4] = xr;
-        }
-        __syncthreads();
-        if (t < 64) {  // stride 2: rows 4t+1
-            const int r = 4 * t + 1;
-            const cplx xm = t > 0 ? XS[r - 2] : czero();
-            XS[r] = nmsub(nmsub(rhs(r), SA[r], xm), SC[r], XS[r + 2]);
-        }
-        __syncthreads();
-        if (t < 128) {  // stride 1: rows 2t
-            const int r = 2 * t;
-            const cplx xm = t > 0 ? XS[r - 1] : czero();
-            XS[r] = nmsub(nmsub(rhs(r), SA[r], xm), SC[r], XS[r + 1]);
-        }
+        sm.pcr[cur ^ 1][0][t] = X;
         if (t == 0) tma_store_wait_read();  // the previous system's TMA store has finished reading xs
         __syncthreads();
-        const cplx X = XS[t];
-        const cplx xl = t > 0 ? XS[t - 1] : czero();
+        const cplx xl = t > 0 ? sm.pcr[cur ^ 1][0][t - 1] : czero();
 
         // ---- back-substitution + staging -----------------------------------------------------------
         bool bad = !cfinite(X);
@@ -553,6 +507,19 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
 // Host side
 // ----------------------------------------------------------------------------------------------
 constexpr int64_t kBatchedMaxN = 2 * (int64_t)kStageRows;  // 4112
+
+static int ceil_log2(int v) {
+    int l = 0;
+    while ((1 << l) < v) ++l;
+    return l;
+}
+
+static int pcr_levels(int64_t n, int cluster) {
+    const HostMap h = host_map(n, cluster);
+    const int chunks = h.chunks[0] > h.chunks[1] ? h.chunks[0] : h.chunks[1];
+    const int lv = ceil_log2(chunks < 1 ? 1 : chunks);
+    return lv > kLevelsMax ? kLevelsMax : lv;
+}
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -640,7 +607,8 @@ static int launch_batched(const Source &src, const cplx *const bands[4], cplx *u
     attr[0].val.clusterDim.x = CLUSTER, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    FH_CUDA(cudaLaunchKernelEx(&cfg, kernel, maps, umaps, src, u, n, batch, status));
+    const int levels = pcr_levels(n, CLUSTER);
+    FH_CUDA(cudaLaunchKernelEx(&cfg, kernel, maps, umaps, src, u, n, batch, levels, status));
     return FH_OK;
 }
 
