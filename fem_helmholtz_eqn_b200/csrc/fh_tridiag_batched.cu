@@ -28,10 +28,9 @@
 // Fused variant: the same kernel with the band loads replaced by the row generator of
 // fh_helm1d.cuh (bit-identical to what fh_assemble_1d_c128 would have stored); 16 B/row written.
 #include <cooperative_groups.h>
-#include <cuda.h>
-#include <string.h>
+#include <stdlib.h>
 
-#include "fh_helm1d.cuh"
+#include "fh_tridiag_dev.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -54,78 +53,6 @@ struct __align__(1024) BatchedSmem {
     unsigned long long full_bar;     // mbarrier: band tiles have landed
     unsigned long long xchg_bar[2];  // mbarrier: partner's interface pair has landed
 };
-
-// ---------------------------------------------------------------------------------------------- PTX helpers
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2,
-                                            unsigned long long *bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, int c0, int c1, int c2, const void *src) {
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map),
-                 "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(src))
-                 : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-// 16 bytes into the partner CTA's shared memory, completing 16 tx-bytes on the partner's mbarrier
-__device__ __forceinline__ void st_async_remote(uint32_t remote_addr, cplx v, uint32_t remote_bar) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0], {%1, %2}, [%3];" ::"r"(
-                     remote_addr),
-                 "d"(v.re), "d"(v.im), "r"(remote_bar)
-                 : "memory");
-}
-__device__ __forceinline__ uint32_t map_to_rank(const void *p, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
-    return r;
-}
-
-// 1/x to ~1 ulp: hardware seed (MUFU.RCP64H, ~20 bits) + two Newton steps.  Non-finite / zero
-// inputs give NaN or Inf, which the status check reports.
-__device__ __forceinline__ double fast_rcp(double x) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    return fma(r, e, r);
-}
-__device__ __forceinline__ cplx frecip(cplx a) {
-    const double s = fast_rcp(fma(a.re, a.re, a.im * a.im));
-    return mk(a.re * s, -a.im * s);
-}
-// A-posteriori accuracy probe.  The elimination is unpivoted; what it can lose shows up as a defect of the
-// INTERFACE rows (row 7 of every chunk -- interior rows are satisfied by construction of the back-substitution;
-// checked against a numpy model: the largest componentwise row residual always sits on an interface row and
-// tracks the normwise backward error with correlation 0.92).  Every thread therefore keeps the original
-// coefficients of its row 7 and re-evaluates that one equation with the computed solution; a relative defect above
-// kProbeTol sets status bit 1, and the host refines exactly those systems (~2 % of a fine wavenumber sweep).
-constexpr double kProbeTol = 5e-14;
-__device__ __forceinline__ double abs1(cplx z) { return fabs(z.re) + fabs(z.im); }
 
 // ---------------------------------------------------------------------------------------------- row -> slot maps
 // How the rows of one system map onto one CTA.  Local rows run from the far end (j = 0) to the cut / the
@@ -185,30 +112,6 @@ __device__ __forceinline__ LocalMap make_map(int64_t n, int rank) {
     }
     return m;
 }
-
-// ---------------------------------------------------------------------------------------------- band sources
-struct TensorMaps {  // built by the host per launch; live in kernel parameter space
-    CUtensorMap dl, d, du, b;
-};
-struct StoreMaps {   // solution tensor as seen by cluster rank 0 (clipped at the cut) and rank 1
-    CUtensorMap r0, r1;
-};
-
-struct BandSource {  // staged pipeline: bands live in global memory
-    const cplx *dl, *d, *du, *b;
-    static constexpr bool kStaged = true;
-};
-
-struct HelmSource {  // fused pipeline: bands are generated, never stored
-    Problem1d p;
-    const double *ks, *k2s;
-    static constexpr bool kStaged = false;
-};
-
-struct HelmState {  // per-thread state of the generator (scalar-h mode: three distinct geometries)
-    RowGeom g_first, g_mid, g_last;
-    double k, k2;
-};
 
 template <class Source>
 __device__ __forceinline__ void helm_row(const Source &src, const HelmState &st, const LocalMap &m, int j, cplx &a,
@@ -521,45 +424,6 @@ static int pcr_levels(int64_t n, int cluster) {
     return lv > kLevelsMax ? kLevelsMax : lv;
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (fn == nullptr) {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
-// Tensor view of one band / solution array: [batch][chunks][16 doubles], origin at row `head0` of system 0.
-static int make_tensor_map(CUtensorMap *out, const cplx *base, int64_t n, int64_t batch, int head0, int chunks_total) {
-    EncodeTiledFn enc = encode_fn();
-    if (enc == nullptr) {
-        set_error("cuTensorMapEncodeTiled is not available from this driver");
-        return FH_E_UNSUPPORTED;
-    }
-    const cuuint64_t dims[3] = {16, (cuuint64_t)(chunks_total < 1 ? 1 : chunks_total), (cuuint64_t)batch};
-    const cuuint64_t strides[2] = {128, (cuuint64_t)n * sizeof(cplx)};
-    const cuuint32_t box[3] = {16, (cuuint32_t)kT, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    void *addr = const_cast<cplx *>(base) + head0;
-    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, addr, dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed with CUresult %d (n=%lld batch=%lld)", (int)r, (long long)n,
-                  (long long)batch);
-        return FH_E_INVALID;
-    }
-    return FH_OK;
-}
-
 template <int CLUSTER, class Source>
 static int launch_batched(const Source &src, const cplx *const bands[4], cplx *u, int64_t n, int64_t batch,
                           int32_t *status, cudaStream_t stream) {
@@ -579,16 +443,16 @@ static int launch_batched(const Source &src, const cplx *const bands[4], cplx *u
     StoreMaps umaps;
     memset(&maps, 0, sizeof(maps));
     memset(&umaps, 0, sizeof(umaps));
-    int rc = make_tensor_map(&umaps.r0, u, n, batch, h.head[0], h.chunks[0]);
+    int rc = make_tensor_map(&umaps.r0, u, n, batch, h.head[0], h.chunks[0], kT);
     if (rc != FH_OK) return rc;
     if (CLUSTER > 1) {
-        rc = make_tensor_map(&umaps.r1, u, n, batch, h.head[0], chunks_total);
+        rc = make_tensor_map(&umaps.r1, u, n, batch, h.head[0], chunks_total, kT);
         if (rc != FH_OK) return rc;
     }
     if (Source::kStaged) {
         CUtensorMap *dst[4] = {&maps.dl, &maps.d, &maps.du, &maps.b};
         for (int i = 0; i < 4; ++i) {
-            rc = make_tensor_map(dst[i], bands[i], n, batch, h.head[0], chunks_total);
+            rc = make_tensor_map(dst[i], bands[i], n, batch, h.head[0], chunks_total, kT);
             if (rc != FH_OK) return rc;
         }
     }
@@ -612,6 +476,17 @@ static int launch_batched(const Source &src, const cplx *const bands[4], cplx *u
     return FH_OK;
 }
 
+// from fh_tridiag_chain.cu: 4-CTA x 128-thread variant, two CTAs per SM
+bool chain_covers(int64_t n);
+int chain_solve_bands(const cplx *dl, const cplx *d, const cplx *du, const cplx *b, cplx *u, int64_t n, int64_t batch,
+                      int32_t *status, cudaStream_t stream);
+int chain_solve_helm(const HelmSource &src, cplx *u, int64_t n, int64_t batch, int32_t *status, cudaStream_t stream);
+// FH_TRIDIAG_KERNEL=pair|chain picks the cluster kernel for systems both cover (development switch)
+static bool prefer_chain() {
+    const char *e = getenv("FH_TRIDIAG_KERNEL");
+    return e != nullptr && strcmp(e, "chain") == 0;
+}
+
 // from fh_tridiag_large.cu
 int solve_large(const cplx *dl, const cplx *d, const cplx *du, const cplx *b, cplx *u, int64_t n,
                 int32_t *status, void *workspace, size_t workspace_bytes, cudaStream_t stream);
@@ -623,6 +498,7 @@ int batched_solve_bands(const cplx *dl, const cplx *d, const cplx *du, const cpl
         set_error("batched kernel handles n <= %lld", (long long)kBatchedMaxN);
         return FH_E_UNSUPPORTED;
     }
+    if (prefer_chain() && chain_covers(n)) return chain_solve_bands(dl, d, du, b, u, n, batch, status, stream);
     BandSource src;
     src.dl = dl, src.d = d, src.du = du, src.b = b;
     const cplx *const bands[4] = {dl, d, du, b};
@@ -684,6 +560,7 @@ int fh_helmholtz1d_sweep_fused_c128(const fh_problem1d *prob_host, const double 
     src.ks = ks, src.k2s = k2s;
     const cplx *const none[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (prefer_chain() && chain_covers(n)) return chain_solve_helm(src, reinterpret_cast<cplx *>(u), n, n_k, status, st);
     if (n <= kStageRows) return launch_batched<1>(src, none, reinterpret_cast<cplx *>(u), n, n_k, status, st);
     return launch_batched<2>(src, none, reinterpret_cast<cplx *>(u), n, n_k, status, st);
 }
