@@ -57,20 +57,20 @@ assemble1d_kernel(Problem1d p, const double *__restrict__ ks, const double *__re
 // against 7.4 TB/s for a plain fill on the same GPU; tools/write_bw_probe.py).
 __global__ void __launch_bounds__(kAsmThreads)
 assemble1d_scalar_kernel(Problem1d p, const double *__restrict__ ks, const double *__restrict__ k2s,
-                         int64_t n_k, int64_t k_per_block, cplx *__restrict__ dl, cplx *__restrict__ d,
+                         int64_t n_k, int64_t per_block, cplx *__restrict__ dl, cplx *__restrict__ d,
                          cplx *__restrict__ du, cplx *__restrict__ b) {
+    // every CTA owns a contiguous range of the flattened (wavenumber, row) index space, whatever the aspect
+    // ratio of the batch is (65,536 short systems or one system of 2^27 rows)
     const int64_t n = p.n_elem + 1;
-    const int64_t k_begin = static_cast<int64_t>(blockIdx.x) * k_per_block;
-    const int64_t k_end = min(n_k, k_begin + k_per_block);
-    if (k_begin >= k_end) return;
+    const int64_t o_begin = static_cast<int64_t>(blockIdx.x) * per_block;
+    const int64_t o_end = min(n_k * n, o_begin + per_block);
+    if (o_begin >= o_end) return;
     const RowGeom g_first = row_geom(p, 0);
     const RowGeom g_mid = row_geom(p, p.n_elem > 1 ? 1 : 0);
     const RowGeom g_last = row_geom(p, p.n_elem);
-    // flat position inside the slab, advanced by blockDim per step; (s, j) follow incrementally
-    int64_t s = k_begin + threadIdx.x / n;
-    int64_t j = threadIdx.x % n;
-    int64_t o = k_begin * n + threadIdx.x;
-    const int64_t o_end = k_end * n;
+    int64_t o = o_begin + threadIdx.x;
+    int64_t s = o / n;      // wavenumber index; (s, j) follow o incrementally from here on
+    int64_t j = o - s * n;  // row
     int64_t s_cached = -1;
     cplx il = czero(), id = czero(), iu = czero(), ib = czero();  // interior row of the cached wavenumber
     double k = 0.0, k2 = 0.0;
@@ -152,10 +152,11 @@ int fh_assemble_1d_c128(const fh_problem1d *prob_host, const double *ks, const d
     const int64_t n = p.n_elem + 1;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (p.h_mode == FH_H_SCALAR && p.n_elem >= 2) {  // structured-fill fast path
+        const int64_t total = n_k * n;
         int64_t slabs = 8ll * fh::sm_count();
-        if (slabs > n_k) slabs = n_k;
-        const int64_t per = (n_k + slabs - 1) / slabs;
-        slabs = (n_k + per - 1) / per;
+        int64_t per = (total + slabs - 1) / slabs;
+        per = ((per + fh::kAsmThreads - 1) / fh::kAsmThreads) * fh::kAsmThreads;  // whole passes of the CTA
+        slabs = (total + per - 1) / per;
         fh::assemble1d_scalar_kernel<<<(unsigned)slabs, fh::kAsmThreads, 0, st>>>(
             p, ks, k2s, n_k, per, reinterpret_cast<fh::cplx *>(dl), reinterpret_cast<fh::cplx *>(d),
             reinterpret_cast<fh::cplx *>(du), reinterpret_cast<fh::cplx *>(b));

@@ -36,12 +36,18 @@ namespace cg = cooperative_groups;
 
 namespace fh {
 
-constexpr int kT = 256;                        // threads per CTA
-constexpr int kM = 8;                          // rows per thread (register chunk)
+#ifndef FH_PAIR_ROWS
+#define FH_PAIR_ROWS 8
+#endif
+constexpr int kM = FH_PAIR_ROWS;               // rows per thread (register chunk): 8 or 4
+constexpr int kT = 2048 / kM;                  // threads per CTA: 256 or 512
 constexpr int kSlots = kT * kM;                // 2048 body rows per CTA
+constexpr int kChunks8 = kSlots / 8;           // 8-row memory chunks (TMA tile rows) per CTA: 256
+constexpr int kPer8 = 8 / kM;                  // threads sharing one memory chunk: 1 or 2
+static_assert(kM == 8 || kM == 4, "register chunk must be 8 or 4 rows");
 constexpr int kHeadMax = 8;                    // extra rows at the far end, eliminated serially
 constexpr int kStageRows = kSlots + kHeadMax;  // 2056
-constexpr int kLevelsMax = 8;                  // log2(kT)
+constexpr int kLevelsMax = kM == 8 ? 8 : 9;    // log2(kT)
 constexpr uint32_t kTileBytes = kSlots * sizeof(cplx);  // 32 KB per band tile
 
 struct __align__(1024) BatchedSmem {
@@ -68,16 +74,18 @@ struct LocalMap {
     // swizzle-128B slot of element i of thread t's chunk in the LOAD tiles (box right-aligned: TMA loads
     // accept negative start coordinates and zero-fill)
     __device__ __forceinline__ int slot(int t, int i) const {
-        const int r = dir > 0 ? t : kT - 1 - t;
-        const int e = dir > 0 ? i : kM - 1 - i;
-        return r * kM + (e ^ (r & 7));
+        const int tt = dir > 0 ? t : kT - 1 - t;           // thread chunk in memory order
+        const int r = tt / kPer8;                          // 8-row memory chunk = TMA tile row
+        const int e = (dir > 0 ? i : kM - 1 - i) + kM * (tt % kPer8);
+        return r * 8 + (e ^ (r & 7));
     }
     // ... and in the STORE tile: TMA stores trap on negative coordinates (measured, tools/tma_probe.cu), so
     // the forward half is left-aligned (box starts at chunk 0, the tensor map clips at the half's last chunk)
     __device__ __forceinline__ int xs_slot(int t, int i) const {
-        const int r = dir > 0 ? t - first_active : kT - 1 - t;
-        const int e = dir > 0 ? i : kM - 1 - i;
-        return r * kM + (e ^ (r & 7));
+        const int tt = dir > 0 ? t - first_active : kT - 1 - t;
+        const int r = tt / kPer8;
+        const int e = (dir > 0 ? i : kM - 1 - i) + kM * (tt % kPer8);
+        return r * 8 + (e ^ (r & 7));
     }
 };
 
@@ -89,10 +97,10 @@ __host__ __device__ inline HostMap host_map(int64_t n, int cluster) {
     m.n_loc[0] = cluster == 1 ? (int)n : (int)(n / 2);
     m.n_loc[1] = cluster == 1 ? 0 : (int)(n - n / 2);
     for (int r = 0; r < 2; ++r) {
-        int c = m.n_loc[r] / kM;
-        if (c > kT) c = kT;
+        int c = m.n_loc[r] / 8;          // 8-row memory chunks
+        if (c > kChunks8) c = kChunks8;
         m.chunks[r] = c;
-        m.head[r] = m.n_loc[r] - c * kM;  // 0..8
+        m.head[r] = m.n_loc[r] - c * 8;  // 0..8
     }
     return m;
 }
@@ -102,10 +110,10 @@ __device__ __forceinline__ LocalMap make_map(int64_t n, int rank) {
     const HostMap h = host_map(n, CLUSTER);
     LocalMap m;
     m.n_loc = h.n_loc[rank], m.head = h.head[rank], m.chunks = h.chunks[rank];
-    m.first_active = kT - m.chunks;
+    m.first_active = kT - kPer8 * m.chunks;  // in threads
     if (rank == 0) {
         m.g0 = 0, m.dir = 1;
-        m.box_c1 = m.chunks - kT;  // thread t <-> box row t <-> memory chunk t - first_active
+        m.box_c1 = m.chunks - kChunks8;  // tile row r <-> memory chunk r + box_c1 (right-aligned)
     } else {
         m.g0 = n - 1, m.dir = -1;
         m.box_c1 = h.chunks[0];    // thread t <-> box row kT-1-t <-> memory chunk chunks0 + (kT-1-t)
@@ -420,7 +428,7 @@ static int ceil_log2(int v) {
 static int pcr_levels(int64_t n, int cluster) {
     const HostMap h = host_map(n, cluster);
     const int chunks = h.chunks[0] > h.chunks[1] ? h.chunks[0] : h.chunks[1];
-    const int lv = ceil_log2(chunks < 1 ? 1 : chunks);
+    const int lv = ceil_log2(chunks < 1 ? 1 : kPer8 * chunks);  // interface rows = thread chunks
     return lv > kLevelsMax ? kLevelsMax : lv;
 }
 
@@ -443,16 +451,16 @@ static int launch_batched(const Source &src, const cplx *const bands[4], cplx *u
     StoreMaps umaps;
     memset(&maps, 0, sizeof(maps));
     memset(&umaps, 0, sizeof(umaps));
-    int rc = make_tensor_map(&umaps.r0, u, n, batch, h.head[0], h.chunks[0], kT);
+    int rc = make_tensor_map(&umaps.r0, u, n, batch, h.head[0], h.chunks[0], kChunks8);
     if (rc != FH_OK) return rc;
     if (CLUSTER > 1) {
-        rc = make_tensor_map(&umaps.r1, u, n, batch, h.head[0], chunks_total, kT);
+        rc = make_tensor_map(&umaps.r1, u, n, batch, h.head[0], chunks_total, kChunks8);
         if (rc != FH_OK) return rc;
     }
     if (Source::kStaged) {
         CUtensorMap *dst[4] = {&maps.dl, &maps.d, &maps.du, &maps.b};
         for (int i = 0; i < 4; ++i) {
-            rc = make_tensor_map(dst[i], bands[i], n, batch, h.head[0], chunks_total, kT);
+            rc = make_tensor_map(dst[i], bands[i], n, batch, h.head[0], chunks_total, kChunks8);
             if (rc != FH_OK) return rc;
         }
     }

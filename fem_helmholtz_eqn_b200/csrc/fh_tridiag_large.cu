@@ -88,10 +88,14 @@ struct HelmRows {  // level-0 rows generated from the Helmholtz problem: local r
     double k, k2;
     int64_t g_off, n;
     __device__ __forceinline__ void fill(LargeSmem &sm, int64_t row0, int rows) const {
+        // scalar-h (the reference's mode): every interior row is the same -- evaluate it once per thread
+        const bool scalar = p.h_mode == FH_H_SCALAR && p.n_elem >= 2;
+        cplx il = czero(), id = czero(), iu = czero(), ib = czero();
+        if (scalar) row_values(p, row_geom(p, 1), 1, k, k2, il, id, iu, ib);
         for (int j = threadIdx.x; j < rows; j += kLT) {
             const int64_t g = g_off + row0 + j;
-            cplx lo, di, hi, rhs;
-            row_values(p, row_geom(p, g), g, k, k2, lo, di, hi, rhs);
+            cplx lo = il, di = id, hi = iu, rhs = ib;
+            if (!scalar || g == 0 || g == p.n_elem) row_values(p, row_geom(p, g), g, k, k2, lo, di, hi, rhs);
             const int s = lswz(j);
             sm.a[s] = lo, sm.b[s] = di, sm.c[s] = hi, sm.d[s] = rhs;
         }
