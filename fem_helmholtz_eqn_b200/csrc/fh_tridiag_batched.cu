@@ -121,6 +121,18 @@ __device__ __forceinline__ LocalMap make_map(int64_t n, int rank) {
     return m;
 }
 
+// The two boundary rows of a system are evaluated out of line: inlining their geometry (two element matrices with
+// IEEE divisions) into every unrolled row slot made the fused kernel 6,900 SASS instructions long and
+// instruction-cache bound (ncu: 8 % "no instruction" stalls).
+struct Row4 {
+    cplx lo, b, hi, d;
+};
+__device__ __noinline__ Row4 helm_boundary_row(const Problem1d &p, int64_t g, double k, double k2) {
+    Row4 r;  // returned by value: taking addresses of the caller's register arrays would push them to local memory
+    row_values(p, row_geom(p, g), g, k, k2, r.lo, r.b, r.hi, r.d);
+    return r;
+}
+
 template <class Source>
 __device__ __forceinline__ void helm_row(const Source &src, const HelmState &st, const LocalMap &m, int j, cplx &a,
                                          cplx &b, cplx &c, cplx &d) {
@@ -128,12 +140,14 @@ __device__ __forceinline__ void helm_row(const Source &src, const HelmState &st,
         const int64_t g = m.global_row(j);
         cplx lo, hi;
         if (src.p.h_mode == FH_H_SCALAR) {
-            RowGeom rg = st.g_mid;
-            if (g == 0) rg = st.g_first;
-            if (g == src.p.n_elem) rg = st.g_last;
-            row_values(src.p, rg, g, st.k, st.k2, lo, b, hi, d);
-        } else {
-            row_values(src.p, row_geom(src.p, g), g, st.k, st.k2, lo, b, hi, d);
+            lo = st.il, b = st.id, hi = st.iu, d = st.ib;  // interior rows are all alike (same bits as row_values)
+            if (g == 0 || g == src.p.n_elem) {
+                const Row4 r = helm_boundary_row(src.p, g, st.k, st.k2);
+                lo = r.lo, b = r.b, hi = r.hi, d = r.d;
+            }
+        } else {  // nodal-h: every row has its own geometry
+            const Row4 r = helm_boundary_row(src.p, g, st.k, st.k2);
+            lo = r.lo, b = r.b, hi = r.hi, d = r.d;
         }
         a = m.dir > 0 ? lo : hi;
         c = m.dir > 0 ? hi : lo;
@@ -177,11 +191,7 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
 
     HelmState hs;
     if constexpr (!Source::kStaged) {
-        if (src.p.h_mode == FH_H_SCALAR) {
-            hs.g_first = row_geom(src.p, 0);
-            hs.g_mid = row_geom(src.p, src.p.n_elem > 1 ? 1 : 0);
-            hs.g_last = row_geom(src.p, src.p.n_elem);
-        }
+        if (src.p.h_mode == FH_H_SCALAR) hs.g_mid = row_geom(src.p, src.p.n_elem > 1 ? 1 : 0);
     }
 
     // one elected thread feeds the pipeline: four band tiles by TMA, head rows by cp.async
@@ -211,7 +221,11 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
     uint32_t it = 0;
     for (int64_t sys = first_sys; sys < batch; sys += sys_stride, ++it) {
         const uint32_t parity = it & 1;
-        if constexpr (!Source::kStaged) hs.k = __ldg(src.ks + sys), hs.k2 = __ldg(src.k2s + sys);
+        if constexpr (!Source::kStaged) {
+            hs.k = __ldg(src.ks + sys), hs.k2 = __ldg(src.k2s + sys);
+            if (src.p.h_mode == FH_H_SCALAR && src.p.n_elem >= 2)
+                row_values(src.p, hs.g_mid, 1, hs.k, hs.k2, hs.il, hs.id, hs.iu, hs.ib);
+        }
         if (CLUSTER > 1 && t == 0) mbar_expect_tx(&sm.xchg_bar[parity], 2 * sizeof(cplx));
 
         // ---- bands -> registers ----------------------------------------------------------------

@@ -99,9 +99,10 @@ struct HelmSource {  // fused pipeline: bands are generated, never stored
     static constexpr bool kStaged = false;
 };
 
-struct HelmState {  // per-thread state of the generator (scalar-h mode: three distinct geometries)
-    RowGeom g_first, g_mid, g_last;
+struct HelmState {  // per-thread state of the generator
+    RowGeom g_first, g_mid, g_last;  // scalar-h mode: the three distinct geometries (chain kernel)
     double k, k2;
+    cplx il, id, iu, ib;  // the interior row of the current wavenumber (scalar-h mode), evaluated once per system
 };
 
 // ---------------------------------------------------------------------------------------------- host: tensor maps
