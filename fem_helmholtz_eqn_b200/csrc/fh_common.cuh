@@ -92,6 +92,13 @@ __device__ __forceinline__ void stg_stream(cplx *p, cplx v) {  // write-once glo
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+// 16-byte shared-memory read that keeps its place in program order (volatile asm statements are not reordered
+// against each other): used where the ORDER of reads and arithmetic is part of the design.
+__device__ __forceinline__ cplx lds_volatile(uint32_t addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return mk(v.x, v.y);
+}
 // 16-byte asynchronous global->shared copy (LDGSTS), L2 only.
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src)

@@ -50,37 +50,64 @@ constexpr int kStageRows = kSlots + kHeadMax;  // 2056
 constexpr int kLevelsMax = kM == 8 ? 8 : 9;    // log2(kT)
 constexpr uint32_t kTileBytes = kSlots * sizeof(cplx);  // 32 KB per band tile
 
+constexpr int kH = kT / 2;              // interface rows that survive the cyclic-reduction step
+constexpr int kHalfPad = kH / 2;        // zero rows on either side of a half-width array (largest PCR stride)
+constexpr int kHalfStride = kH + 2 * kHalfPad + 1;  // (+1: the four arrays start on different banks)
+
 struct __align__(1024) BatchedSmem {
     cplx stage[4][kSlots];      // TMA destination: bands of the NEXT system (a, b, c, d), swizzle-128B
     cplx xs[kSlots];            // TMA source: solution of the CURRENT system, swizzle-128B
-    cplx pcr[2][4][kT];         // PCR ping-pong: A, C, D, V  (pcr[1] doubles as the row-0 exchange)
+    cplx row0[3][kT];           // normalised first rows of the chunks (read by the thread above)
+    cplx full[4][kT + 1];       // interface rows A, C, D, V; entry kT is a zero row (and staggers the banks)
+    cplx half[2][4][kHalfStride];  // PCR ping-pong over the odd interface rows, zero rows on both sides
     cplx headst[4][kHeadMax];   // head rows of the next system (cp.async by one thread)
+    cplx cutst[2][4];           // [parity] the cut row: lo, diag, hi, rhs (cp.async by the same thread)
     cplx xchg[2][2];            // [parity][{Y, V}] written by the partner CTA (st.async)
     unsigned long long full_bar;     // mbarrier: band tiles have landed
     unsigned long long xchg_bar[2];  // mbarrier: partner's interface pair has landed
 };
 
+// One PCR / CR node: 1 / (1 - A*Cm - C*Ap) is kept as conj(den) and 1/|den|^2, so that the products with
+// conj(den) run while the reciprocal is still in flight (the chain is den -> |den|^2 -> rcp -> one multiply).
+struct PcrPivot {
+    cplx cden;
+    double s;
+};
+__device__ __forceinline__ PcrPivot pcr_pivot(cplx A, cplx Cm, cplx C, cplx Ap) {
+    double t1r = fma(-A.re, Cm.re, 1.0);
+    t1r = fma(A.im, Cm.im, t1r);
+    double t2r = C.re * Ap.re;
+    t2r = fma(-C.im, Ap.im, t2r);
+    double t1i = A.re * Cm.im;
+    t1i = fma(A.im, Cm.re, t1i);
+    double t2i = C.re * Ap.im;
+    t2i = fma(C.im, Ap.re, t2i);
+    PcrPivot p;
+    p.cden = mk(t1r - t2r, t1i + t2i);  // conj(den): den.im = -(t1i + t2i)
+    p.s = fast_rcp(fma(p.cden.re, p.cden.re, p.cden.im * p.cden.im));
+    return p;
+}
+__device__ __forceinline__ cplx pcr_scale(cplx num, const PcrPivot &p) {  // num / den
+    const cplx m = num * p.cden;
+    return mk(m.re * p.s, m.im * p.s);
+}
+
 // ---------------------------------------------------------------------------------------------- row -> slot maps
-// How the rows of one system map onto one CTA.  Local rows run from the far end (j = 0) to the cut / the
-// system's last row (j = n_loc - 1).  The first `head` rows are "head rows"; the other 8 * chunks rows
-// fill the chunks of threads kT - chunks .. kT - 1 (right-aligned).
+// How the rows of one system map onto the CTAs.  Single CTA: all n rows.  Cluster of two: rank 0 takes the first
+// m = n / 2 rows, rank 1 the LAST m rows in reversed order; for odd n the row in the middle (the "cut row") belongs
+// to neither: both halves couple to its unknown, which is found together with the exchange (one 4097-row system =
+// 2 x 2048 + 1: no leftover rows to eliminate serially -- those cost the reversed CTA 1000 cycles per system).
+// Inside a CTA, local rows run from the far end (j = 0) to the cut (j = n_loc - 1).  The first `head` rows are "head
+// rows"; the other 8 * chunks rows fill the chunks of threads kT - kPer8 * chunks .. kT - 1 (right-aligned).
 struct LocalMap {
     int n_loc, head, chunks;
-    int first_active;  // kT - chunks
+    int first_active;  // kT - kPer8 * chunks
     int64_t g0;        // global row of local row 0
     int dir;           // +1 forward, -1 reversed
-    int box_c1;        // chunk coordinate at which this CTA's TMA box starts (may be negative)
+    int box_c1;        // chunk coordinate at which this CTA's TMA LOAD box starts (may be negative)
     __device__ __forceinline__ int64_t global_row(int j) const { return g0 + (int64_t)dir * j; }
-    // swizzle-128B slot of element i of thread t's chunk in the LOAD tiles (box right-aligned: TMA loads
-    // accept negative start coordinates and zero-fill)
-    __device__ __forceinline__ int slot(int t, int i) const {
-        const int tt = dir > 0 ? t : kT - 1 - t;           // thread chunk in memory order
-        const int r = tt / kPer8;                          // 8-row memory chunk = TMA tile row
-        const int e = (dir > 0 ? i : kM - 1 - i) + kM * (tt % kPer8);
-        return r * 8 + (e ^ (r & 7));
-    }
-    // ... and in the STORE tile: TMA stores trap on negative coordinates (measured, tools/tma_probe.cu), so
-    // the forward half is left-aligned (box starts at chunk 0, the tensor map clips at the half's last chunk)
+    // swizzle-128B slot of element i of thread t's chunk in the STORE tile: TMA stores trap on negative coordinates
+    // (measured, tools/tma_probe.cu), so the tile is left-aligned (box starts at chunk 0; the tensor map clips)
     __device__ __forceinline__ int xs_slot(int t, int i) const {
         const int tt = dir > 0 ? t - first_active : kT - 1 - t;
         const int r = tt / kPer8;
@@ -91,17 +118,22 @@ struct LocalMap {
 
 struct HostMap {  // the same numbers, computed on the host for the tensor maps
     int n_loc[2], head[2], chunks[2];
+    int row0[2];  // first row of the chunk grid of each rank (origin of its tensor maps)
+    int cut;      // 1: row n_loc[0] is the cut row
 };
 __host__ __device__ inline HostMap host_map(int64_t n, int cluster) {
     HostMap m;
+    m.cut = cluster == 2 ? (int)(n & 1) : 0;
     m.n_loc[0] = cluster == 1 ? (int)n : (int)(n / 2);
-    m.n_loc[1] = cluster == 1 ? 0 : (int)(n - n / 2);
+    m.n_loc[1] = cluster == 1 ? 0 : (int)(n / 2);
     for (int r = 0; r < 2; ++r) {
         int c = m.n_loc[r] / 8;          // 8-row memory chunks
         if (c > kChunks8) c = kChunks8;
         m.chunks[r] = c;
         m.head[r] = m.n_loc[r] - c * 8;  // 0..8
     }
+    m.row0[0] = m.head[0];               // rank 0: head rows first, then the chunks
+    m.row0[1] = m.n_loc[0] + m.cut;      // rank 1 (reversed): chunks first in memory, head rows at the far end
     return m;
 }
 
@@ -116,7 +148,7 @@ __device__ __forceinline__ LocalMap make_map(int64_t n, int rank) {
         m.box_c1 = m.chunks - kChunks8;  // tile row r <-> memory chunk r + box_c1 (right-aligned)
     } else {
         m.g0 = n - 1, m.dir = -1;
-        m.box_c1 = h.chunks[0];    // thread t <-> box row kT-1-t <-> memory chunk chunks0 + (kT-1-t)
+        m.box_c1 = 0;                    // thread t <-> tile row kT-1-t <-> memory chunk kT-1-t of rank 1's grid
     }
     return m;
 }
@@ -154,6 +186,39 @@ __device__ __forceinline__ void helm_row(const Source &src, const HelmState &st,
     }
 }
 
+// Development aid (-DFH_TRACE): warp leaders of the first cluster stamp clock64 / globaltimer at the phase
+// boundaries of one iteration; tools/trace_phases.py prints the phase lengths.
+#ifdef FH_TRACE
+__device__ long long *g_trace = nullptr;
+__device__ int g_trace_iter = 0;
+#define FH_TR(k)                                                                                              \
+    do {                                                                                                      \
+        if (g_trace != nullptr && it == (uint32_t)g_trace_iter && blockIdx.x < 2 && (t & 31) == 0) {          \
+            unsigned long long gt__;                                                                          \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt__));                                          \
+            g_trace[((blockIdx.x * 8 + (t >> 5)) * 16 + (k)) * 2] = clock64();                                \
+            g_trace[((blockIdx.x * 8 + (t >> 5)) * 16 + (k)) * 2 + 1] = (long long)gt__;                      \
+        }                                                                                                     \
+    } while (0)
+#else
+#define FH_TR(k) do { } while (0)
+#endif
+
+// any single row in GLOBAL terms (lo = sub-diagonal entry, hi = super-diagonal entry): the cut row of the fused variant
+template <class Source>
+__device__ __forceinline__ Row4 helm_any_row(const Source &src, const HelmState &st, int64_t g) {
+    Row4 r;
+    r.lo = r.b = r.hi = r.d = czero();
+    if constexpr (!Source::kStaged) {
+        if (src.p.h_mode == FH_H_SCALAR && g != 0 && g != src.p.n_elem) {
+            r.lo = st.il, r.b = st.id, r.hi = st.iu, r.d = st.ib;
+        } else {
+            r = helm_boundary_row(src.p, g, st.k, st.k2);
+        }
+    }
+    return r;
+}
+
 // ---------------------------------------------------------------------------------------------- the kernel
 template <int CLUSTER, class Source>
 __global__ void __launch_bounds__(kT, 1)
@@ -177,9 +242,18 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
     const bool active = t >= map.first_active;
 
     // reversed half: sub- and super-diagonal swap roles
-    const CUtensorMap *map_lo = map.dir > 0 ? &maps.dl : &maps.du;
-    const CUtensorMap *map_hi = map.dir > 0 ? &maps.du : &maps.dl;
+    const CUtensorMap *tmaps = maps.band[rank];
+    const CUtensorMap *map_lo = map.dir > 0 ? &tmaps[0] : &tmaps[2];
+    const CUtensorMap *map_hi = map.dir > 0 ? &tmaps[2] : &tmaps[0];
+    const bool has_cut = CLUSTER > 1 && (n & 1);
+    const int64_t cut_row = n / 2;  // (global row of the cut row when has_cut)
 
+    // zero rows that the half-width PCR reads beyond either end of the interface system (never written again)
+    for (int i = t; i < 2 * 4 * kHalfStride; i += kT) {
+        const int c = i % kHalfStride;
+        if (c < kHalfPad || c >= kHalfPad + kH) (&sm.half[0][0][0])[i] = czero();
+    }
+    if (t < 4) sm.full[t][kT] = czero();
     if (t == 0) {
         mbar_init(&sm.full_bar, 1);
         mbar_init(&sm.xchg_bar[0], 1);
@@ -195,14 +269,14 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
     }
 
     // one elected thread feeds the pipeline: four band tiles by TMA, head rows by cp.async
-    auto prefetch = [&](int64_t sys) {
+    auto prefetch = [&](int64_t sys, uint32_t par) {
         if constexpr (Source::kStaged) {
             if (t == map.first_active % kT) {  // the thread that also consumes the head rows
                 mbar_expect_tx(&sm.full_bar, 4 * kTileBytes);
                 tma_load_3d(sm.stage[0], map_lo, 0, map.box_c1, (int)sys, &sm.full_bar);
-                tma_load_3d(sm.stage[1], &maps.d, 0, map.box_c1, (int)sys, &sm.full_bar);
+                tma_load_3d(sm.stage[1], &tmaps[1], 0, map.box_c1, (int)sys, &sm.full_bar);
                 tma_load_3d(sm.stage[2], map_hi, 0, map.box_c1, (int)sys, &sm.full_bar);
-                tma_load_3d(sm.stage[3], &maps.b, 0, map.box_c1, (int)sys, &sm.full_bar);
+                tma_load_3d(sm.stage[3], &tmaps[3], 0, map.box_c1, (int)sys, &sm.full_bar);
                 const cplx *lo = map.dir > 0 ? src.dl : src.du, *hi = map.dir > 0 ? src.du : src.dl;
                 for (int j = 0; j < map.head; ++j) {
                     const int64_t g = sys * n + map.global_row(j);
@@ -211,12 +285,19 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
                     cp_async16(&sm.headst[2][j], hi + g);
                     cp_async16(&sm.headst[3][j], src.b + g);
                 }
+                if (has_cut) {  // (always the memory order lo, diag, hi: the 3x3 cut solve is written in global terms)
+                    const int64_t g = sys * n + cut_row;
+                    cp_async16(&sm.cutst[par][0], src.dl + g);
+                    cp_async16(&sm.cutst[par][1], src.d + g);
+                    cp_async16(&sm.cutst[par][2], src.du + g);
+                    cp_async16(&sm.cutst[par][3], src.b + g);
+                }
                 cp_async_commit();
             }
         }
     };
     const int feeder = map.first_active % kT;  // == first_active, or 0 when the CTA has no chunk at all
-    if (first_sys < batch) prefetch(first_sys);
+    if (first_sys < batch) prefetch(first_sys, 0);
 
     uint32_t it = 0;
     for (int64_t sys = first_sys; sys < batch; sys += sys_stride, ++it) {
@@ -226,37 +307,46 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
             if (src.p.h_mode == FH_H_SCALAR && src.p.n_elem >= 2)
                 row_values(src.p, hs.g_mid, 1, hs.k, hs.k2, hs.il, hs.id, hs.iu, hs.ib);
         }
+        FH_TR(0);
         if (CLUSTER > 1 && t == 0) mbar_expect_tx(&sm.xchg_bar[parity], 2 * sizeof(cplx));
 
-        // ---- bands -> registers ----------------------------------------------------------------
+        // ---- bands -> registers, interleaved with phase 1 -------------------------------------------------------
+        // Phase 1 is the downward elimination inside the chunk; b[i] (i < kM - 1) becomes 1 / pivot.  Row i + 2 is
+        // requested from the staging tiles before step i is computed: issuing all 4 * kM tile reads up front parked
+        // every warp behind the shared-memory queue (1024 wavefronts per CTA) before its first multiply, and the two
+        // phases ran one after the other (2300 cycles) instead of overlapped.
         cplx a[kM], b[kM], c[kM], d[kM];
+        uint32_t tile_addr = 0, tile_x = 0;
         if constexpr (Source::kStaged) {
             mbar_wait(&sm.full_bar, parity);
-            if (active) {
-#pragma unroll
-                for (int i = 0; i < kM; ++i) {
-                    const int s = map.slot(t, i);
-                    a[i] = sm.stage[0][s], b[i] = sm.stage[1][s], c[i] = sm.stage[2][s], d[i] = sm.stage[3][s];
-                }
-            }
-        } else {
-            if (active) {
-#pragma unroll
-                for (int i = 0; i < kM; ++i)
-                    helm_row(src, hs, map, map.head + (t - map.first_active) * kM + i, a[i], b[i], c[i], d[i]);
-            }
+            if (map.head > 0 && t == feeder) cp_async_wait_all();  // the head rows have landed too
+            const int tt = map.dir > 0 ? t : kT - 1 - t;  // thread chunk in memory order
+            const int r = tt / kPer8;                     // 8-row memory chunk = TMA tile row
+            tile_addr = smem_u32(&sm.stage[0][0]) + (uint32_t)r * 128u;
+            tile_x = (uint32_t)(r & 7);
         }
-        if (!active) {
-#pragma unroll
-            for (int i = 0; i < kM; ++i) a[i] = czero(), b[i] = cone(), c[i] = czero(), d[i] = czero();
-        }
-        if (map.head == 0 && t == map.first_active) a[0] = czero();  // local row 0: nothing above it
-        if (CLUSTER == 1 && t == kT - 1) c[kM - 1] = czero();        // last row of the system
+        FH_TR(1);
+        auto load_row = [&](int i) {
+            if (!active) {
+                a[i] = czero(), b[i] = cone(), c[i] = czero(), d[i] = czero();
+            } else if constexpr (Source::kStaged) {
+                const int tt = map.dir > 0 ? t : kT - 1 - t;
+                const uint32_t e = (uint32_t)((map.dir > 0 ? i : kM - 1 - i) + kM * (tt % kPer8));
+                const uint32_t ad = tile_addr + ((e ^ tile_x) << 4);
+                a[i] = lds_volatile(ad), b[i] = lds_volatile(ad + kTileBytes);
+                c[i] = lds_volatile(ad + 2 * kTileBytes), d[i] = lds_volatile(ad + 3 * kTileBytes);
+            } else {
+                helm_row(src, hs, map, map.head + (t - map.first_active) * kM + i, a[i], b[i], c[i], d[i]);
+            }
+            if (i == 0 && map.head == 0 && t == map.first_active) a[0] = czero();  // local row 0: nothing above it
+            if (i == kM - 1 && CLUSTER == 1 && t == kT - 1) c[kM - 1] = czero();     // last row of the system
+        };
+        load_row(0);
+        load_row(1);
 
         // ---- head rows (far end, at most 8): serial Thomas by one thread, folded into its row 0 ------
         cplx hcp[kHeadMax], hdp[kHeadMax];
         if (map.head > 0 && t == feeder) {
-            if constexpr (Source::kStaged) cp_async_wait_all();
             cplx cp = czero(), dp = czero();
 #pragma unroll
             for (int j = 0; j < kHeadMax; ++j) {
@@ -281,22 +371,24 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
                 a[0] = czero();
             }
         }
-        if constexpr (Source::kStaged) {
-            __syncthreads();  // every thread has drained the staging tiles ...
-            if (sys + sys_stride < batch) prefetch(sys + sys_stride);  // ... refill them
-        }
-
-        // ---- phase 1: downward elimination inside the chunk; b[i] (i < 7) becomes 1 / pivot --------
-        const cplx a7o = a[kM - 1], b7o = b[kM - 1], c7o = c[kM - 1], d7o = d[kM - 1];  // for the probe
         b[0] = frecip(b[0]);
+        cplx a7o, b7o, c7o, d7o;  // the original interface row, for the probe
 #pragma unroll
         for (int i = 1; i < kM; ++i) {
+            if (i + 1 < kM) load_row(i + 1);
+            if (i == kM - 1) a7o = a[i], b7o = b[i], c7o = c[i], d7o = d[i];
             const cplx w = a[i] * b[i - 1];
             b[i] = nmsub(b[i], w, c[i - 1]);
             d[i] = nmsub(d[i], w, d[i - 1]);
             a[i] = -(w * a[i - 1]);
             if (i < kM - 1) b[i] = frecip(b[i]);
         }
+        FH_TR(2);
+        if constexpr (Source::kStaged) {
+            __syncthreads();  // every thread has drained the staging tiles ...
+            if (sys + sys_stride < batch) prefetch(sys + sys_stride, parity ^ 1);  // ... refill them
+        }
+        FH_TR(3);
         // ---- phase 2: upward elimination; afterwards row i < 7 couples to x_left and x_7 only -------
 #pragma unroll
         for (int i = kM - 3; i >= 0; --i) {
@@ -306,16 +398,18 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
             c[i] = -(w * c[i + 1]);
         }
         // ---- interface row: eliminate the next chunk's first unknown with its (normalised) row 0 -----
-        sm.pcr[1][0][t] = a[0] * b[0];
-        sm.pcr[1][1][t] = c[0] * b[0];
-        sm.pcr[1][2][t] = d[0] * b[0];
+        FH_TR(4);
+        sm.row0[0][t] = a[0] * b[0];
+        sm.row0[1][t] = c[0] * b[0];
+        sm.row0[2][t] = d[0] * b[0];
         __syncthreads();
+        FH_TR(5);
         cplx rA, rC, rD, rV;
         {
             cplx rb = b[kM - 1];
             rA = a[kM - 1], rC = czero(), rD = d[kM - 1], rV = czero();
             if (t < kT - 1) {
-                const cplx nA = sm.pcr[1][0][t + 1], nC = sm.pcr[1][1][t + 1], nD = sm.pcr[1][2][t + 1];
+                const cplx nA = sm.row0[0][t + 1], nC = sm.row0[1][t + 1], nD = sm.row0[2][t + 1];
                 rb = nmsub(rb, c[kM - 1], nA);
                 rC = -(c[kM - 1] * nC);
                 rD = nmsub(rD, c[kM - 1], nD);
@@ -325,63 +419,114 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
             const cplx inv = frecip(rb);
             rA = rA * inv, rC = rC * inv, rD = rD * inv, rV = rV * inv;
         }
-        // ---- PCR over the CTA's 256 interface rows (unit diagonal) ------------------------------------
-        int cur = 0;
-        sm.pcr[0][0][t] = rA, sm.pcr[0][1][t] = rC, sm.pcr[0][2][t] = rD;
-        if (CLUSTER > 1) sm.pcr[0][3][t] = rV;
-        __syncthreads();
-        for (int lv = 0, s = 1; lv < levels; ++lv, s <<= 1) {
-            const bool last = lv == levels - 1;
-            cplx Am = czero(), Cm = czero(), Dm = czero(), Vm = czero();
-            cplx Ap = czero(), Cp = czero(), Dp = czero(), Vp = czero();
-            if (t - s >= 0) {
-                Am = sm.pcr[cur][0][t - s], Cm = sm.pcr[cur][1][t - s], Dm = sm.pcr[cur][2][t - s];
-                if (CLUSTER > 1) Vm = sm.pcr[cur][3][t - s];
-            }
-            if (t + s < kT) {
-                Ap = sm.pcr[cur][0][t + s], Cp = sm.pcr[cur][1][t + s], Dp = sm.pcr[cur][2][t + s];
-                if (CLUSTER > 1) Vp = sm.pcr[cur][3][t + s];
-            }
-            const cplx inv = frecip(nmsub(nmsub(cone(), rA, Cm), rC, Ap));
-            const cplx nD = nmsub(nmsub(rD, rA, Dm), rC, Dp) * inv;
-            cplx nV = czero();
-            if (CLUSTER > 1) nV = nmsub(nmsub(rV, rA, Vm), rC, Vp) * inv;
-            cur ^= 1;
-            if (!last) {  // the last level leaves no couplings: A and C are not needed any more
-                const cplx nA = -((rA * Am) * inv);
-                const cplx nC = -((rC * Cp) * inv);
-                rA = nA, rC = nC;
-                sm.pcr[cur][0][t] = rA, sm.pcr[cur][1][t] = rC;
-            }
-            rD = nD, rV = nV;
-            sm.pcr[cur][2][t] = rD;
-            if (CLUSTER > 1) sm.pcr[cur][3][t] = rV;
-            __syncthreads();
+        // ---- interface system: kT unit-diagonal rows  x_t + A x_{t-1} + C x_{t+1} = D - V x_partner ----------------
+        // The full-width 8-level PCR was bound by the fp64 pipe (70 DP instructions per row and level) and by
+        // shared-memory bandwidth.  Now: (1) ONE cyclic-reduction step keeps the odd rows only (the last row, which
+        // holds the cut unknown, is odd); (2) the kT/2 survivors are solved by PCR with TWO threads per row: role 0
+        // updates {D, A}, role 1 updates {V, C} -- the same instruction stream, operands picked by array index, so
+        // there is no divergence; (3) the even rows follow from their own equation, which never left the registers.
+        sm.full[0][t] = rA, sm.full[1][t] = rC, sm.full[2][t] = rD, sm.full[3][t] = rV;
+        FH_TR(13);
+        if (t == 0) tma_store_wait_read();  // the previous system's TMA store has finished reading xs
+        if constexpr (Source::kStaged) {
+            if (has_cut && map.head == 0 && t == feeder) cp_async_wait_all();  // the cut row (read after the exchange)
         }
-        // now x_last(t) = rD - rV * x_partner
-        cplx X = rD, x_partner = czero();
+        FH_TR(14);
+        __syncthreads();
+        FH_TR(6);
+        int cur = 0;
+        cplx qA, qC, xv;   // PCR state of this thread's (row, role): both couplings, and D (role 0) or V (role 1)
+        int j, role;
+        {   // level 0 (cyclic reduction): thread pair (t, t^1) reduces the odd row r = t | 1
+            const int r = t | 1;
+            role = t & 1, j = t >> 1;
+            const int va = 2 + role;
+            const cplx oA = sm.full[0][r], oC = sm.full[1][r], oX = sm.full[va][r];
+            const cplx Cm = sm.full[1][r - 1], Ap = sm.full[0][r + 1];  // (row kT is a zero row)
+            const cplx Xm = sm.full[va][r - 1], Xp = sm.full[va][r + 1];
+            const cplx Qn = role ? sm.full[1][r + 1] : sm.full[0][r - 1];
+            const PcrPivot pv = pcr_pivot(oA, Cm, oC, Ap);
+            cplx *H = sm.half[0][0] + kHalfPad + j;
+            H[va * kHalfStride] = pcr_scale(nmsub(nmsub(oX, oA, Xm), oC, Xp), pv);
+            H[role * kHalfStride] = -pcr_scale((role ? oC : oA) * Qn, pv);
+        }
+        __syncthreads();
+        FH_TR(7);
+        j = t & (kH - 1), role = t / kH;  // levels >= 1: role is uniform per warp
+        const int va = 2 + role;
+        {
+            const cplx *H = sm.half[0][0] + kHalfPad + j;
+            qA = H[0], qC = H[kHalfStride], xv = H[va * kHalfStride];
+        }
+        for (int lv = 0, s = 1; lv < levels; ++lv, s <<= 1) {
+            const cplx *H = sm.half[cur][0] + kHalfPad + j;  // rows beyond either end read as zero rows
+            const cplx Cm = H[kHalfStride - s], Ap = H[s];
+            const cplx Xm = H[va * kHalfStride - s], Xp = H[va * kHalfStride + s];
+            const cplx Qn = H[role * kHalfStride + (role ? s : -s)];
+            const PcrPivot pv = pcr_pivot(qA, Cm, qC, Ap);
+            xv = pcr_scale(nmsub(nmsub(xv, qA, Xm), qC, Xp), pv);
+            const cplx nQ = -pcr_scale((role ? qC : qA) * Qn, pv);
+            cur ^= 1;
+            cplx *G = sm.half[cur][0] + kHalfPad + j;
+            G[va * kHalfStride] = xv;
+            G[role * kHalfStride] = nQ;  // (not needed after the last level; kept for uniformity)
+            __syncthreads();
+            if (role) qC = nQ, qA = G[0];
+            else qA = nQ, qC = G[kHalfStride];
+        }
+        FH_TR(8);
+        // now x(row 2j+1) = D_j - V_j * x_partner, with D, V in half[cur]
+        const cplx *HD = sm.half[cur][2] + kHalfPad, *HV = sm.half[cur][3] + kHalfPad;
+        // x_partner: the unknown the V column couples to -- the partner's cut-side unknown, or the cut row's
+        cplx x_partner = czero();
         if (CLUSTER > 1) {
-            if (t == kT - 1) {
+            if (j == kH - 1) {  // two threads: role 0 sends D, role 1 sends V
                 const uint32_t rbar = map_to_rank(&sm.xchg_bar[parity], rank ^ 1);
-                st_async_remote(map_to_rank(&sm.xchg[parity][0], rank ^ 1), rD, rbar);
-                st_async_remote(map_to_rank(&sm.xchg[parity][1], rank ^ 1), rV, rbar);
+                st_async_remote(map_to_rank(&sm.xchg[parity][role], rank ^ 1), xv, rbar);
+            }
+            cplx cl, cb, ch, cd;  // the cut row: lo x(rank 0 side) + diag x_cut + hi x(rank 1 side) = rhs
+            if (has_cut) {
+                if constexpr (Source::kStaged) {
+                    cl = sm.cutst[parity][0], cb = sm.cutst[parity][1], ch = sm.cutst[parity][2], cd = sm.cutst[parity][3];
+                } else {
+                    const Row4 r = helm_any_row(src, hs, cut_row);
+                    cl = r.lo, cb = r.b, ch = r.hi, cd = r.d;
+                }
             }
             mbar_wait(&sm.xchg_bar[parity], (it >> 1) & 1);
             const cplx Yp = sm.xchg[parity][0], Vp = sm.xchg[parity][1];
-            const cplx Ym = sm.pcr[cur][2][kT - 1], Vm = sm.pcr[cur][3][kT - 1];
-            // x_me = Ym - Vm x_p ; x_p = Yp - Vp x_me
-            const cplx x_me = nmsub(Ym, Vm, Yp) * frecip(nmsub(cone(), Vm, Vp));
-            const cplx x_p = nmsub(Yp, Vp, x_me);
-            X = nmsub(rD, rV, x_p);
-            x_partner = x_p;
+            const cplx Ym = HD[kH - 1], Vm = HV[kH - 1];
+            if (has_cut) {
+                // x_0 = Y0 - V0 x_cut, x_1 = Y1 - V1 x_cut (subscript = cluster rank); evaluated in the same order
+                // on both CTAs, so both obtain the same bits
+                const cplx Y0 = rank == 0 ? Ym : Yp, V0 = rank == 0 ? Vm : Vp;
+                const cplx Y1 = rank == 0 ? Yp : Ym, V1 = rank == 0 ? Vp : Vm;
+                const cplx den = nmsub(nmsub(cb, cl, V0), ch, V1);
+                x_partner = nmsub(nmsub(cd, cl, Y0), ch, Y1) * frecip(den);
+                if (rank == 0 && t == kT - 1) stg_stream(u + sys * n + cut_row, x_partner);
+            } else {
+                // x_me = Ym - Vm x_p ; x_p = Yp - Vp x_me
+                const cplx x_me = nmsub(Ym, Vm, Yp) * frecip(nmsub(cone(), Vm, Vp));
+                x_partner = nmsub(Yp, Vp, x_me);
+            }
         }
-        sm.pcr[cur ^ 1][0][t] = X;
-        if (t == 0) tma_store_wait_read();  // the previous system's TMA store has finished reading xs
-        __syncthreads();
-        const cplx xl = t > 0 ? sm.pcr[cur ^ 1][0][t - 1] : czero();
+        FH_TR(9);
+        cplx X, xl;
+        {
+            const int jo = t >> 1;  // odd t: own row; even t: the odd row above (t + 1)
+            const cplx Xhi = nmsub(HD[jo], HV[jo], x_partner);
+            if (t & 1) {
+                X = Xhi;
+            } else {
+                xl = nmsub(HD[jo - 1], HV[jo - 1], x_partner);  // (t == 0 reads the zero row: xl = 0)
+                X = nmsub(nmsub(rD, rA, xl), rC, Xhi);
+            }
+            const double ure = __shfl_up_sync(0xffffffffu, X.re, 1), uim = __shfl_up_sync(0xffffffffu, X.im, 1);
+            if (t & 1) xl = mk(ure, uim);
+        }
 
         // ---- back-substitution + staging -----------------------------------------------------------
-        bool bad = !cfinite(X);
+        bool bad = !cfinite(X) || !cfinite(x_partner);
         cplx x0 = X, x6 = X;
 #pragma unroll
         for (int i = 0; i < kM; ++i) {
@@ -404,11 +549,13 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
                 }
             }
         }
+        FH_TR(10);
         fence_proxy_async();  // make this thread's xs writes visible to the TMA engine
         const int any_nonfinite = __syncthreads_or(bad ? 1 : 0);  // (returns a truth value, not a bit-wise OR)
+        FH_TR(11);
         if (t == 0) {
             if (map.chunks > 0) {  // (a system shorter than one chunk consists of head rows only)
-                tma_store_3d(rank == 0 ? &umaps.r0 : &umaps.r1, 0, rank == 0 ? 0 : map.box_c1, (int)sys, sm.xs);
+                tma_store_3d(&umaps.r[rank], 0, 0, (int)sys, sm.xs);
                 tma_store_commit();
             }
             // status[] is zeroed by the host wrapper before the launch; both cluster ranks may flag it
@@ -423,6 +570,7 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
             // rare: one global atomic per affected warp (status[] was zeroed by the host wrapper)
             if (__any_sync(0xffffffffu, off) && (t & 31) == 0 && status != nullptr) atomicOr(&status[sys], 2);
         }
+        FH_TR(12);
     }
     if (t == 0) tma_store_wait_read();
     if (CLUSTER > 1) cg::this_cluster().sync();  // no CTA leaves while its partner may still address it
@@ -442,8 +590,10 @@ static int ceil_log2(int v) {
 static int pcr_levels(int64_t n, int cluster) {
     const HostMap h = host_map(n, cluster);
     const int chunks = h.chunks[0] > h.chunks[1] ? h.chunks[0] : h.chunks[1];
-    const int lv = ceil_log2(chunks < 1 ? 1 : kPer8 * chunks);  // interface rows = thread chunks
-    return lv > kLevelsMax ? kLevelsMax : lv;
+    const int rows = chunks < 1 ? 1 : kPer8 * chunks;  // active interface rows = thread chunks (the last `rows` threads)
+    // level 0 is the cyclic-reduction step; PCR then runs over the odd rows among the active ones
+    const int lv = ceil_log2((rows + 1) / 2);
+    return lv > kLevelsMax - 1 ? kLevelsMax - 1 : lv;
 }
 
 template <int CLUSTER, class Source>
@@ -460,22 +610,18 @@ static int launch_batched(const Source &src, const cplx *const bands[4], cplx *u
         return FH_E_UNSUPPORTED;
     }
     const HostMap h = host_map(n, CLUSTER);
-    const int chunks_total = h.chunks[0] + h.chunks[1];
     TensorMaps maps;
     StoreMaps umaps;
     memset(&maps, 0, sizeof(maps));
     memset(&umaps, 0, sizeof(umaps));
-    int rc = make_tensor_map(&umaps.r0, u, n, batch, h.head[0], h.chunks[0], kChunks8);
-    if (rc != FH_OK) return rc;
-    if (CLUSTER > 1) {
-        rc = make_tensor_map(&umaps.r1, u, n, batch, h.head[0], chunks_total, kChunks8);
+    for (int r = 0; r < CLUSTER; ++r) {  // every rank sees only its own chunks: loads zero-fill, stores clip
+        int rc = make_tensor_map(&umaps.r[r], u, n, batch, h.row0[r], h.chunks[r], kChunks8);
         if (rc != FH_OK) return rc;
-    }
-    if (Source::kStaged) {
-        CUtensorMap *dst[4] = {&maps.dl, &maps.d, &maps.du, &maps.b};
-        for (int i = 0; i < 4; ++i) {
-            rc = make_tensor_map(dst[i], bands[i], n, batch, h.head[0], chunks_total, kChunks8);
-            if (rc != FH_OK) return rc;
+        if (Source::kStaged) {
+            for (int i = 0; i < 4; ++i) {
+                rc = make_tensor_map(&maps.band[r][i], bands[i], n, batch, h.row0[r], h.chunks[r], kChunks8);
+                if (rc != FH_OK) return rc;
+            }
         }
     }
     FH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -498,17 +644,6 @@ static int launch_batched(const Source &src, const cplx *const bands[4], cplx *u
     return FH_OK;
 }
 
-// from fh_tridiag_chain.cu: 4-CTA x 128-thread variant, two CTAs per SM
-bool chain_covers(int64_t n);
-int chain_solve_bands(const cplx *dl, const cplx *d, const cplx *du, const cplx *b, cplx *u, int64_t n, int64_t batch,
-                      int32_t *status, cudaStream_t stream);
-int chain_solve_helm(const HelmSource &src, cplx *u, int64_t n, int64_t batch, int32_t *status, cudaStream_t stream);
-// FH_TRIDIAG_KERNEL=pair|chain picks the cluster kernel for systems both cover (development switch)
-static bool prefer_chain() {
-    const char *e = getenv("FH_TRIDIAG_KERNEL");
-    return e != nullptr && strcmp(e, "chain") == 0;
-}
-
 // from fh_tridiag_large.cu
 int solve_large(const cplx *dl, const cplx *d, const cplx *du, const cplx *b, cplx *u, int64_t n,
                 int32_t *status, void *workspace, size_t workspace_bytes, cudaStream_t stream);
@@ -520,7 +655,6 @@ int batched_solve_bands(const cplx *dl, const cplx *d, const cplx *du, const cpl
         set_error("batched kernel handles n <= %lld", (long long)kBatchedMaxN);
         return FH_E_UNSUPPORTED;
     }
-    if (prefer_chain() && chain_covers(n)) return chain_solve_bands(dl, d, du, b, u, n, batch, status, stream);
     BandSource src;
     src.dl = dl, src.d = d, src.du = du, src.b = b;
     const cplx *const bands[4] = {dl, d, du, b};
@@ -531,6 +665,14 @@ int batched_solve_bands(const cplx *dl, const cplx *d, const cplx *du, const cpl
 }  // namespace fh
 
 extern "C" {
+
+#ifdef FH_TRACE
+__attribute__((visibility("default"))) int fh_debug_set_trace(long long *buf, int iter) {
+    cudaMemcpyToSymbol(fh::g_trace, &buf, sizeof(buf));
+    cudaMemcpyToSymbol(fh::g_trace_iter, &iter, sizeof(iter));
+    return (int)cudaGetLastError();
+}
+#endif
 
 int64_t fh_tridiag_batched_max_n(void) { return fh::kBatchedMaxN; }
 
@@ -582,7 +724,6 @@ int fh_helmholtz1d_sweep_fused_c128(const fh_problem1d *prob_host, const double 
     src.ks = ks, src.k2s = k2s;
     const cplx *const none[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (prefer_chain() && chain_covers(n)) return chain_solve_helm(src, reinterpret_cast<cplx *>(u), n, n_k, status, st);
     if (n <= kStageRows) return launch_batched<1>(src, none, reinterpret_cast<cplx *>(u), n, n_k, status, st);
     return launch_batched<2>(src, none, reinterpret_cast<cplx *>(u), n, n_k, status, st);
 }

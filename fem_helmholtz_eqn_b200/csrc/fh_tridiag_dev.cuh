@@ -1,5 +1,4 @@
-// Device / host helpers shared by the cluster solvers (fh_tridiag_batched.cu: 2 CTAs x 256 threads per system;
-// fh_tridiag_chain.cu: 4 CTAs x 128 threads per system, two CTAs resident per SM).
+// Device / host helpers of the cluster solver (fh_tridiag_batched.cu: 2 CTAs x 256 threads per system).
 #pragma once
 #include <cuda.h>
 #include <string.h>
@@ -29,6 +28,18 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
         "r"(parity)
         : "memory");
 }
+// spinning variant (test_wait does not suspend the warp): lower wake-up latency for waits that are known to be short
+__device__ __forceinline__ void mbar_spin(unsigned long long *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "SPIN_%=:\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra SPIN_%=;\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2,
                                             unsigned long long *bar) {
     asm volatile(
@@ -50,6 +61,10 @@ __device__ __forceinline__ void st_async_remote(uint32_t remote_addr, cplx v, ui
                      remote_addr),
                  "d"(v.re), "d"(v.im), "r"(remote_bar)
                  : "memory");
+}
+// barrier over the first `threads` threads of the CTA (a whole number of warps), hardware barrier `id` (1..15)
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 __device__ __forceinline__ uint32_t map_to_rank(const void *p, uint32_t rank) {
     uint32_t r;
@@ -81,11 +96,11 @@ constexpr double kProbeTol = 5e-14;
 __device__ __forceinline__ double abs1(cplx z) { return fabs(z.re) + fabs(z.im); }
 
 // ---------------------------------------------------------------------------------------------- band sources
-struct TensorMaps {  // built by the host per launch; live in kernel parameter space
-    CUtensorMap dl, d, du, b;
+struct TensorMaps {  // built by the host per launch; live in kernel parameter space.  [cluster rank][dl, d, du, b]
+    CUtensorMap band[2][4];
 };
-struct StoreMaps {   // solution tensor as seen by cluster rank 0 (clipped at the cut) and rank 1
-    CUtensorMap r0, r1;
+struct StoreMaps {   // solution tensor as seen by cluster rank 0 and rank 1 (each clipped to its own chunks)
+    CUtensorMap r[2];
 };
 
 struct BandSource {  // staged pipeline: bands live in global memory
@@ -100,7 +115,7 @@ struct HelmSource {  // fused pipeline: bands are generated, never stored
 };
 
 struct HelmState {  // per-thread state of the generator
-    RowGeom g_first, g_mid, g_last;  // scalar-h mode: the three distinct geometries (chain kernel)
+    RowGeom g_mid;  // scalar-h mode: geometry of the interior rows
     double k, k2;
     cplx il, id, iu, ib;  // the interior row of the current wavenumber (scalar-h mode), evaluated once per system
 };
@@ -122,8 +137,8 @@ static inline EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// Tensor view of one band / solution array: [batch][chunks][16 doubles], origin at row `head0` of system 0.
-static inline int make_tensor_map(CUtensorMap *out, const cplx *base, int64_t n, int64_t batch, int head0, int chunks_total,
+// Tensor view of one band / solution array: [batch][chunks][16 doubles], origin at row `row0` of system 0.
+static inline int make_tensor_map(CUtensorMap *out, const cplx *base, int64_t n, int64_t batch, int row0, int chunks_total,
                                   int box_rows) {
     EncodeTiledFn enc = encode_fn();
     if (enc == nullptr) {
@@ -134,7 +149,7 @@ static inline int make_tensor_map(CUtensorMap *out, const cplx *base, int64_t n,
     const cuuint64_t strides[2] = {128, (cuuint64_t)n * sizeof(cplx)};
     const cuuint32_t box[3] = {16, (cuuint32_t)box_rows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
-    void *addr = const_cast<cplx *>(base) + head0;
+    void *addr = const_cast<cplx *>(base) + row0;
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, addr, dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
