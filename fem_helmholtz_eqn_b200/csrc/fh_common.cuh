@@ -99,6 +99,9 @@ __device__ __forceinline__ cplx lds_volatile(uint32_t addr) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
     return mk(v.x, v.y);
 }
+__device__ __forceinline__ void sts_volatile(uint32_t addr, cplx v) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(v.re), "d"(v.im) : "memory");
+}
 // 16-byte asynchronous global->shared copy (LDGSTS), L2 only.
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src)

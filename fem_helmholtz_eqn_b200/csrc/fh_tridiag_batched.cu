@@ -435,7 +435,6 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
         __syncthreads();
         FH_TR(6);
         int cur = 0;
-        cplx qA, qC, xv;   // PCR state of this thread's (row, role): both couplings, and D (role 0) or V (role 1)
         int j, role;
         {   // level 0 (cyclic reduction): thread pair (t, t^1) reduces the odd row r = t | 1
             const int r = t | 1;
@@ -454,25 +453,28 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
         FH_TR(7);
         j = t & (kH - 1), role = t / kH;  // levels >= 1: role is uniform per warp
         const int va = 2 + role;
-        {
-            const cplx *H = sm.half[0][0] + kHalfPad + j;
-            qA = H[0], qC = H[kHalfStride], xv = H[va * kHalfStride];
-        }
-        for (int lv = 0, s = 1; lv < levels; ++lv, s <<= 1) {
-            const cplx *H = sm.half[cur][0] + kHalfPad + j;  // rows beyond either end read as zero rows
-            const cplx Cm = H[kHalfStride - s], Ap = H[s];
-            const cplx Xm = H[va * kHalfStride - s], Xp = H[va * kHalfStride + s];
-            const cplx Qn = H[role * kHalfStride + (role ? s : -s)];
-            const PcrPivot pv = pcr_pivot(qA, Cm, qC, Ap);
-            xv = pcr_scale(nmsub(nmsub(xv, qA, Xm), qC, Xp), pv);
-            const cplx nQ = -pcr_scale((role ? qC : qA) * Qn, pv);
+        // "own" = the coupling this thread updates (A for role 0, C for role 1), "oth" = the one its partner thread
+        // updates.  Both threads of a row evaluate den = 1 - A * C(j-s) - C * A(j+s) in the SAME order: their pivots
+        // must agree to the last bit, or the row ends up scaled inconsistently (that cost two digits of backward
+        // error near small pivots).  Rows beyond either end read as zero rows.
+        constexpr uint32_t kArr = kHalfStride * sizeof(cplx);
+        const uint32_t hb0 = smem_u32(&sm.half[0][0][kHalfPad + j]), hb1 = smem_u32(&sm.half[1][0][kHalfPad + j]);
+        const uint32_t o_val = va * kArr, o_own = role * kArr;
+        cplx own = lds_volatile(hb0 + o_own), xv = lds_volatile(hb0 + o_val);
+#pragma unroll 1
+        for (int lv = 0, sb = (int)sizeof(cplx); lv < levels; ++lv, sb <<= 1) {
+            const uint32_t rd = cur ? hb1 : hb0, wr = cur ? hb0 : hb1;
+            const cplx Cm = lds_volatile(rd + kArr - sb), Ap = lds_volatile(rd + sb);
+            const cplx Aj = lds_volatile(rd), Cj = lds_volatile(rd + kArr);  // (one of them is `own`: same bits)
+            const cplx Xm = lds_volatile(rd + o_val - sb), Xp = lds_volatile(rd + o_val + sb);
+            const cplx Q = lds_volatile(rd + o_own + (role ? sb : -sb));  // own array, own side
+            const PcrPivot pv = pcr_pivot(Aj, Cm, Cj, Ap);
+            xv = pcr_scale(nmsub(nmsub(xv, Aj, Xm), Cj, Xp), pv);
+            own = -pcr_scale(own * Q, pv);
+            sts_volatile(wr + o_val, xv);
+            sts_volatile(wr + o_own, own);  // (not needed after the last level; kept for uniformity)
             cur ^= 1;
-            cplx *G = sm.half[cur][0] + kHalfPad + j;
-            G[va * kHalfStride] = xv;
-            G[role * kHalfStride] = nQ;  // (not needed after the last level; kept for uniformity)
             __syncthreads();
-            if (role) qC = nQ, qA = G[0];
-            else qA = nQ, qC = G[kHalfStride];
         }
         FH_TR(8);
         // now x(row 2j+1) = D_j - V_j * x_partner, with D, V in half[cur]
