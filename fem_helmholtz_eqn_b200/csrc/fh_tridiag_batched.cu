@@ -61,7 +61,6 @@ struct __align__(1024) BatchedSmem {
     cplx full[4][kT + 1];       // interface rows A, C, D, V; entry kT is a zero row (and staggers the banks)
     cplx half[2][4][kHalfStride];  // PCR ping-pong over the odd interface rows, zero rows on both sides
     cplx headst[4][kHeadMax];   // head rows of the next system (cp.async by one thread)
-    cplx cutst[2][4];           // [parity] the cut row: lo, diag, hi, rhs (cp.async by the same thread)
     cplx xchg[2][2];            // [parity][{Y, V}] written by the partner CTA (st.async)
     unsigned long long full_bar;     // mbarrier: band tiles have landed
     unsigned long long xchg_bar[2];  // mbarrier: partner's interface pair has landed
@@ -269,7 +268,7 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
     }
 
     // one elected thread feeds the pipeline: four band tiles by TMA, head rows by cp.async
-    auto prefetch = [&](int64_t sys, uint32_t par) {
+    auto prefetch = [&](int64_t sys) {
         if constexpr (Source::kStaged) {
             if (t == map.first_active % kT) {  // the thread that also consumes the head rows
                 mbar_expect_tx(&sm.full_bar, 4 * kTileBytes);
@@ -285,19 +284,12 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
                     cp_async16(&sm.headst[2][j], hi + g);
                     cp_async16(&sm.headst[3][j], src.b + g);
                 }
-                if (has_cut) {  // (always the memory order lo, diag, hi: the 3x3 cut solve is written in global terms)
-                    const int64_t g = sys * n + cut_row;
-                    cp_async16(&sm.cutst[par][0], src.dl + g);
-                    cp_async16(&sm.cutst[par][1], src.d + g);
-                    cp_async16(&sm.cutst[par][2], src.du + g);
-                    cp_async16(&sm.cutst[par][3], src.b + g);
-                }
                 cp_async_commit();
             }
         }
     };
     const int feeder = map.first_active % kT;  // == first_active, or 0 when the CTA has no chunk at all
-    if (first_sys < batch) prefetch(first_sys, 0);
+    if (first_sys < batch) prefetch(first_sys);
 
     uint32_t it = 0;
     for (int64_t sys = first_sys; sys < batch; sys += sys_stride, ++it) {
@@ -386,7 +378,7 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
         FH_TR(2);
         if constexpr (Source::kStaged) {
             __syncthreads();  // every thread has drained the staging tiles ...
-            if (sys + sys_stride < batch) prefetch(sys + sys_stride, parity ^ 1);  // ... refill them
+            if (sys + sys_stride < batch) prefetch(sys + sys_stride);  // ... refill them
         }
         FH_TR(3);
         // ---- phase 2: upward elimination; afterwards row i < 7 couples to x_left and x_7 only -------
@@ -428,12 +420,23 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
         sm.full[0][t] = rA, sm.full[1][t] = rC, sm.full[2][t] = rD, sm.full[3][t] = rV;
         FH_TR(13);
         if (t == 0) tma_store_wait_read();  // the previous system's TMA store has finished reading xs
-        if constexpr (Source::kStaged) {
-            if (has_cut && map.head == 0 && t == feeder) cp_async_wait_all();  // the cut row (read after the exchange)
-        }
         FH_TR(14);
         __syncthreads();
         FH_TR(6);
+        // The cut row (lo x(rank 0 side) + diag x_cut + hi x(rank 1 side) = rhs) is needed right after the exchange:
+        // requested here (its sectors were just fetched by the tile loads of one of the two CTAs: an L2 hit), so the
+        // latency hides behind the PCR.
+        cplx cl = czero(), cb = cone(), ch = czero(), cd = czero();
+        if (has_cut) {
+            if constexpr (Source::kStaged) {
+                const int64_t g = sys * n + cut_row;
+                cl = ldg_stream(src.dl + g), cb = ldg_stream(src.d + g), ch = ldg_stream(src.du + g);
+                cd = ldg_stream(src.b + g);
+            } else {
+                const Row4 r = helm_any_row(src, hs, cut_row);
+                cl = r.lo, cb = r.b, ch = r.hi, cd = r.d;
+            }
+        }
         int cur = 0;
         int j, role;
         {   // level 0 (cyclic reduction): thread pair (t, t^1) reduces the odd row r = t | 1
@@ -485,15 +488,6 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
             if (j == kH - 1) {  // two threads: role 0 sends D, role 1 sends V
                 const uint32_t rbar = map_to_rank(&sm.xchg_bar[parity], rank ^ 1);
                 st_async_remote(map_to_rank(&sm.xchg[parity][role], rank ^ 1), xv, rbar);
-            }
-            cplx cl, cb, ch, cd;  // the cut row: lo x(rank 0 side) + diag x_cut + hi x(rank 1 side) = rhs
-            if (has_cut) {
-                if constexpr (Source::kStaged) {
-                    cl = sm.cutst[parity][0], cb = sm.cutst[parity][1], ch = sm.cutst[parity][2], cd = sm.cutst[parity][3];
-                } else {
-                    const Row4 r = helm_any_row(src, hs, cut_row);
-                    cl = r.lo, cb = r.b, ch = r.hi, cd = r.d;
-                }
             }
             mbar_wait(&sm.xchg_bar[parity], (it >> 1) & 1);
             const cplx Yp = sm.xchg[parity][0], Vp = sm.xchg[parity][1];
