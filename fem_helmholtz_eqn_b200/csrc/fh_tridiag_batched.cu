@@ -522,16 +522,24 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
         }
 
         // ---- back-substitution + staging -----------------------------------------------------------
+        // Non-finite values: a vanishing pivot anywhere in this thread's chunk turns into a NaN that travels down the
+        // elimination chain into the thread's own interface row (0 * Inf and Inf * 0 are NaN, NaN never cancels), so
+        // testing X -- not all eight unknowns -- is enough; the interior rows only multiply finite numbers.
         bool bad = !cfinite(X) || !cfinite(x_partner);
-        cplx x0 = X, x6 = X;
+        cplx xr[kM];
 #pragma unroll
-        for (int i = 0; i < kM; ++i) {
-            cplx xi = X;
-            if (i < kM - 1) xi = nmsub(nmsub(d[i], a[i], xl), c[i], X) * b[i];
-            if (i == 0) x0 = xi;
-            if (i == kM - 2) x6 = xi;
-            bad |= !cfinite(xi);
-            if (active) sm.xs[map.xs_slot(t, i)] = xi;
+        for (int i = 0; i < kM - 1; ++i) xr[i] = nmsub(nmsub(d[i], a[i], xl), c[i], X) * b[i];
+        xr[kM - 1] = X;
+        const cplx x0 = xr[0], x6 = xr[kM - 2];
+        if (active) {
+            const int tt = map.dir > 0 ? t - map.first_active : kT - 1 - t;  // chunk in memory order, left-aligned
+            const int r = tt / kPer8;
+            const uint32_t base = smem_u32(&sm.xs[0]) + (uint32_t)r * 128u, x = (uint32_t)(r & 7);
+#pragma unroll
+            for (int i = 0; i < kM; ++i) {
+                const uint32_t e = (uint32_t)((map.dir > 0 ? i : kM - 1 - i) + kM * (tt % kPer8));
+                sts_volatile(base + ((e ^ x) << 4), xr[i]);
+            }
         }
         if (map.head > 0 && t == feeder) {
             cplx xn = x0;  // first unknown after the head rows (unused when the system has no chunk)
