@@ -50,6 +50,10 @@ constexpr int kStageRows = kSlots + kHeadMax;  // 2056
 constexpr int kLevelsMax = kM == 8 ? 8 : 9;    // log2(kT)
 constexpr uint32_t kTileBytes = kSlots * sizeof(cplx);  // 32 KB per band tile
 
+// single-thread duties are spread over warps (whichever warp carries one is late for the next barrier): the band
+// prefetch is issued by the first active thread (warp 0 for full systems), the solution store by warp 1, the exchange
+// barrier is armed by warp 2
+constexpr int kStoreThread = 32, kXchgThread = 64;
 constexpr int kH = kT / 2;              // interface rows that survive the cyclic-reduction step
 constexpr int kHalfPad = kH / 2;        // zero rows on either side of a half-width array (largest PCR stride)
 constexpr int kHalfStride = kH + 2 * kHalfPad + 1;  // (+1: the four arrays start on different banks)
@@ -300,7 +304,7 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
                 row_values(src.p, hs.g_mid, 1, hs.k, hs.k2, hs.il, hs.id, hs.iu, hs.ib);
         }
         FH_TR(0);
-        if (CLUSTER > 1 && t == 0) mbar_expect_tx(&sm.xchg_bar[parity], 2 * sizeof(cplx));
+        if (CLUSTER > 1 && t == kXchgThread) mbar_expect_tx(&sm.xchg_bar[parity], 2 * sizeof(cplx));
 
         // ---- bands -> registers, interleaved with phase 1 -------------------------------------------------------
         // Phase 1 is the downward elimination inside the chunk; b[i] (i < kM - 1) becomes 1 / pivot.  Row i + 2 is
@@ -419,7 +423,7 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
         // there is no divergence; (3) the even rows follow from their own equation, which never left the registers.
         sm.full[0][t] = rA, sm.full[1][t] = rC, sm.full[2][t] = rD, sm.full[3][t] = rV;
         FH_TR(13);
-        if (t == 0) tma_store_wait_read();  // the previous system's TMA store has finished reading xs
+        if (t == kStoreThread) tma_store_wait_read();  // the previous system's TMA store has finished reading xs
         FH_TR(14);
         __syncthreads();
         FH_TR(6);
@@ -557,7 +561,7 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
         fence_proxy_async();  // make this thread's xs writes visible to the TMA engine
         const int any_nonfinite = __syncthreads_or(bad ? 1 : 0);  // (returns a truth value, not a bit-wise OR)
         FH_TR(11);
-        if (t == 0) {
+        if (t == kStoreThread) {
             if (map.chunks > 0) {  // (a system shorter than one chunk consists of head rows only)
                 tma_store_3d(&umaps.r[rank], 0, 0, (int)sys, sm.xs);
                 tma_store_commit();
@@ -576,7 +580,7 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
         }
         FH_TR(12);
     }
-    if (t == 0) tma_store_wait_read();
+    if (t == kStoreThread) tma_store_wait_read();
     if (CLUSTER > 1) cg::this_cluster().sync();  // no CTA leaves while its partner may still address it
 }
 
