@@ -56,7 +56,8 @@ constexpr uint32_t kTileBytes = kSlots * sizeof(cplx);  // 32 KB per band tile
 constexpr int kStoreThread = 32, kXchgThread = 64;
 constexpr int kH = kT / 2;              // interface rows that survive the cyclic-reduction step
 constexpr int kHalfPad = kH / 2;        // zero rows on either side of a half-width array (largest PCR stride)
-constexpr int kHalfStride = kH + 2 * kHalfPad + 1;  // (+1: the four arrays start on different banks)
+constexpr int kHalfStride = kH + 2 * kHalfPad + 4;  // (+4 rows = 64 B: the two arrays a lane pair touches together
+                                                    // fall on different halves of the 32 banks)
 
 struct __align__(1024) BatchedSmem {
     cplx stage[4][kSlots];      // TMA destination: bands of the NEXT system (a, b, c, d), swizzle-128B
@@ -441,40 +442,39 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
                 cl = r.lo, cb = r.b, ch = r.hi, cd = r.d;
             }
         }
+        // Thread pair (t, t ^ 1) owns the odd row r = t | 1, compacted index j = t >> 1: role 0 (even lane) updates
+        // {A, D}, role 1 (odd lane) updates {C, V}.  "own" = the coupling this thread updates, "oth" = its partner's
+        // (one shuffle away).  Both threads evaluate den = 1 - A * C(j-s) - C * A(j+s) in the SAME operand order: their
+        // pivots must agree to the last bit, or the row ends up scaled inconsistently (that cost two digits of
+        // backward error near small pivots).  The pair reads the same neighbour couplings (one wavefront serves both).
         int cur = 0;
-        int j, role;
-        {   // level 0 (cyclic reduction): thread pair (t, t^1) reduces the odd row r = t | 1
+        const int role = t & 1, j = t >> 1, va = 2 + role;
+        cplx own, xv;
+        {   // level 0 (cyclic reduction), from the full-width arrays; row kT is a zero row
             const int r = t | 1;
-            role = t & 1, j = t >> 1;
-            const int va = 2 + role;
             const cplx oA = sm.full[0][r], oC = sm.full[1][r], oX = sm.full[va][r];
-            const cplx Cm = sm.full[1][r - 1], Ap = sm.full[0][r + 1];  // (row kT is a zero row)
+            const cplx Cm = sm.full[1][r - 1], Ap = sm.full[0][r + 1];
             const cplx Xm = sm.full[va][r - 1], Xp = sm.full[va][r + 1];
             const cplx Qn = role ? sm.full[1][r + 1] : sm.full[0][r - 1];
             const PcrPivot pv = pcr_pivot(oA, Cm, oC, Ap);
-            cplx *H = sm.half[0][0] + kHalfPad + j;
-            H[va * kHalfStride] = pcr_scale(nmsub(nmsub(oX, oA, Xm), oC, Xp), pv);
-            H[role * kHalfStride] = -pcr_scale((role ? oC : oA) * Qn, pv);
+            xv = pcr_scale(nmsub(nmsub(oX, oA, Xm), oC, Xp), pv);
+            own = -pcr_scale((role ? oC : oA) * Qn, pv);
         }
-        __syncthreads();
-        FH_TR(7);
-        j = t & (kH - 1), role = t / kH;  // levels >= 1: role is uniform per warp
-        const int va = 2 + role;
-        // "own" = the coupling this thread updates (A for role 0, C for role 1), "oth" = the one its partner thread
-        // updates.  Both threads of a row evaluate den = 1 - A * C(j-s) - C * A(j+s) in the SAME order: their pivots
-        // must agree to the last bit, or the row ends up scaled inconsistently (that cost two digits of backward
-        // error near small pivots).  Rows beyond either end read as zero rows.
         constexpr uint32_t kArr = kHalfStride * sizeof(cplx);
         const uint32_t hb0 = smem_u32(&sm.half[0][0][kHalfPad + j]), hb1 = smem_u32(&sm.half[1][0][kHalfPad + j]);
         const uint32_t o_val = va * kArr, o_own = role * kArr;
-        cplx own = lds_volatile(hb0 + o_own), xv = lds_volatile(hb0 + o_val);
+        sts_volatile(hb0 + o_val, xv);
+        sts_volatile(hb0 + o_own, own);
+        __syncthreads();
+        FH_TR(7);
 #pragma unroll 1
-        for (int lv = 0, sb = (int)sizeof(cplx); lv < levels; ++lv, sb <<= 1) {
+        for (int lv = 0, sb = (int)sizeof(cplx); lv < levels; ++lv, sb <<= 1) {  // rows beyond either end: zero rows
             const uint32_t rd = cur ? hb1 : hb0, wr = cur ? hb0 : hb1;
             const cplx Cm = lds_volatile(rd + kArr - sb), Ap = lds_volatile(rd + sb);
-            const cplx Aj = lds_volatile(rd), Cj = lds_volatile(rd + kArr);  // (one of them is `own`: same bits)
             const cplx Xm = lds_volatile(rd + o_val - sb), Xp = lds_volatile(rd + o_val + sb);
             const cplx Q = lds_volatile(rd + o_own + (role ? sb : -sb));  // own array, own side
+            const cplx oth = mk(__shfl_xor_sync(0xffffffffu, own.re, 1), __shfl_xor_sync(0xffffffffu, own.im, 1));
+            const cplx Aj = role ? oth : own, Cj = role ? own : oth;
             const PcrPivot pv = pcr_pivot(Aj, Cm, Cj, Ap);
             xv = pcr_scale(nmsub(nmsub(xv, Aj, Xm), Cj, Xp), pv);
             own = -pcr_scale(own * Q, pv);
