@@ -67,6 +67,7 @@ struct __align__(1024) BatchedSmem {
     cplx half[2][4][kHalfStride];  // PCR ping-pong over the odd interface rows, zero rows on both sides
     cplx headst[4][kHeadMax];   // head rows of the next system (cp.async by one thread)
     cplx xchg[2][2];            // [parity][{Y, V}] written by the partner CTA (st.async)
+    RowGeom bgeom[2];           // fused variant, scalar-h: geometry of the first / last row of the mesh (k-independent)
     unsigned long long full_bar;     // mbarrier: band tiles have landed
     unsigned long long xchg_bar[2];  // mbarrier: partner's interface pair has landed
 };
@@ -269,7 +270,12 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
 
     HelmState hs;
     if constexpr (!Source::kStaged) {
-        if (src.p.h_mode == FH_H_SCALAR) hs.g_mid = row_geom(src.p, src.p.n_elem > 1 ? 1 : 0);
+        if (src.p.h_mode == FH_H_SCALAR) {
+            hs.g_mid = row_geom(src.p, src.p.n_elem > 1 ? 1 : 0);
+            // the two boundary rows have their own geometry (IEEE divisions): evaluated once, not once per system
+            if (t < 2) sm.bgeom[t] = row_geom(src.p, t == 0 ? 0 : src.p.n_elem);
+            __syncthreads();
+        }
     }
 
     // one elected thread feeds the pipeline: four band tiles by TMA, head rows by cp.async
@@ -301,8 +307,10 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
         const uint32_t parity = it & 1;
         if constexpr (!Source::kStaged) {
             hs.k = __ldg(src.ks + sys), hs.k2 = __ldg(src.k2s + sys);
-            if (src.p.h_mode == FH_H_SCALAR && src.p.n_elem >= 2)
+            if (src.p.h_mode == FH_H_SCALAR && src.p.n_elem >= 2) {
                 row_values(src.p, hs.g_mid, 1, hs.k, hs.k2, hs.il, hs.id, hs.iu, hs.ib);
+                hs.ia = map.dir > 0 ? hs.il : hs.iu, hs.ic = map.dir > 0 ? hs.iu : hs.il;  // in local row order
+            }
         }
         FH_TR(0);
         if (CLUSTER > 1 && t == kXchgThread) mbar_expect_tx(&sm.xchg_bar[parity], 2 * sizeof(cplx));
@@ -332,6 +340,18 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
                 const uint32_t ad = tile_addr + ((e ^ tile_x) << 4);
                 a[i] = lds_volatile(ad), b[i] = lds_volatile(ad + kTileBytes);
                 c[i] = lds_volatile(ad + 2 * kTileBytes), d[i] = lds_volatile(ad + 3 * kTileBytes);
+            } else if (src.p.h_mode == FH_H_SCALAR && src.p.n_elem >= 2) {
+                // all interior rows are alike; a mesh boundary row can only sit in the first slot of the first active
+                // thread (local row 0, when there are no head rows) or, single-CTA, in the last slot of the last thread
+                a[i] = hs.ia, b[i] = hs.id, c[i] = hs.ic, d[i] = hs.ib;
+                const bool first = i == 0 && map.head == 0 && t == map.first_active;
+                const bool last = i == kM - 1 && CLUSTER == 1 && t == kT - 1;
+                if (first || last) {
+                    const int64_t g = first ? map.global_row(0) : n - 1;
+                    cplx lo, hi;
+                    row_values(src.p, sm.bgeom[g == 0 ? 0 : 1], g, hs.k, hs.k2, lo, b[i], hi, d[i]);
+                    a[i] = map.dir > 0 ? lo : hi, c[i] = map.dir > 0 ? hi : lo;
+                }
             } else {
                 helm_row(src, hs, map, map.head + (t - map.first_active) * kM + i, a[i], b[i], c[i], d[i]);
             }

@@ -121,6 +121,7 @@ struct HelmState {  // per-thread state of the generator
     RowGeom g_mid;  // scalar-h mode: geometry of the interior rows
     double k, k2;
     cplx il, id, iu, ib;  // the interior row of the current wavenumber (scalar-h mode), evaluated once per system
+    cplx ia, ic;          // il / iu in the CTA's local row order (the reversed half swaps them)
 };
 
 // ---------------------------------------------------------------------------------------------- host: tensor maps

@@ -26,10 +26,13 @@ def main():
     lib.fh_debug_set_trace.argtypes = [ctypes.c_void_p, ctypes.c_int]
     ks = torch.linspace(1.0, 1000.0, n_k, dtype=torch.float64)
     dl, d, du, b = fh.assemble_bands(4096, ks, 1.0 / 4096)
-    fh.solve_tridiagonal(dl, d, du, b, refine=False)
+    fused = len(sys.argv) > 3 and sys.argv[3] == "fused"
+    run = ((lambda: fh.solve_helmholtz_sweep(4096, ks, fused=True, check_singular=False)) if fused
+           else (lambda: fh.solve_tridiagonal(dl, d, du, b, refine=False)))
+    run()
     torch.cuda.synchronize()
     assert lib.fh_debug_set_trace(buf.data_ptr(), it) == 0
-    fh.solve_tridiagonal(dl, d, du, b, refine=False)
+    run()
     torch.cuda.synchronize()
     lib.fh_debug_set_trace(None, 0)
     tr = buf.cpu().numpy().reshape(2, 8, 16, 2)
