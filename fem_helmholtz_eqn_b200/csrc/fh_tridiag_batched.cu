@@ -270,8 +270,8 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
 
     HelmState hs;
     if constexpr (!Source::kStaged) {
-        if (src.p.h_mode == FH_H_SCALAR) {
-            hs.g_mid = row_geom(src.p, src.p.n_elem > 1 ? 1 : 0);
+        if (src.p.h_mode == FH_H_SCALAR) hs.g_mid = row_geom(src.p, src.p.n_elem > 1 ? 1 : 0);
+        if constexpr (Source::kUniform) {
             // the two boundary rows have their own geometry (IEEE divisions): evaluated once, not once per system
             if (t < 2) sm.bgeom[t] = row_geom(src.p, t == 0 ? 0 : src.p.n_elem);
             __syncthreads();
@@ -307,10 +307,8 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
         const uint32_t parity = it & 1;
         if constexpr (!Source::kStaged) {
             hs.k = __ldg(src.ks + sys), hs.k2 = __ldg(src.k2s + sys);
-            if (src.p.h_mode == FH_H_SCALAR && src.p.n_elem >= 2) {
+            if (src.p.h_mode == FH_H_SCALAR && src.p.n_elem >= 2)
                 row_values(src.p, hs.g_mid, 1, hs.k, hs.k2, hs.il, hs.id, hs.iu, hs.ib);
-                hs.ia = map.dir > 0 ? hs.il : hs.iu, hs.ic = map.dir > 0 ? hs.iu : hs.il;  // in local row order
-            }
         }
         FH_TR(0);
         if (CLUSTER > 1 && t == kXchgThread) mbar_expect_tx(&sm.xchg_bar[parity], 2 * sizeof(cplx));
@@ -331,6 +329,17 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
             tile_x = (uint32_t)(r & 7);
         }
         FH_TR(1);
+        // fused, uniform mesh: the interior row in local order, and the CTA's two possible mesh-boundary rows --
+        // evaluated by every thread (a dozen operations), so that the one thread that owns such a row does not diverge
+        cplx ia, ic, fa, fb, fc, fd, la, lb, lc, ld;
+        if constexpr (Source::kUniform) {
+            ia = map.dir > 0 ? hs.il : hs.iu, ic = map.dir > 0 ? hs.iu : hs.il;
+            cplx lo, hi;
+            const int64_t g = map.global_row(0);  // local row 0: mesh row 0 (forward) or n - 1 (reversed)
+            row_values(src.p, sm.bgeom[g == 0 ? 0 : 1], g, hs.k, hs.k2, lo, fb, hi, fd);
+            fa = map.dir > 0 ? lo : hi, fc = map.dir > 0 ? hi : lo;
+            if (CLUSTER == 1) row_values(src.p, sm.bgeom[1], n - 1, hs.k, hs.k2, la, lb, lc, ld);
+        }
         auto load_row = [&](int i) {
             if (!active) {
                 a[i] = czero(), b[i] = cone(), c[i] = czero(), d[i] = czero();
@@ -340,18 +349,12 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
                 const uint32_t ad = tile_addr + ((e ^ tile_x) << 4);
                 a[i] = lds_volatile(ad), b[i] = lds_volatile(ad + kTileBytes);
                 c[i] = lds_volatile(ad + 2 * kTileBytes), d[i] = lds_volatile(ad + 3 * kTileBytes);
-            } else if (src.p.h_mode == FH_H_SCALAR && src.p.n_elem >= 2) {
+            } else if constexpr (Source::kUniform) {
                 // all interior rows are alike; a mesh boundary row can only sit in the first slot of the first active
                 // thread (local row 0, when there are no head rows) or, single-CTA, in the last slot of the last thread
-                a[i] = hs.ia, b[i] = hs.id, c[i] = hs.ic, d[i] = hs.ib;
-                const bool first = i == 0 && map.head == 0 && t == map.first_active;
-                const bool last = i == kM - 1 && CLUSTER == 1 && t == kT - 1;
-                if (first || last) {
-                    const int64_t g = first ? map.global_row(0) : n - 1;
-                    cplx lo, hi;
-                    row_values(src.p, sm.bgeom[g == 0 ? 0 : 1], g, hs.k, hs.k2, lo, b[i], hi, d[i]);
-                    a[i] = map.dir > 0 ? lo : hi, c[i] = map.dir > 0 ? hi : lo;
-                }
+                a[i] = ia, b[i] = hs.id, c[i] = ic, d[i] = hs.ib;
+                if (i == 0 && map.head == 0 && t == map.first_active) a[i] = fa, b[i] = fb, c[i] = fc, d[i] = fd;
+                if (i == kM - 1 && CLUSTER == 1 && t == kT - 1) a[i] = la, b[i] = lb, c[i] = lc, d[i] = ld;
             } else {
                 helm_row(src, hs, map, map.head + (t - map.first_active) * kM + i, a[i], b[i], c[i], d[i]);
             }
@@ -737,23 +740,31 @@ int fh_helmholtz1d_sweep_fused_c128(const fh_problem1d *prob_host, const double 
                                     size_t workspace_bytes, fh_stream_t stream) {
     using namespace fh;
     (void)workspace, (void)workspace_bytes;
-    HelmSource src;
-    int rc = problem_from_host(prob_host, src.p);
+    Problem1d p;
+    int rc = problem_from_host(prob_host, p);
     if (rc != FH_OK) return rc;
     FH_REQUIRE(n_k >= 0, "n_k must be >= 0");
     if (n_k == 0) return FH_OK;
     FH_REQUIRE(ks && k2s && u, "NULL device pointer");
-    const int64_t n = src.p.n_elem + 1;
+    const int64_t n = p.n_elem + 1;
     if (n > kBatchedMaxN) {
         set_error("fused sweep supports meshes up to %lld nodes; use fh_helmholtz1d_solve_large_fused_c128 beyond",
                   (long long)kBatchedMaxN);
         return FH_E_UNSUPPORTED;
     }
-    src.ks = ks, src.k2s = k2s;
     const cplx *const none[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (n <= kStageRows) return launch_batched<1>(src, none, reinterpret_cast<cplx *>(u), n, n_k, status, st);
-    return launch_batched<2>(src, none, reinterpret_cast<cplx *>(u), n, n_k, status, st);
+    cplx *out = reinterpret_cast<cplx *>(u);
+    if (p.h_mode == FH_H_SCALAR && p.n_elem >= 2) {  // uniform mesh: the fast generator
+        HelmSourceT<true> src;
+        src.p = p, src.ks = ks, src.k2s = k2s;
+        if (n <= kStageRows) return launch_batched<1>(src, none, out, n, n_k, status, st);
+        return launch_batched<2>(src, none, out, n, n_k, status, st);
+    }
+    HelmSourceT<false> src;
+    src.p = p, src.ks = ks, src.k2s = k2s;
+    if (n <= kStageRows) return launch_batched<1>(src, none, out, n, n_k, status, st);
+    return launch_batched<2>(src, none, out, n, n_k, status, st);
 }
 
 }  // extern "C"

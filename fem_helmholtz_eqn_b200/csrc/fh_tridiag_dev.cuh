@@ -109,12 +109,18 @@ struct StoreMaps {   // solution tensor as seen by cluster rank 0 and rank 1 (ea
 struct BandSource {  // staged pipeline: bands live in global memory
     const cplx *dl, *d, *du, *b;
     static constexpr bool kStaged = true;
+    static constexpr bool kUniform = false;
 };
 
-struct HelmSource {  // fused pipeline: bands are generated, never stored
+// fused pipeline: bands are generated, never stored.  UNIFORM = scalar-h mesh with at least two elements: every
+// interior row of a system is the same, only the two mesh-boundary rows differ (compile-time switch: the generic
+// generator, with its per-row geometry and IEEE divisions, stays out of the fast kernel).
+template <bool UNIFORM>
+struct HelmSourceT {
     Problem1d p;
     const double *ks, *k2s;
     static constexpr bool kStaged = false;
+    static constexpr bool kUniform = UNIFORM;
 };
 
 struct HelmState {  // per-thread state of the generator
