@@ -391,8 +391,8 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
                 a[0] = czero();
             }
         }
-        b[0] = frecip(b[0]);
         cplx a7o, b7o, c7o, d7o;  // the original interface row, for the probe
+        b[0] = frecip(b[0]);
 #pragma unroll
         for (int i = 1; i < kM; ++i) {
             if (i + 1 < kM) load_row(i + 1);
