@@ -81,6 +81,8 @@ _SIGNATURES = {
     "fh_tridiag_solve_pivoted_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "fh_tridiag_solve_pivoted_c128": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, _P, C.c_size_t, _P]),
     "fh_tridiag_residual_vector_c128": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, _P]),
+    "fh_tridiag_refine_flagged_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int64]),
+    "fh_tridiag_refine_flagged_c128": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, _P, C.c_size_t, _P]),
     "fh_l2_error_1d_c128": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, _P, _P, C.c_int, _P, _P]),
     "fh_tridiag_residual_c128": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, _P]),
 }

@@ -113,6 +113,148 @@ extern "C" int fh_tridiag_residual_c128(const fh_c128 *dl, const fh_c128 *d, con
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Selective iterative refinement, entirely on the device (no host round trip): the batched solver flags the systems
+// whose interface-row probe found a defect (status bit 1, value 2); exactly those get one step  r = b - A u,
+// A e = r, u += e.  Four stream-ordered launches:
+//   1. compact_flagged_kernel   status -> ascending list of flagged systems + their number (one CTA, block scan)
+//   2. residual_subset_kernel   r_i = b - A u of system list[i]                (compact rows)
+//   3. the batched solver       A(list[i]) e_i = r_i, matrices read in place   (fh_tridiag_batched.cu)
+//   4. correct_subset_kernel    u(list[i]) += e_i; status bit 1 cleared, bit 0 of the correction solve merged in
+// Launch sizes depend on the capacity of the workspace only; the kernels read the count from device memory.
+namespace fh {
+
+int batched_solve_subset(const cplx *dl, const cplx *d, const cplx *du, const cplx *r, cplx *e, int64_t n, int64_t batch,
+                         const int32_t *list, const int32_t *count, int64_t cap, int32_t *status, cudaStream_t stream);
+
+constexpr int kCompactThreads = 1024;
+
+// header[0] = number of flagged systems, header[1] = number refined by this call (min(flagged, cap))
+__global__ void __launch_bounds__(kCompactThreads)
+compact_flagged_kernel(const int32_t *__restrict__ status, int64_t batch, int32_t mask, int32_t cap,
+                       int32_t *__restrict__ list, int32_t *__restrict__ header) {
+    __shared__ int warp_tot[kCompactThreads / 32];
+    __shared__ int base_s;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0) base_s = 0;
+    __syncthreads();
+    // tiles of kCompactThreads consecutive systems, so that the list comes out in ascending order
+    for (int64_t s0 = 0; s0 < batch; s0 += kCompactThreads) {
+        const int64_t s = s0 + t;
+        const int f = (s < batch && (status[s] & mask) != 0) ? 1 : 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        const int before = __popc(bal & ((1u << lane) - 1u));
+        if (lane == 0) warp_tot[warp] = __popc(bal);
+        __syncthreads();
+        int off = base_s;
+        for (int w = 0; w < warp; ++w) off += warp_tot[w];
+        if (f && off + before < cap) list[off + before] = (int32_t)s;
+        __syncthreads();
+        if (t == kCompactThreads - 1) base_s = off + before + f;
+        __syncthreads();
+    }
+    if (t == 0) {
+        header[0] = base_s;
+        header[1] = base_s < cap ? base_s : cap;
+    }
+}
+
+__global__ void __launch_bounds__(kResThreads)
+residual_subset_kernel(const cplx *__restrict__ dl, const cplx *__restrict__ d, const cplx *__restrict__ du,
+                       const cplx *__restrict__ b, const cplx *__restrict__ u, int64_t n,
+                       const int32_t *__restrict__ list, const int32_t *__restrict__ header, cplx *__restrict__ r) {
+    const int64_t total = (int64_t)header[1] * n;
+    for (int64_t o = (int64_t)blockIdx.x * kResThreads + threadIdx.x; o < total; o += (int64_t)gridDim.x * kResThreads) {
+        const int64_t i = o / n, j = o - i * n;
+        const int64_t g = (int64_t)list[i] * n + j;
+        cplx v = nmsub(ldg_stream(b + g), ldg_stream(d + g), u[g]);
+        if (j > 0) v = nmsub(v, ldg_stream(dl + g), u[g - 1]);
+        if (j < n - 1) v = nmsub(v, ldg_stream(du + g), u[g + 1]);
+        r[o] = v;
+    }
+}
+
+__global__ void __launch_bounds__(kResThreads)
+correct_subset_kernel(cplx *__restrict__ u, int64_t n, const int32_t *__restrict__ list,
+                      const int32_t *__restrict__ header, const cplx *__restrict__ e,
+                      const int32_t *__restrict__ status_e, int32_t mask, int32_t *__restrict__ status) {
+    const int64_t m = header[1], total = m * n;
+    for (int64_t o = (int64_t)blockIdx.x * kResThreads + threadIdx.x; o < total; o += (int64_t)gridDim.x * kResThreads) {
+        const int64_t i = o / n, j = o - i * n;
+        const int64_t g = (int64_t)list[i] * n + j;
+        u[g] = u[g] + ldg_stream(e + o);
+        if (j == 0) status[list[i]] = (status[list[i]] & ~mask) | (status_e[i] & 1);
+    }
+}
+
+struct RefinePlan {  // carving of the workspace
+    int64_t cap;
+    size_t off_header, off_list, off_status, off_r, off_e, total;
+};
+static RefinePlan refine_plan(int64_t n, int64_t batch, size_t workspace_bytes) {
+    RefinePlan p;
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    p.off_header = 0;
+    p.off_list = up(2 * sizeof(int32_t));
+    p.off_status = p.off_list + up(sizeof(int32_t) * (size_t)batch);
+    const size_t fixed = p.off_status + up(sizeof(int32_t) * (size_t)batch);
+    const size_t per_system = 2 * sizeof(cplx) * (size_t)n;
+    int64_t cap = workspace_bytes > fixed ? (int64_t)((workspace_bytes - fixed) / per_system) : 0;
+    if (cap > batch) cap = batch;
+    p.cap = cap;
+    p.off_r = fixed;
+    p.off_e = fixed + sizeof(cplx) * (size_t)n * (size_t)cap;
+    p.total = fixed + per_system * (size_t)cap;
+    return p;
+}
+}  // namespace fh
+
+// Workspace for refining up to `max_systems` flagged systems per call.
+extern "C" size_t fh_tridiag_refine_flagged_workspace_bytes(int64_t n, int64_t batch, int64_t max_systems) {
+    if (n <= 0 || batch <= 0) return 0;
+    if (max_systems > batch) max_systems = batch;
+    if (max_systems < 1) max_systems = 1;
+    const fh::RefinePlan p = fh::refine_plan(n, batch, (size_t)0);
+    return p.off_r + 2 * sizeof(fh::cplx) * (size_t)n * (size_t)max_systems;
+}
+
+extern "C" int fh_tridiag_refine_flagged_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c128 *du, const fh_c128 *b,
+                                              fh_c128 *u, int64_t n, int64_t batch, int32_t *status, void *workspace,
+                                              size_t workspace_bytes, fh_stream_t stream) {
+    using namespace fh;
+    FH_REQUIRE(n >= 0 && batch >= 0, "n and batch must be >= 0");
+    if (n == 0 || batch == 0) return FH_OK;
+    FH_REQUIRE(dl && d && du && b && u && status && workspace, "NULL device pointer");
+    FH_REQUIRE(batch < (1ll << 31), "batch too large");
+    if (n > fh_tridiag_batched_max_n()) {
+        set_error("refinement is implemented for the batched solver (n <= %lld)", (long long)fh_tridiag_batched_max_n());
+        return FH_E_UNSUPPORTED;
+    }
+    const RefinePlan p = refine_plan(n, batch, workspace_bytes);
+    FH_REQUIRE(p.cap >= 1, "workspace too small (see fh_tridiag_refine_flagged_workspace_bytes)");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char *ws = static_cast<char *>(workspace);
+    int32_t *header = reinterpret_cast<int32_t *>(ws + p.off_header);
+    int32_t *list = reinterpret_cast<int32_t *>(ws + p.off_list);
+    int32_t *status_e = reinterpret_cast<int32_t *>(ws + p.off_status);
+    cplx *r = reinterpret_cast<cplx *>(ws + p.off_r), *e = reinterpret_cast<cplx *>(ws + p.off_e);
+    const int32_t mask = 2;  // FH_STATUS_SMALL_PIVOT
+    compact_flagged_kernel<<<1, kCompactThreads, 0, st>>>(status, batch, mask, (int32_t)p.cap, list, header);
+    FH_LAUNCH_CHECK("compact_flagged_kernel");
+    const unsigned grid = (unsigned)(8 * sm_count());
+    residual_subset_kernel<<<grid, kResThreads, 0, st>>>(
+        reinterpret_cast<const cplx *>(dl), reinterpret_cast<const cplx *>(d), reinterpret_cast<const cplx *>(du),
+        reinterpret_cast<const cplx *>(b), reinterpret_cast<const cplx *>(u), n, list, header, r);
+    FH_LAUNCH_CHECK("residual_subset_kernel");
+    int rc = batched_solve_subset(reinterpret_cast<const cplx *>(dl), reinterpret_cast<const cplx *>(d),
+                                  reinterpret_cast<const cplx *>(du), r, e, n, batch, list, header + 1, p.cap, status_e, st);
+    if (rc != FH_OK) return rc;
+    correct_subset_kernel<<<grid, kResThreads, 0, st>>>(reinterpret_cast<cplx *>(u), n, list, header, e, status_e, mask,
+                                                       status);
+    FH_LAUNCH_CHECK("correct_subset_kernel");
+    return FH_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Pivoted fallback.  The fast solvers are unpivoted; a system on which they produce a non-finite value (an
 // exactly vanishing leading minor, e.g. k*h = 2 on the first element) is re-solved here the way LAPACK zgtsv
 // does it: Gaussian elimination with partial pivoting between adjacent rows, one thread per system, serial in

@@ -278,22 +278,29 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
         }
     }
 
+    // system index of the MATRIX of (compact) system `sys`: they differ when a subset is refined
+    auto matrix_of = [&](int64_t sys) -> int64_t {
+        if constexpr (Source::kSubset) return src.list[sys];
+        else return sys;
+    };
+    if constexpr (Source::kSubset) batch = *src.count < batch ? *src.count : batch;
     // one elected thread feeds the pipeline: four band tiles by TMA, head rows by cp.async
     auto prefetch = [&](int64_t sys) {
         if constexpr (Source::kStaged) {
             if (t == map.first_active % kT) {  // the thread that also consumes the head rows
+                const int64_t sysm = matrix_of(sys);
                 mbar_expect_tx(&sm.full_bar, 4 * kTileBytes);
-                tma_load_3d(sm.stage[0], map_lo, 0, map.box_c1, (int)sys, &sm.full_bar);
-                tma_load_3d(sm.stage[1], &tmaps[1], 0, map.box_c1, (int)sys, &sm.full_bar);
-                tma_load_3d(sm.stage[2], map_hi, 0, map.box_c1, (int)sys, &sm.full_bar);
+                tma_load_3d(sm.stage[0], map_lo, 0, map.box_c1, (int)sysm, &sm.full_bar);
+                tma_load_3d(sm.stage[1], &tmaps[1], 0, map.box_c1, (int)sysm, &sm.full_bar);
+                tma_load_3d(sm.stage[2], map_hi, 0, map.box_c1, (int)sysm, &sm.full_bar);
                 tma_load_3d(sm.stage[3], &tmaps[3], 0, map.box_c1, (int)sys, &sm.full_bar);
                 const cplx *lo = map.dir > 0 ? src.dl : src.du, *hi = map.dir > 0 ? src.du : src.dl;
                 for (int j = 0; j < map.head; ++j) {
-                    const int64_t g = sys * n + map.global_row(j);
+                    const int64_t g = sysm * n + map.global_row(j);
                     cp_async16(&sm.headst[0][j], lo + g);
                     cp_async16(&sm.headst[1][j], src.d + g);
                     cp_async16(&sm.headst[2][j], hi + g);
-                    cp_async16(&sm.headst[3][j], src.b + g);
+                    cp_async16(&sm.headst[3][j], src.b + sys * n + map.global_row(j));
                 }
                 cp_async_commit();
             }
@@ -457,9 +464,9 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
         cplx cl = czero(), cb = cone(), ch = czero(), cd = czero();
         if (has_cut) {
             if constexpr (Source::kStaged) {
-                const int64_t g = sys * n + cut_row;
+                const int64_t g = matrix_of(sys) * n + cut_row;
                 cl = ldg_stream(src.dl + g), cb = ldg_stream(src.d + g), ch = ldg_stream(src.du + g);
-                cd = ldg_stream(src.b + g);
+                cd = ldg_stream(src.b + sys * n + cut_row);
             } else {
                 const Row4 r = helm_any_row(src, hs, cut_row);
                 cl = r.lo, cb = r.b, ch = r.hi, cd = r.d;
@@ -629,14 +636,17 @@ static int pcr_levels(int64_t n, int cluster) {
 
 template <int CLUSTER, class Source>
 static int launch_batched(const Source &src, const cplx *const bands[4], cplx *u, int64_t n, int64_t batch,
-                          int32_t *status, cudaStream_t stream) {
+                          int32_t *status, cudaStream_t stream, int64_t batch_matrices = -1) {
+    // batch = number of right-hand sides / solutions (an upper bound when src.count is set); batch_matrices = number
+    // of systems in the dl / d / du arrays when it differs (subset refinement)
+    if (batch_matrices < 0) batch_matrices = batch;
     auto kernel = tridiag_batched_kernel<CLUSTER, Source>;
     const size_t smem = sizeof(BatchedSmem) + 1024;  // slack for the in-kernel 1024-byte round-up
     if (smem > smem_optin_bytes()) {
         set_error("kernel needs %zu B of shared memory, device offers %zu", smem, smem_optin_bytes());
         return FH_E_UNSUPPORTED;
     }
-    if (batch >= (1ll << 31)) {
+    if (batch >= (1ll << 31) || batch_matrices >= (1ll << 31)) {
         set_error("batch too large for one launch");
         return FH_E_UNSUPPORTED;
     }
@@ -650,7 +660,8 @@ static int launch_batched(const Source &src, const cplx *const bands[4], cplx *u
         if (rc != FH_OK) return rc;
         if (Source::kStaged) {
             for (int i = 0; i < 4; ++i) {
-                rc = make_tensor_map(&maps.band[r][i], bands[i], n, batch, h.row0[r], h.chunks[r], kChunks8);
+                rc = make_tensor_map(&maps.band[r][i], bands[i], n, i < 3 ? batch_matrices : batch, h.row0[r],
+                                     h.chunks[r], kChunks8);
                 if (rc != FH_OK) return rc;
             }
         }
@@ -691,6 +702,19 @@ int batched_solve_bands(const cplx *dl, const cplx *d, const cplx *du, const cpl
     const cplx *const bands[4] = {dl, d, du, b};
     if (n <= kStageRows) return launch_batched<1>(src, bands, u, n, batch, status, stream);
     return launch_batched<2>(src, bands, u, n, batch, status, stream);
+}
+
+// Solve the systems  A(list[i]) e_i = r_i,  i < min(*count, cap):  matrices picked from a batch of `batch` systems,
+// right-hand sides and solutions compact (cap rows).  Everything the launch needs is known on the host; how many
+// systems there are is read on the device.
+int batched_solve_subset(const cplx *dl, const cplx *d, const cplx *du, const cplx *r, cplx *e, int64_t n, int64_t batch,
+                         const int32_t *list, const int32_t *count, int64_t cap, int32_t *status, cudaStream_t stream) {
+    BandSubsetSource src;
+    src.dl = dl, src.d = d, src.du = du, src.b = r;
+    src.list = list, src.count = count;
+    const cplx *const bands[4] = {dl, d, du, r};
+    if (n <= kStageRows) return launch_batched<1>(src, bands, e, n, cap, status, stream, batch);
+    return launch_batched<2>(src, bands, e, n, cap, status, stream, batch);
 }
 
 }  // namespace fh

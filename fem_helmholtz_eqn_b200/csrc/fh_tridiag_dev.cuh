@@ -111,6 +111,17 @@ struct BandSource {  // staged pipeline: bands live in global memory
     const cplx *dl, *d, *du, *b;
     static constexpr bool kStaged = true;
     static constexpr bool kUniform = false;
+    static constexpr bool kSubset = false;
+};
+
+// Refinement of a SUBSET of a batch (fh_tridiag_refine_flagged_c128): the matrix of compact system i is system
+// list[i] of dl / d / du, its right-hand side and solution are rows i of compact arrays, and the number of systems is
+// read from *count (decided on the device, no host round trip).  A separate type, so that the ordinary solve does not
+// carry the indirection.
+struct BandSubsetSource : BandSource {
+    const int32_t *list;
+    const int32_t *count;
+    static constexpr bool kSubset = true;
 };
 
 // fused pipeline: bands are generated, never stored.  UNIFORM = scalar-h mesh with at least two elements: every
@@ -122,6 +133,7 @@ struct HelmSourceT {
     const double *ks, *k2s;
     static constexpr bool kStaged = false;
     static constexpr bool kUniform = UNIFORM;
+    static constexpr bool kSubset = false;
 };
 
 struct HelmState {  // per-thread state of the generator

@@ -224,26 +224,46 @@ def assembly(N: int, k, h: float, elements=None, theta=0.0, *, bc_left="neumann"
     return (A, b[0].cpu().numpy()) if scalar else (A, b)
 
 
-def refine_flagged(dl, d, du, b, u, status):
+_refine_ws = {}
+
+
+def _refine_workspace(n, batch, device):
+    """Workspace of fh_tridiag_refine_flagged_c128, sized for batch/16 systems per call (a fine sweep flags 2-3 % of its
+    wavenumbers) and kept between calls: allocating half a gigabyte per step would cost more than the refinement."""
+    lib = _lib.load()
+    cap = min(batch, max(256, batch // 16))
+    key = (n, batch, device)
+    ws = _refine_ws.get(key)
+    if ws is None:
+        _refine_ws.clear()
+        nbytes = lib.fh_tridiag_refine_flagged_workspace_bytes(n, batch, cap)
+        ws = _refine_ws[key] = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    return ws
+
+
+def refine_flagged(dl, d, du, b, u, status, sync=True):
     """One step of iterative refinement for exactly the systems whose elimination met a small pivot
-    (``status & STATUS_SMALL_PIVOT``): r = b - A u, solve A e = r, u += e -- all on the device, on the gathered
-    subset.  The solver is unpivoted, so a pivot that cancels to 1e-5 of its scale costs five digits of backward
-    error (seen for ~1 in 10^4 wavenumbers of a fine sweep); one refinement step restores it.  Returns the number
-    of refined systems (reading it is the only host synchronisation)."""
+    (``status & STATUS_SMALL_PIVOT``): r = b - A u, solve A e = r, u += e -- all on the device, matrices read in
+    place through an index list that never visits the host (``fh_tridiag_refine_flagged_c128``).  The solver is
+    unpivoted, so a pivot that cancels to 1e-5 of its scale costs five digits of backward error (seen for ~1 in 10^4
+    wavenumbers of a fine sweep); one refinement step restores it.  Returns the number of refined systems; reading it
+    is the only host synchronisation (``sync=False`` skips it and returns None: at most batch/16 systems are then
+    refined)."""
     lib = _lib.require_cuda()
-    idx = torch.nonzero((status & STATUS_SMALL_PIVOT) != 0).flatten()
-    m = int(idx.numel())
-    if m == 0:
-        return 0
-    n = d.shape[1]
-    sub = [t.index_select(0, idx).contiguous() for t in (dl, d, du, b, u)]
-    r = torch.empty_like(sub[4])
-    check(lib.fh_tridiag_residual_vector_c128(*(ptr(t) for t in sub), n, m, ptr(r), stream_ptr()),
-          "fh_tridiag_residual_vector_c128")
-    e, st = solve_tridiagonal(sub[0], sub[1], sub[2], r, refine=False)
-    u.index_add_(0, idx, e)
-    status.index_copy_(0, idx, (status.index_select(0, idx) | st) & ~STATUS_SMALL_PIVOT)
-    return m
+    batch, n = d.shape
+    if n > lib.fh_tridiag_batched_max_n():
+        return 0  # the large-system solver does not set the flag
+    ws = _refine_workspace(n, batch, d.device)
+    total = 0
+    while True:
+        check(lib.fh_tridiag_refine_flagged_c128(ptr(dl), ptr(d), ptr(du), ptr(b), ptr(u), n, batch, ptr(status),
+                                                 ptr(ws), ws.numel(), stream_ptr()), "fh_tridiag_refine_flagged_c128")
+        if not sync:
+            return None
+        flagged, refined = (int(v) for v in ws[:8].view(torch.int32).tolist())
+        total += refined
+        if flagged <= refined:
+            return total
 
 
 def resolve_nonfinite(dl, d, du, b, u, status):

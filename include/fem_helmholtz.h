@@ -161,6 +161,17 @@ FH_API int fh_tridiag_solve_pivoted_c128(const fh_c128 *dl, const fh_c128 *d, co
 FH_API int fh_tridiag_residual_vector_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c128 *du, const fh_c128 *b,
                                     const fh_c128 *u, int64_t n, int64_t batch, fh_c128 *r, fh_stream_t stream);
 
+/* Selective iterative refinement on the device (keeps np.linalg.solve's accuracy, nb:204, on the unpivoted fast path):
+ * every system whose status carries FH_STATUS_SMALL_PIVOT (2, set by fh_tridiag_solve_batched_c128) gets one step
+ * r = b - A u, A e = r, u += e; the flag is cleared, a non-finite correction sets FH_STATUS_NONFINITE (1).  No host
+ * synchronisation: the list of flagged systems is built and consumed on the device.  One call refines at most as many
+ * systems as the workspace was sized for (max_systems); on return the first two int32 of the workspace hold
+ * {flagged, refined}: call again while flagged > refined.  n <= fh_tridiag_batched_max_n(). */
+FH_API size_t fh_tridiag_refine_flagged_workspace_bytes(int64_t n, int64_t batch, int64_t max_systems);
+FH_API int fh_tridiag_refine_flagged_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c128 *du, const fh_c128 *b,
+                                   fh_c128 *u, int64_t n, int64_t batch, int32_t *status, void *workspace,
+                                   size_t workspace_bytes, fh_stream_t stream);
+
 /* ---- L2 error against the continuum solution -exp(ikx) (replaces nb:259-281 compute_L2_error, quirks kept:
  * complex square without abs, weight h*w).  sum_out[s] = the complex sum BEFORE the final sqrt (nb:281). */
 FH_API int fh_l2_error_1d_c128(const double *nodes, const fh_c128 *u, const double *ks, int64_t n_elem, int64_t batch,
