@@ -128,33 +128,35 @@ int batched_solve_subset(const cplx *dl, const cplx *d, const cplx *du, const cp
 
 constexpr int kCompactThreads = 1024;
 
-// header[0] = number of flagged systems, header[1] = number refined by this call (min(flagged, cap))
+// header[0] = number of flagged systems, header[1] = number refined by this call (min(flagged, cap)).  One CTA; every
+// thread owns a contiguous slice of status[] (so the list comes out ascending): count, one block-wide scan, write.
 __global__ void __launch_bounds__(kCompactThreads)
 compact_flagged_kernel(const int32_t *__restrict__ status, int64_t batch, int32_t mask, int32_t cap,
                        int32_t *__restrict__ list, int32_t *__restrict__ header) {
     __shared__ int warp_tot[kCompactThreads / 32];
-    __shared__ int base_s;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    if (t == 0) base_s = 0;
-    __syncthreads();
-    // tiles of kCompactThreads consecutive systems, so that the list comes out in ascending order
-    for (int64_t s0 = 0; s0 < batch; s0 += kCompactThreads) {
-        const int64_t s = s0 + t;
-        const int f = (s < batch && (status[s] & mask) != 0) ? 1 : 0;
-        const unsigned bal = __ballot_sync(0xffffffffu, f);
-        const int before = __popc(bal & ((1u << lane) - 1u));
-        if (lane == 0) warp_tot[warp] = __popc(bal);
-        __syncthreads();
-        int off = base_s;
-        for (int w = 0; w < warp; ++w) off += warp_tot[w];
-        if (f && off + before < cap) list[off + before] = (int32_t)s;
-        __syncthreads();
-        if (t == kCompactThreads - 1) base_s = off + before + f;
-        __syncthreads();
+    const int64_t per = (batch + kCompactThreads - 1) / kCompactThreads;
+    const int64_t s0 = t * per, s1 = s0 + per < batch ? s0 + per : batch;
+    int mine = 0;
+    for (int64_t s = s0; s < s1; ++s) mine += (status[s] & mask) != 0;
+    int incl = mine;  // inclusive scan inside the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
     }
-    if (t == 0) {
-        header[0] = base_s;
-        header[1] = base_s < cap ? base_s : cap;
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int off = incl - mine;
+    for (int w = 0; w < warp; ++w) off += warp_tot[w];
+    for (int64_t s = s0; s < s1; ++s)
+        if ((status[s] & mask) != 0) {
+            if (off < cap) list[off] = (int32_t)s;
+            ++off;
+        }
+    if (t == kCompactThreads - 1) {
+        header[0] = off;
+        header[1] = off < cap ? off : cap;
     }
 }
 
