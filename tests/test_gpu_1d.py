@@ -152,6 +152,39 @@ def test_random_systems_all_kernel_shapes(n):
     assert res["backward"].max() < 1e-15
 
 
+@pytest.mark.parametrize("n,batch", [(9, 40), (1000, 37), (2057, 21), (3001, 12), (4097, 9), (4112, 7), (300, 600)])
+def test_device_side_refinement_of_flagged_subset(n, batch):
+    """fh_tridiag_refine_flagged_c128: exactly the systems flagged FH_STATUS_SMALL_PIVOT get one refinement step (their
+    matrices are read in place through a device-built index list); the others are not touched (bit-for-bit).  Covers
+    the single-CTA kernel, cut rows (odd n), head rows (4112) and a batch that needs several calls (600 flagged systems
+    against a workspace for 256)."""
+    rng = np.random.default_rng(1000 * n + batch)
+    sh = (batch, n)
+    dl = rng.normal(size=sh) + 1j * rng.normal(size=sh)
+    du = rng.normal(size=sh) + 1j * rng.normal(size=sh)
+    d = 4.0 + rng.normal(size=sh) + 1j * rng.normal(size=sh)
+    b = rng.normal(size=sh) + 1j * rng.normal(size=sh)
+    dl[:, 0] = 0.0
+    du[:, -1] = 0.0
+    tens = [torch.as_tensor(a, device="cuda") for a in (dl, d, du, b)]
+    u, status = fh.solve_tridiagonal(*tens, refine=False)
+    assert int(status.abs().sum()) == 0
+    flagged = np.ones(batch, bool) if batch == 600 else rng.random(batch) < 0.4
+    flagged[-1] = True
+    noise = 1e-6 * (rng.normal(size=sh) + 1j * rng.normal(size=sh))
+    u_bad = u.clone() + torch.as_tensor(noise * flagged[:, None], device="cuda")   # spoil the flagged solutions
+    u_ref = u_bad.clone()
+    status = torch.as_tensor(np.where(flagged, 2, 0).astype(np.int32), device="cuda")
+    m = fh.fem1d.refine_flagged(*tens, u_bad, status)
+    assert m == int(flagged.sum())
+    assert int(status.abs().sum()) == 0                       # flags cleared, no new ones
+    keep = torch.as_tensor(~flagged, device="cuda")
+    assert torch.equal(u_bad[keep], u_ref[keep])              # unflagged systems untouched
+    res = fh.tridiagonal_residual(*tens, u_bad)["backward"]
+    assert res.max() < 1e-15, res.max()                       # one step repairs a 1e-6 perturbation
+    assert rel_err(_np(u_bad), _np(u)) < 1e-12
+
+
 def test_singular_system_raises_linalgerror():
     n = 64
     z = np.zeros((1, n), dtype=complex)
