@@ -78,6 +78,10 @@ _SIGNATURES = {
                                               C.c_double, C.c_double, _P]),
     "fh_csr_to_dense_c128": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P]),
     "fh_dense_lu_solve_c128": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P]),
+    "fh_csr_bandwidth": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P]),
+    "fh_band_lu_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int64]),
+    "fh_csr_band_lu_solve_c128": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int64, _P, _P, C.c_size_t,
+                                            _P, _P]),
     "fh_tridiag_solve_pivoted_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "fh_tridiag_solve_pivoted_c128": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, _P, C.c_size_t, _P]),
     "fh_tridiag_residual_vector_c128": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, _P]),

@@ -75,21 +75,6 @@ __device__ __forceinline__ uint32_t map_to_rank(const void *p, uint32_t rank) {
     return r;
 }
 
-// 1/x to ~1 ulp: hardware seed (MUFU.RCP64H, relative error <= 2^-19.9 measured over 2^26 arguments,
-// tools/rcp_probe.cu) + ONE cubically convergent step r (1 + e + e^2), e = 1 - x r: three dependent FMAs instead of the
-// four of two Newton steps (every reciprocal sits on the critical path of an elimination chain); measured error
-// <= 2.2e-16.  Non-finite / zero inputs give NaN or Inf, which the status check reports.
-__device__ __forceinline__ double fast_rcp(double x) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    const double e = fma(-x, r, 1.0);
-    const double p = fma(e, e, e);
-    return fma(r, p, r);
-}
-__device__ __forceinline__ cplx frecip(cplx a) {
-    const double s = fast_rcp(fma(a.re, a.re, a.im * a.im));
-    return mk(a.re * s, -a.im * s);
-}
 // A-posteriori accuracy probe.  The elimination is unpivoted; what it can lose shows up as a defect of the
 // INTERFACE rows (row 7 of every chunk -- interior rows are satisfied by construction of the back-substitution;
 // checked against a numpy model: the largest componentwise row residual always sits on an interface row and

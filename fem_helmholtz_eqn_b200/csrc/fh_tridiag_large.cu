@@ -131,7 +131,7 @@ large_reduce_kernel(Source src, cplx *__restrict__ ra, cplx *__restrict__ rb, cp
                     cplx pa = sm.a[s], pb = sm.b[s], pc = sm.c[s], pd = sm.d[s];
                     for (int i = 2; i < len; ++i) {
                         s = lswz(r0 + i);
-                        const cplx w = sm.a[s] * crecip(pb);
+                        const cplx w = sm.a[s] * frecip(pb);
                         const cplx nb = nmsub(sm.b[s], w, pc), nd = nmsub(sm.d[s], w, pd);
                         pa = -(w * pa), pb = nb, pc = sm.c[s], pd = nd;
                     }
@@ -142,7 +142,7 @@ large_reduce_kernel(Source src, cplx *__restrict__ ra, cplx *__restrict__ rb, cp
                     cplx qa = sm.a[s], qb = sm.b[s], qc = sm.c[s], qd = sm.d[s];
                     for (int i = len - 3; i >= 0; --i) {
                         s = lswz(r0 + i);
-                        const cplx w = sm.c[s] * crecip(qb);
+                        const cplx w = sm.c[s] * frecip(qb);
                         const cplx nb = nmsub(sm.b[s], w, qa), nd = nmsub(sm.d[s], w, qd);
                         qc = -(w * qc), qb = nb, qa = sm.a[s], qd = nd;
                     }
@@ -181,7 +181,7 @@ large_backsub_kernel(Source src, const cplx *__restrict__ xr, cplx *__restrict__
             for (int i = 1; i <= len - 2; ++i) {
                 const int s = lswz(r0 + i);
                 const cplx ai = sm.a[s];
-                const cplx inv = crecip(nmsub(sm.b[s], ai, cp));
+                const cplx inv = frecip(nmsub(sm.b[s], ai, cp));
                 dp = nmsub(sm.d[s], ai, dp) * inv;
                 cp = sm.c[s] * inv;
                 sm.c[s] = cp, sm.d[s] = dp;

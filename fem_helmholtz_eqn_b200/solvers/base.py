@@ -281,19 +281,70 @@ class BaseSolver(ABC):
             self.F = self._F_dev.cpu().numpy()
         return self.K, self.F
 
+    # which device solver np.linalg.solve maps to: "band" (sparse, default) or "dense"; "auto" = band unless the band is
+    # no narrower than the matrix
+    linear_solver = "auto"
+
+    def _band_plan(self):
+        """Bandwidth of K under the mesh's own numbering and, if that is wide (an unstructured gmsh mesh), under a
+        reverse Cuthill-McKee ordering of its pattern (host, scipy; the pattern is a few kilobytes).  Cached per
+        pattern.  Returns ``(perm_or_None, kl, ku)``."""
+        key = ("band", self.K.nnz, self.K.n)
+        if key in self._pattern:
+            return self._pattern[key]
+        lib, n, dev = _lib.require_cuda(), self.K.n, self.K.vals.device
+        klku = torch.zeros(2, dtype=torch.int32, device=dev)
+
+        def width(perm):
+            check(lib.fh_csr_bandwidth(ptr(self.K.rowptr), ptr(self.K.colidx), ptr(perm), n, ptr(klku), stream_ptr()),
+                  "fh_csr_bandwidth")
+            kl, ku = (int(v) for v in klku.tolist())
+            return kl, ku
+
+        perm, (kl, ku) = None, width(None)
+        if 2 * kl + ku + 1 > max(96, n // 6):
+            from scipy.sparse import csr_matrix
+            from scipy.sparse.csgraph import reverse_cuthill_mckee
+            rp, ci = self.K.rowptr.cpu().numpy(), self.K.colidx.cpu().numpy()
+            pat = csr_matrix((np.ones(len(ci), dtype=np.int8), ci, rp), shape=(n, n))
+            order = reverse_cuthill_mckee((pat + pat.T).tocsr(), symmetric_mode=True)   # order[new] = old
+            new_of_old = np.empty(n, dtype=np.int32)
+            new_of_old[order] = np.arange(n, dtype=np.int32)
+            cand = _lib.as_device(new_of_old, torch.int32)
+            kl2, ku2 = width(cand)
+            if 2 * kl2 + ku2 < 2 * kl + ku:
+                perm, kl, ku = cand, kl2, ku2
+        self._pattern[key] = (perm, kl, ku)
+        return self._pattern[key]
+
     def _solve_device(self):
-        """np.linalg.solve(K, F) (fem2d.py:176) -> dense LU with partial pivoting on the device."""
+        """np.linalg.solve(K, F) (fem2d.py:176) on the device: banded LU with partial pivoting on the CSR matrix
+        (``fh_csr_band_lu_solve_c128``), or -- when the band would be as wide as the matrix -- the dense LU."""
         lib, n = _lib.require_cuda(), self.K.n
         dev = self.K.vals.device
-        A = torch.empty((n, n), dtype=torch.complex128, device=dev)
-        check(lib.fh_csr_to_dense_c128(ptr(self.K.rowptr), ptr(self.K.colidx), ptr(self.K.vals), n, ptr(A), stream_ptr()),
-              "fh_csr_to_dense_c128")
-        b = self._F_dev.clone()
         x = torch.empty(n, dtype=torch.complex128, device=dev)
-        piv = torch.empty(n, dtype=torch.int32, device=dev)
         status = torch.zeros(1, dtype=torch.int32, device=dev)
-        check(lib.fh_dense_lu_solve_c128(ptr(A), ptr(b), ptr(x), n, ptr(piv), ptr(status), stream_ptr()),
-              "fh_dense_lu_solve_c128")
+        mode = self.linear_solver
+        if mode not in ("auto", "band", "dense"):
+            raise ValueError("linear_solver must be 'auto', 'band' or 'dense'")
+        if mode != "dense":
+            perm, kl, ku = self._band_plan()
+            if mode == "auto" and 2 * kl + ku + 1 >= n:
+                mode = "dense"
+        if mode != "dense":
+            ws_bytes = lib.fh_band_lu_workspace_bytes(n, kl, ku)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            check(lib.fh_csr_band_lu_solve_c128(ptr(self.K.rowptr), ptr(self.K.colidx), ptr(self.K.vals), ptr(self._F_dev),
+                                                ptr(perm), n, kl, ku, ptr(x), ptr(ws), ws_bytes, ptr(status), stream_ptr()),
+                  "fh_csr_band_lu_solve_c128")
+        else:
+            A = torch.empty((n, n), dtype=torch.complex128, device=dev)
+            check(lib.fh_csr_to_dense_c128(ptr(self.K.rowptr), ptr(self.K.colidx), ptr(self.K.vals), n, ptr(A),
+                                           stream_ptr()), "fh_csr_to_dense_c128")
+            b = self._F_dev.clone()
+            piv = torch.empty(n, dtype=torch.int32, device=dev)
+            check(lib.fh_dense_lu_solve_c128(ptr(A), ptr(b), ptr(x), n, ptr(piv), ptr(status), stream_ptr()),
+                  "fh_dense_lu_solve_c128")
         if int(status.item()) != 0:
             raise np.linalg.LinAlgError("Singular matrix")
         return x

@@ -234,6 +234,18 @@ FH_API int fh_csr_to_dense_c128(const int64_t *rowptr, const int32_t *colidx, co
 FH_API int fh_dense_lu_solve_c128(fh_c128 *A, fh_c128 *b, fh_c128 *x, int64_t n, int32_t *piv, int32_t *status,
                            fh_stream_t stream);
 
+/* *.solve() without the dense matrix: the CSR system is scattered into LAPACK band storage under an
+ * optional node permutation (perm[i] = new index of node i, NULL = identity), factorised with partial pivoting (the
+ * pivot rule and elimination order of zgbtf2 / zgesv, i.e. np.linalg.solve's accuracy) and solved; x comes back in the
+ * original numbering.  kl / ku = lower / upper bandwidth under the permutation, from fh_csr_bandwidth (klku: device
+ * int32[2]).  status: device int32[1], non-zero = singular to working precision. */
+FH_API int fh_csr_bandwidth(const int64_t *rowptr, const int32_t *colidx, const int32_t *perm, int64_t n,
+                     int32_t *klku, fh_stream_t stream);
+FH_API size_t fh_band_lu_workspace_bytes(int64_t n, int64_t kl, int64_t ku);
+FH_API int fh_csr_band_lu_solve_c128(const int64_t *rowptr, const int32_t *colidx, const fh_c128 *vals,
+                              const fh_c128 *b, const int32_t *perm, int64_t n, int64_t kl, int64_t ku, fh_c128 *x,
+                              void *workspace, size_t workspace_bytes, int32_t *status, fh_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
