@@ -165,7 +165,7 @@ def workload_config(n_gpus):
             "n_elem": N_ELEM, "n_k_per_gpu": N_K_PER_GPU, "n_k_total": N_K_PER_GPU * n_gpus,
             "dof_per_step": N_K_PER_GPU * n_gpus * (N_ELEM + 1),
             "pipeline": "staged: fh_assemble_1d_c128 -> fh_tridiag_solve_batched_c128",
-            "parallelism": f"k-sharded x{n_gpus}, no data-path collective",
+            "parallelism": f"k-sharded x{n_gpus} (rank r owns ks[r::{n_gpus}]), no data-path collective",
             "l2": "inputs larger than L2 (17.2 GB of bands + 4.3 GB of solutions per step; no flush needed)"}
 
 
@@ -196,7 +196,9 @@ def run_gpu(args):
 
     n, n_k = N_ELEM + 1, args.n_k
     ks_global = np.linspace(K_MIN, K_MAX, n_k * world)
-    ks_h = ks_global[rank * n_k:(rank + 1) * n_k]
+    # cyclic sharding: every rank sees the same mix of wavenumbers (a contiguous slice of the top of the range flags
+    # 13 % of its systems for refinement, one of the bottom 0.2 % -- the slowest rank sets the step time)
+    ks_h = np.ascontiguousarray(ks_global[rank::world])
     k2s_h = ks_h**2
     ks_d = torch.from_numpy(ks_h).to(dev)
     k2s_d = torch.from_numpy(k2s_h).to(dev)
@@ -246,7 +248,7 @@ def run_gpu(args):
         t_end.record()
         barrier()
     flagged, done = (int(v) for v in fem1d._refine_workspace(n, n_k, dev)[:8].view(torch.int32).tolist())
-    assert flagged == done, "more systems flagged than one refinement call handles: use refine_flagged(sync=True)"
+    assert flagged == done, "more systems flagged than the workspace sized during warm-up holds"
     refined = [done] * args.steps
     total_ms = t_begin.elapsed_time(t_end)
     asm_ms = [e[0].elapsed_time(e[1]) for e in ev]
@@ -288,10 +290,11 @@ def run_gpu(args):
 
     # max over ranks
     vals = torch.tensor([total_ms, e2e["seconds"] if e2e else 0.0, fused_ms,
-                         statistics.mean(sol_ms), statistics.mean(asm_ms)], dtype=torch.float64, device=dev)
+                         statistics.mean(sol_ms), statistics.mean(asm_ms), float(done), backward_max],
+                        dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-    total_ms, e2e_s, fused_ms, sol_mean, asm_mean = vals.tolist()
+    total_ms, e2e_s, fused_ms, sol_mean, asm_mean, refined_max, backward_max = vals.tolist()
 
     if rank == 0:
         dof_rank = n_k * n
@@ -319,7 +322,7 @@ def run_gpu(args):
             "stages": {"assembly_ms": asm_mean, "solve_ms": sol_mean, "refine_ms": statistics.mean(ref_ms),
                        "solve_ms_per_step": [round(v, 3) for v in sol_ms],
                        "refined_per_step": refined,
-                       "refined_systems_per_step": statistics.mean(refined),
+                       "refined_systems_per_step_max_over_ranks": int(refined_max), "refined_systems_per_step": statistics.mean(refined),
                        "assembly_gbs": BYTES_ASSEMBLY * dof_rank / (asm_mean * 1e-3) / 1e9,
                        "assembly_frac": BYTES_ASSEMBLY * dof_rank / (asm_mean * 1e-3) / 1e9 / peak,
                        "staged_gbs": (BYTES_ASSEMBLY + BYTES_SOLVE) * dof_rank / (ms_per_step * 1e-3) / 1e9,

@@ -125,24 +125,40 @@ def solve_partitioned(N, k, L=1.0, theta=0.0, *, group=None, ops=None, gather=Fa
     return 0, n, torch.cat([out[r, :sizes[r]] for r in range(world)])
 
 
-def sweep_sharded(N, ks, L=1.0, theta=0.0, *, group=None, gather=False, solver=None, **kw):
-    """Wavenumber sweep sharded over the ranks of ``group``: rank r solves ``ks[k_slice(...)]``.
+def sweep_sharded(N, ks, L=1.0, theta=0.0, *, group=None, gather=False, solver=None, layout="contiguous", **kw):
+    """Wavenumber sweep sharded over the ranks of ``group``.
 
-    Returns ``(lo, hi, U_local)``; with ``gather=True`` every rank gets ``(0, n_k, U)`` (the only collective
-    of the sweep, an all-gather of the solutions).  ``solver(N, ks_local, L, theta, **kw) -> (nodes, U)`` defaults
-    to :func:`fem1d.solve_helmholtz_sweep`."""
-    import torch.distributed as dist
+    ``layout="contiguous"``: rank r solves ``ks[k_slice(...)]`` and gets ``(lo, hi, U_local)``.
+    ``layout="cyclic"``: rank r solves ``ks[r::world]`` and gets ``(r, world, U_local)`` -- the shards then see the
+    same mix of wavenumbers, which balances the one data-dependent cost of the path (the selective refinement: on a
+    sweep over k in [1, 1000] the top eighth of the range flags 13 % of its systems, the bottom eighth 0.2 %).
+    With ``gather=True`` every rank gets ``(0, n_k, U)`` in the order of ``ks`` (the only collective of the sweep, an
+    all-gather of the solutions).  ``solver(N, ks_local, L, theta, **kw) -> (nodes, U)`` defaults to
+    :func:`fem1d.solve_helmholtz_sweep`."""
     world, rank = _world(group)
     ks_h = np.asarray(ks.detach().cpu().numpy() if isinstance(ks, torch.Tensor) else ks, dtype=np.float64).ravel()
-    lo, hi = k_slice(len(ks_h), world, rank)
+    if layout not in ("contiguous", "cyclic"):
+        raise ValueError("layout must be 'contiguous' or 'cyclic'")
     solver = solver if solver is not None else fem1d.solve_helmholtz_sweep
-    _, U = solver(N, ks_h[lo:hi], L, theta, **kw)
+    if layout == "cyclic":
+        _, U = solver(N, ks_h[rank::world], L, theta, **kw)
+        sizes = [len(range(r, len(ks_h), world)) for r in range(world)]
+        head = (rank, world)
+    else:
+        lo, hi = k_slice(len(ks_h), world, rank)
+        _, U = solver(N, ks_h[lo:hi], L, theta, **kw)
+        sizes = [k_slice(len(ks_h), world, r)[1] - k_slice(len(ks_h), world, r)[0] for r in range(world)]
+        head = (lo, hi)
     if not gather or world == 1:
-        return (lo, hi, U) if not gather else (0, len(ks_h), U)
+        return head + (U,) if not gather else (0, len(ks_h), U)
     n = U.shape[1]
-    sizes = [k_slice(len(ks_h), world, r)[1] - k_slice(len(ks_h), world, r)[0] for r in range(world)]
     pad = max(sizes)
     buf = torch.zeros((pad, n), dtype=U.dtype, device=U.device)
     buf[:U.shape[0]] = U
     out = _all_gather(buf, world, group)
+    if layout == "cyclic":
+        full = torch.empty((len(ks_h), n), dtype=U.dtype, device=U.device)
+        for r in range(world):
+            full[r::world] = out[r, :sizes[r]]
+        return 0, len(ks_h), full
     return 0, len(ks_h), torch.cat([out[r, :sizes[r]] for r in range(world)])

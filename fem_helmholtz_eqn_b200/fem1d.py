@@ -227,18 +227,19 @@ def assembly(N: int, k, h: float, elements=None, theta=0.0, *, bc_left="neumann"
 _refine_ws = {}
 
 
-def _refine_workspace(n, batch, device):
-    """Workspace of fh_tridiag_refine_flagged_c128, sized for batch/16 systems per call (a fine sweep flags 2-3 % of its
-    wavenumbers) and kept between calls: allocating half a gigabyte per step would cost more than the refinement."""
+def _refine_workspace(n, batch, device, min_systems=0):
+    """Workspace of fh_tridiag_refine_flagged_c128, kept between calls (allocating it per step would cost more than the
+    refinement).  Sized for batch/16 systems per call to begin with (a fine sweep flags 2-3 % of its wavenumbers) and
+    grown when a batch turns out to flag more (``min_systems``)."""
     lib = _lib.load()
-    cap = min(batch, max(256, batch // 16))
     key = (n, batch, device)
-    ws = _refine_ws.get(key)
-    if ws is None:
+    ent = _refine_ws.get(key)
+    cap = min(batch, max(256, batch // 16, int(min_systems)))
+    if ent is None or ent[0] < cap:
         _refine_ws.clear()
         nbytes = lib.fh_tridiag_refine_flagged_workspace_bytes(n, batch, cap)
-        ws = _refine_ws[key] = torch.empty(nbytes, dtype=torch.uint8, device=device)
-    return ws
+        ent = _refine_ws[key] = (cap, torch.empty(nbytes, dtype=torch.uint8, device=device))
+    return ent[1]
 
 
 def refine_flagged(dl, d, du, b, u, status, sync=True):
@@ -264,6 +265,9 @@ def refine_flagged(dl, d, du, b, u, status, sync=True):
         total += refined
         if flagged <= refined:
             return total
+        # more flagged systems than the workspace holds: finish them now, and size the workspace for the next batch
+        # of this shape (so that a later sync=False call covers it in one go)
+        ws = _refine_workspace(n, batch, d.device, min_systems=flagged + flagged // 4)
 
 
 def resolve_nonfinite(dl, d, du, b, u, status):

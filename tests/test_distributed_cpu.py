@@ -62,8 +62,11 @@ def _worker(rank, world, port, results):
         ks = np.linspace(1.0, 50.0, 7)
         lo, hi, U_loc = fh_dist.sweep_sharded(64, ks, solver=_numpy_sweep)
         _, n_k, U_all = fh_dist.sweep_sharded(64, ks, solver=_numpy_sweep, gather=True)
+        r_c, w_c, U_cyc = fh_dist.sweep_sharded(64, ks, solver=_numpy_sweep, layout="cyclic")
+        _, _, U_cyc_all = fh_dist.sweep_sharded(64, ks, solver=_numpy_sweep, layout="cyclic", gather=True)
         results[rank] = dict(begin=begin, end=end, u_loc=u_loc.numpy(), u_all=u_all.numpy(), lo=lo, hi=hi,
-                             U_loc=U_loc.numpy(), U_all=U_all.numpy(), n_k=n_k)
+                             U_loc=U_loc.numpy(), U_all=U_all.numpy(), n_k=n_k, cyc=(r_c, w_c),
+                             U_cyc=U_cyc.numpy(), U_cyc_all=U_cyc_all.numpy())
     finally:
         dist.destroy_process_group()
 
@@ -103,6 +106,10 @@ def test_world_size_2_partitioned_solve_and_sharded_sweep():
     assert np.array_equal(np.concatenate([results[0]["U_loc"], results[1]["U_loc"]]), Uref.numpy())
     for r in range(world):
         assert results[r]["n_k"] == 7 and np.array_equal(results[r]["U_all"], Uref.numpy())
+        # cyclic layout: rank r owns ks[r::world]; the gathered result is back in the order of ks
+        assert results[r]["cyc"] == (r, world)
+        assert np.array_equal(results[r]["U_cyc"], Uref.numpy()[r::world])
+        assert np.array_equal(results[r]["U_cyc_all"], Uref.numpy())
 
 
 def test_single_process_path_needs_no_process_group():
