@@ -6,27 +6,32 @@
 //      its interior couplings with a downward and an upward elimination sweep (pivots are kept as
 //      reciprocals), leaving  a_i x_left + b_i x_i + c_i x_last = d_i  (i < 7) and one interface
 //      row per thread;
-//   2. the 256 interface rows of a CTA are solved by parallel cyclic reduction (PCR) in shared
-//      memory, <= 8 levels, rows kept normalised (unit diagonal);
+//   2. the 256 interface rows of a CTA (unit diagonal) are solved in shared memory: one cyclic-reduction
+//      step keeps the 128 odd rows; those are solved by <= 7 levels of parallel cyclic reduction with two
+//      threads per row (even lane: couplings A and right-hand side D, odd lane: C and the cut column V);
+//      the even rows follow from their own equation;
 //   3. back-substitution in registers; the solution is staged in shared memory and leaves with one
 //      TMA tensor store.
 //   A system of up to 2056 rows is handled by one CTA; up to 4112 rows by a 2-CTA cluster: rank 0
-//   takes the first half, rank 1 the second half in REVERSED row order, so both halves end at the
-//   cut.  Each half carries one extra PCR right-hand side (its coupling to the partner's interface
-//   unknown); the two coupled interface values are exchanged through distributed shared memory
-//   with st.async + mbarrier complete_tx (no cluster-wide barrier, no fence).
+//   takes the first half, rank 1 the last half in REVERSED row order, so both halves end at the cut;
+//   for odd n the middle row (the "cut row") belongs to neither.  Each half carries one extra
+//   right-hand side V (its coupling to the cut unknown / the partner's cut-side unknown); the two
+//   (D, V) pairs are exchanged through distributed shared memory with st.async + mbarrier
+//   complete_tx (no cluster-wide barrier, no fence) and both CTAs solve the small cut system.
 //
-// Data movement (staged variant): the CTA is persistent.  While system s is processed from
-// registers, the four band tiles of system s + stride are in flight: one elected thread issues four
-// TMA tensor loads (cp.async.bulk.tensor.3d, 32 KB each, 128-byte swizzle) that complete on an
-// mbarrier.  The tensor view of a band array is [system][chunk of 8 rows][8 complex]; the
-// hardware swizzle makes the later per-thread chunk reads (stride 128 B) bank-conflict free.  Rows
-// that do not fill a chunk (n mod 8, at most 8 "head" rows at the far end) travel by cp.async and
-// are eliminated serially by one thread.  HBM traffic = algorithmic traffic: 64 B/row read +
-// 16 B/row written (ncu: profiles/).
+// Data movement (staged variant): the CTA is persistent.  While system s is processed, the four band
+// tiles of system s + stride are in flight: one elected thread issues four TMA tensor loads
+// (cp.async.bulk.tensor.3d, 32 KB each, 128-byte swizzle) that complete on an mbarrier.  The tensor
+// view of a band array is [system][chunk of 8 rows][8 complex]; the hardware swizzle makes the
+// per-thread chunk reads (stride 128 B) bank-conflict free; they are interleaved with the downward
+// sweep.  Rows that do not fill a chunk (at most 8 "head" rows per half, none for n = 4097) travel by
+// cp.async and are eliminated serially by one thread.  HBM traffic = algorithmic traffic: 64 B/row
+// read + 16 B/row written (ncu: profiles/).
 //
 // Fused variant: the same kernel with the band loads replaced by the row generator of
 // fh_helm1d.cuh (bit-identical to what fh_assemble_1d_c128 would have stored); 16 B/row written.
+// Subset variant (BandSubsetSource): matrices picked through a device index list -- the correction
+// solve of fh_tridiag_refine_flagged_c128.
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
@@ -36,18 +41,16 @@ namespace cg = cooperative_groups;
 
 namespace fh {
 
-#ifndef FH_PAIR_ROWS
-#define FH_PAIR_ROWS 8
-#endif
-constexpr int kM = FH_PAIR_ROWS;               // rows per thread (register chunk): 8 or 4
-constexpr int kT = 2048 / kM;                  // threads per CTA: 256 or 512
+constexpr int kM = 8;                          // rows per thread (register chunk)
+constexpr int kT = 2048 / kM;                  // threads per CTA: 256
 constexpr int kSlots = kT * kM;                // 2048 body rows per CTA
 constexpr int kChunks8 = kSlots / 8;           // 8-row memory chunks (TMA tile rows) per CTA: 256
-constexpr int kPer8 = 8 / kM;                  // threads sharing one memory chunk: 1 or 2
-static_assert(kM == 8 || kM == 4, "register chunk must be 8 or 4 rows");
+constexpr int kPer8 = 8 / kM;                  // threads sharing one memory chunk: 1
+// (a 4-row / 512-thread variant was measured earlier in the round: twice the interface rows, no faster, and its
+// interface arrays no longer fit next to the staging tiles)
 constexpr int kHeadMax = 8;                    // extra rows at the far end, eliminated serially
 constexpr int kStageRows = kSlots + kHeadMax;  // 2056
-constexpr int kLevelsMax = kM == 8 ? 8 : 9;    // log2(kT)
+constexpr int kLevelsMax = 8;                  // log2(kT)
 constexpr uint32_t kTileBytes = kSlots * sizeof(cplx);  // 32 KB per band tile
 
 // single-thread duties are spread over warps (whichever warp carries one is late for the next barrier): the band
