@@ -408,8 +408,10 @@ class HostSweepPlan:
     sets of device buffers so that chunk i+1 is assembled+solved while chunk i is copied back.  (Pinning
     gigabytes of host memory costs about a second, so a caller that sweeps repeatedly keeps the plan.)"""
 
-    def __init__(self, N, n_k, chunk=None):
+    def __init__(self, N, n_k, chunk=None, numa_local=True):
         _lib.require_cuda()
+        # pinned buffers on the GPU's own NUMA node (matters with one process per GPU on a two-socket host)
+        self.cpu_cores = _lib.bind_host_thread_near_device() if numa_local else None
         self.N, self.n, self.n_k = int(N), int(N) + 1, int(n_k)
         if chunk is None:  # ~256 MB of solution per chunk keeps both the copy engine and the SMs busy
             chunk = max(1, min(self.n_k, (256 << 20) // (16 * self.n)))
