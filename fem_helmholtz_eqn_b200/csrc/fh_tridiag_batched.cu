@@ -608,8 +608,12 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
             const cplx r = nmsub(nmsub(nmsub(d7o, a7o, x6), b7o, X), c7o, xn);
             const double scale = abs1(a7o) * abs1(x6) + abs1(b7o) * abs1(X) + abs1(c7o) * abs1(xn) + abs1(d7o);
             const bool off = active && abs1(r) > kProbeTol * scale;
+            // a defect that one refinement step cannot be trusted to repair counts as a breakdown: bit 0 sends the
+            // system to the pivoted re-solve, exactly like a non-finite value
+            const bool severe = active && abs1(r) > kSevereTol * scale;
             // rare: one global atomic per affected warp (status[] was zeroed by the host wrapper)
-            if (__any_sync(0xffffffffu, off) && (t & 31) == 0 && status != nullptr) atomicOr(&status[sys], 2);
+            const bool any_off = __any_sync(0xffffffffu, off), any_severe = __any_sync(0xffffffffu, severe);
+            if (any_off && (t & 31) == 0 && status != nullptr) atomicOr(&status[sys], any_severe ? 3 : 2);
         }
         FH_TR(12);
     }

@@ -82,6 +82,9 @@ __device__ __forceinline__ uint32_t map_to_rank(const void *p, uint32_t rank) {
 // coefficients of its row 7 and re-evaluates that one equation with the computed solution; a relative defect above
 // kProbeTol sets status bit 1, and the host refines exactly those systems (~2 % of a fine wavenumber sweep).
 constexpr double kProbeTol = 5e-14;
+// ... and above kSevereTol bit 0 as well (treated like a non-finite value: pivoted re-solve).  One refinement step
+// squares the relative error of the unpivoted solve, so 1e-8 is where it stops being enough for 1e-13.
+constexpr double kSevereTol = 1e-8;
 __device__ __forceinline__ double abs1(cplx z) { return fabs(z.re) + fabs(z.im); }
 
 // ---------------------------------------------------------------------------------------------- band sources

@@ -120,8 +120,8 @@ def _check_elements(N, elements):
         raise ValueError("only the reference's canonical connectivity [[i, i+1]] is supported")
 
 
-STATUS_NONFINITE = 1    # the solution holds a NaN / Inf (zero pivot, singular system)
-STATUS_SMALL_PIVOT = 2  # a pivot fell below 1e-3 of its scale; cleared again once the system has been refined
+STATUS_NONFINITE = 1    # breakdown of the unpivoted solve: NaN / Inf (zero pivot, singular system) or a defect > 1e-8
+STATUS_SMALL_PIVOT = 2  # the interface-row probe found a defect > 5e-14; cleared again once the system has been refined
 
 
 def _raise_if_singular(status):

@@ -87,10 +87,13 @@ FH_API int fh_assemble_1d_c128(const fh_problem1d *prob_host, const double *ks, 
 /* ---- batched tridiagonal solve (replaces nb:204 `np.linalg.solve(A, b)` for tridiagonal A) ------
  * Thread-chunk partition (8 rows per thread in registers) + parallel cyclic reduction of the
  * per-thread interface rows in shared memory; a 2-CTA cluster solves one system when n > 2056.
- * status[batch] (device int32, may be NULL): bit 0 set if the solution holds a non-finite value
- * (zero pivot / singular system); bit 1 set if the unpivoted elimination met a pivot below 1e-3 of its
- * scale (backward error may exceed ~1e-13: refine that system, see fh_tridiag_residual_vector_c128).  n <= fh_tridiag_batched_max_n() takes the cluster kernel, larger
- * n is routed to the partitioned large-system solver using `workspace`. */
+ * status[batch] (device int32, may be NULL): bit 0 (FH_STATUS_NONFINITE) set if the unpivoted elimination broke
+ * down -- the solution holds a non-finite value (zero pivot / singular system) or the a-posteriori probe found a
+ * relative defect above 1e-8: re-solve that system with fh_tridiag_solve_pivoted_c128; bit 1
+ * (FH_STATUS_SMALL_PIVOT) set if the probe -- every thread re-evaluates the original equation of its interface row
+ * with the computed solution -- found a relative defect above 5e-14 (backward error may exceed ~1e-13: refine that
+ * system, see fh_tridiag_refine_flagged_c128).  n <= fh_tridiag_batched_max_n() takes the cluster kernel, larger n
+ * is routed to the partitioned large-system solver using `workspace`. */
 FH_API int64_t fh_tridiag_batched_max_n(void);
 FH_API size_t fh_tridiag_solve_batched_workspace_bytes(int64_t n, int64_t batch);
 FH_API int fh_tridiag_solve_batched_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c128 *du,
