@@ -372,13 +372,14 @@ def solve_helmholtz_sweep(N, ks, L=1.0, theta=0.0, *, bc_left="neumann", bc_righ
                     C.byref(prob), float(ks_h[i]), float(k2s_h[i]), ptr(U[i]), ptr(status[i:i + 1]), ptr(ws),
                     ws_bytes, stream_ptr()), "fh_helmholtz1d_solve_large_fused_c128")
     if fused and n <= lib.fh_tridiag_batched_max_n():
-        idx = torch.nonzero((status & STATUS_SMALL_PIVOT) != 0).flatten()
-        if idx.numel() > 0:  # the fused kernel stores no bands: assemble them for the few flagged wavenumbers
+        idx = torch.nonzero(status != 0).flatten()
+        if idx.numel() > 0:
+            # the fused kernel stores no bands: assemble them for the few flagged wavenumbers and solve those again
+            # through the staged path (pivoted re-solve of breakdowns, refinement of small-pivot systems)
             sel = idx.cpu().numpy()
             bands = assemble_bands(N, (ks_h[sel], k2s_h[sel]), h, theta, bc_left=bc_left, bc_right=bc_right,
                                    g_left=g_left, g_right=g_right, nodes=nodes if nodal_h else None)
-            u_sub, st_sub = U.index_select(0, idx), status.index_select(0, idx)
-            refine_flagged(*bands, u_sub, st_sub)
+            u_sub, st_sub = solve_tridiagonal(*bands)
             U.index_copy_(0, idx, u_sub)
             status.index_copy_(0, idx, st_sub)
     if check_singular:
@@ -465,7 +466,9 @@ def solve_helmholtz_sweep_host(N, ks, L=1.0, theta=0.0, *, plan=None, fused=Fals
                                           ptr(b), stream_ptr()), "fh_assemble_1d_c128")
             check(lib.fh_tridiag_solve_batched_c128(ptr(dl), ptr(d), ptr(du), ptr(b), ptr(U), plan.n, m, ptr(st),
                                                     None, 0, stream_ptr()), "fh_tridiag_solve_batched_c128")
-            refine_flagged(dl, d, du, b, U, st)
+            # stream-ordered (no host round trip inside the pipeline); whatever one call cannot take is finished below
+            _refine_workspace(plan.n, m, d.device, min_systems=m // 4)
+            refine_flagged(dl, d, du, b, U, st, sync=False)
         ready = torch.cuda.Event()
         ready.record(main)
         with torch.cuda.stream(plan.copy_stream):
@@ -475,6 +478,19 @@ def solve_helmholtz_sweep_host(N, ks, L=1.0, theta=0.0, *, plan=None, fused=Fals
             done[slot].record(plan.copy_stream)
     main.wait_stream(plan.copy_stream)
     status_host = plan.status.cpu()  # synchronises: everything above has finished
+    left = torch.nonzero(status_host != 0).flatten()
+    if left.numel() > 0:
+        # breakdowns of the unpivoted kernels, flagged systems of the fused variant (which keeps no bands), or more
+        # flagged systems in a chunk than its refinement workspace holds: solve those wavenumbers again through the
+        # staged path (pivoted re-solve + refinement) and patch their rows of the result
+        sel = left.numpy()
+        bands = assemble_bands(N, (ks_h[sel], k2s_h[sel]), h, theta, bc_left=bc.get("bc_left", "neumann"),
+                               bc_right=bc.get("bc_right", "sommerfeld"), g_left=bc.get("g_left", 1.0),
+                               g_right=bc.get("g_right", 0.0))
+        u_fix, st_fix = solve_tridiagonal(*bands)
+        plan.U_host[left] = u_fix.cpu()
+        status_host[left] = st_fix.cpu()
+        plan.status.copy_(status_host)
     if check_singular and bool(torch.any((status_host & STATUS_NONFINITE) != 0)):
         bad = torch.nonzero(status_host & STATUS_NONFINITE).flatten()[:8].tolist()
         raise np.linalg.LinAlgError(f"Singular matrix (zero pivot / non-finite solution) in systems {bad}")

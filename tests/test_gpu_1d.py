@@ -292,3 +292,19 @@ def test_zero_pivot_is_resolved_by_the_pivoted_fallback():
     bands = fh.assemble_bands(64, 128.0, 1.0 / 64)
     _, st = fh.solve_tridiagonal(*bands, refine=False)
     assert int(st[0]) & 1
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_host_sweep_repairs_breakdowns_and_flagged_systems(fused):
+    """solve_helmholtz_sweep_host and the fused sweep keep the accuracy of the staged device path: systems the
+    unpivoted kernels flag (small pivot) or break on (k*h = 2: exact zero pivot) are solved again through the staged
+    path and their rows of the result patched -- also in the fused variant, which keeps no bands to refine from."""
+    N = 4096
+    ks = np.concatenate([np.linspace(900.0, 1000.0, 2047), [2.0 * N]])        # last entry: k*h = 2
+    nodes, U = fh.fem1d.solve_helmholtz_sweep_host(N, ks, fused=fused)
+    dl, d, du, b = fh.assemble_bands(N, ks, 1.0 / N)
+    res = fh.tridiagonal_residual(dl, d, du, b, U)["backward"]
+    assert res.max() < 1e-13, res.max()
+    _, U_dev = fh.solve_helmholtz_sweep(N, ks, fused=fused)
+    assert fh.tridiagonal_residual(dl, d, du, b, U_dev)["backward"].max() < 1e-13
+    assert rel_err(U[-1], banded1d.solve_bands(*banded1d.assemble_bands(N, float(ks[-1]), 1.0 / N))) < 1e-11
