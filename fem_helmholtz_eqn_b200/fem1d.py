@@ -387,6 +387,71 @@ def solve_helmholtz_sweep(N, ks, L=1.0, theta=0.0, *, bc_left="neumann", bc_righ
     return (nodes, U, status) if return_status else (nodes, U)
 
 
+class LargeMeshPlan:
+    """One long mesh, many solves (BASELINE configs 2 and 5: N = 10^6, a new wavenumber per call).  At that size the
+    work is 0.15 GB -- tens of microseconds of HBM time -- and the path is bound by its nine dependent kernel launches
+    (assembly, three reduction levels, the coarse cluster solve, three back-substitution levels).  The plan owns the
+    buffers and a captured CUDA graph of the whole sequence; ``solve(k)`` updates (k, k**2) in device memory and
+    replays it.  Results are bit-identical to ``solve_helmholtz_sweep(N, [k])``."""
+
+    def __init__(self, N, L=1.0, theta=0.0, *, bc_left="neumann", bc_right="sommerfeld", g_left=1.0, g_right=0.0,
+                 use_graph=True):
+        lib = _lib.require_cuda()
+        self.N, self.n, self.L = int(N), int(N) + 1, float(L)
+        dev = _lib.device()
+        self.k_host = torch.empty(2, dtype=torch.float64).pin_memory()
+        self.k_dev = torch.zeros(2, dtype=torch.float64, device=dev)
+        self.bands = torch.empty((4, 1, self.n), dtype=torch.complex128, device=dev)
+        self.U = torch.empty((1, self.n), dtype=torch.complex128, device=dev)
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        ws_bytes = lib.fh_tridiag_solve_batched_workspace_bytes(self.n, 1)
+        self.ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        self._prob = _problem(N, L / N, theta, bc_left, bc_right, g_left, g_right, None)
+        self.graph = None
+        self._set_k(1.0)
+        self._launch()                      # warm-up: module load, function attributes, driver entry points
+        torch.cuda.synchronize()
+        if use_graph:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._launch()
+            torch.cuda.current_stream().wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._launch()
+
+    def _set_k(self, k):
+        self.k_host[0], self.k_host[1] = float(k), float(k**2)   # nb:185: k**2 evaluated on the host
+        self.k_dev.copy_(self.k_host, non_blocking=True)
+
+    def _launch(self):
+        lib, B = _lib.load(), self.bands
+        check(lib.fh_assemble_1d_c128(C.byref(self._prob), ptr(self.k_dev[0:1]), ptr(self.k_dev[1:2]), 1, ptr(B[0]),
+                                      ptr(B[1]), ptr(B[2]), ptr(B[3]), stream_ptr()), "fh_assemble_1d_c128")
+        check(lib.fh_tridiag_solve_batched_c128(ptr(B[0]), ptr(B[1]), ptr(B[2]), ptr(B[3]), ptr(self.U), self.n, 1,
+                                                ptr(self.status), ptr(self.ws), self.ws.numel(), stream_ptr()),
+              "fh_tridiag_solve_batched_c128")
+
+    def solve(self, k):
+        """Assemble and solve for wavenumber ``k``; returns the device tensor complex128[N+1] (valid until the next
+        call).  Stream-ordered on the current stream; ``status`` is checked by :meth:`solution`."""
+        self._set_k(k)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._launch()
+        return self.U[0]
+
+    def solution(self, k):
+        """``solve_helmholtz_fem(N, k)`` for this mesh: ``(nodes, u)`` as numpy arrays."""
+        u = self.solve(k)
+        out = u.cpu().numpy()
+        if int(self.status.item()) & STATUS_NONFINITE:      # rare: take the general path (pivoted re-solve)
+            return solve_helmholtz_fem(self.N, k, L=self.L)
+        return np.linspace(0, self.L, self.N + 1), out
+
+
 def solve_helmholtz_fem(N, k, order=0, L=1.0, *, theta=0.0, bc_left="neumann", bc_right="sommerfeld",
                         g_left=1.0, g_right=0.0, fused=False):
     """nb:190-205 -> ``(nodes, u)`` as numpy arrays (``order`` is accepted and ignored, as in the

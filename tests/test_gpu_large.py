@@ -187,3 +187,22 @@ def test_nccl_partitioned_two_gpus(tmp_path):
                           "--master-addr", "127.0.0.1", "--master-port", "29731", str(script)], env=env,
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_large_mesh_plan_replays_a_cuda_graph_bit_identically():
+    """fem1d.LargeMeshPlan (configs 2 / 5 are launch-bound): assembly + recursive-partition solve captured once as a
+    CUDA graph and replayed per wavenumber -- same bits as the eager path, same answer as the CPU oracle."""
+    N = 200_000
+    plan = fh.fem1d.LargeMeshPlan(N)
+    assert plan.graph is not None
+    for k in (10.0, 1000.0, 37.25):
+        u = plan.solve(k).clone()
+        _, U = fh.solve_helmholtz_sweep(N, [k])
+        assert torch.equal(u, U[0])
+    nodes, u = plan.solution(10.0)
+    bands = banded1d.assemble_bands(N, 10.0, 1.0 / N)
+    # (forward error is cond(A) * eps ~ 1e-9 at this size for LAPACK too: gate on the backward error)
+    assert nodes.shape == (N + 1,) and rel_err(u, banded1d.solve_bands(*bands)) < 1e-7
+    assert banded1d.residual_metrics(*bands, u)[0] < 1e-15
+    eager = fh.fem1d.LargeMeshPlan(N, use_graph=False)
+    assert torch.equal(eager.solve(10.0), plan.solve(10.0))

@@ -58,6 +58,13 @@ def main():
             med_a, _ = timed(lambda: fh.assemble_bands(N, k, 1.0 / N, out=torch.stack([dl, d, du, b])), flush=flush)
             med_s, min_s = timed(lambda: fh.solve_tridiagonal(dl, d, du, b, refine=False), flush=flush)
             med_f, min_f = timed(lambda: fh.solve_helmholtz_sweep(N, [k], fused=True, check_singular=False), flush=flush)
+            plan = fh.fem1d.LargeMeshPlan(N)
+            med_g, min_g = timed(lambda: plan.solve(k), flush=flush)
+            warm_g, _ = timed(lambda: plan.solve(k), reps=20)
+            assert torch.equal(plan.solve(k), fh.solve_tridiagonal(dl, d, du, b, refine=False)[0][0])
+            out[name + "_graph"] = {"assemble_plus_solve_ms_cold_l2": med_g, "min_ms": min_g, "warm_l2_ms": warm_g,
+                                    "dof_per_s": (N + 1) / (med_g * 1e-3)}
+            del plan
             out[name] = {"assemble_ms": med_a, "solve_large_ms": med_s, "solve_large_min_ms": min_s,
                          "fused_ms": med_f, "fused_min_ms": min_f,
                          "staged_dof_per_s": (N + 1) / ((med_a + med_s) * 1e-3), "fused_dof_per_s": (N + 1) / (med_f * 1e-3)}
