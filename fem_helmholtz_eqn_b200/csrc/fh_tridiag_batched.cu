@@ -496,6 +496,8 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
         constexpr uint32_t kArr = kHalfStride * sizeof(cplx);
         const uint32_t hb0 = smem_u32(&sm.half[0][0][kHalfPad + j]), hb1 = smem_u32(&sm.half[1][0][kHalfPad + j]);
         const uint32_t o_val = va * kArr, o_own = role * kArr;
+        // the partner lane's coupling travels by shuffle, issued BEFORE the barrier so that its latency hides behind it
+        cplx oth = mk(__shfl_xor_sync(0xffffffffu, own.re, 1), __shfl_xor_sync(0xffffffffu, own.im, 1));
         sts_volatile(hb0 + o_val, xv);
         sts_volatile(hb0 + o_own, own);
         __syncthreads();
@@ -506,11 +508,11 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
             const cplx Cm = lds_volatile(rd + kArr - sb), Ap = lds_volatile(rd + sb);
             const cplx Xm = lds_volatile(rd + o_val - sb), Xp = lds_volatile(rd + o_val + sb);
             const cplx Q = lds_volatile(rd + o_own + (role ? sb : -sb));  // own array, own side
-            const cplx oth = mk(__shfl_xor_sync(0xffffffffu, own.re, 1), __shfl_xor_sync(0xffffffffu, own.im, 1));
             const cplx Aj = role ? oth : own, Cj = role ? own : oth;
             const PcrPivot pv = pcr_pivot(Aj, Cm, Cj, Ap);
-            xv = pcr_scale(nmsub(nmsub(xv, Aj, Xm), Cj, Xp), pv);
             own = -pcr_scale(own * Q, pv);
+            oth = mk(__shfl_xor_sync(0xffffffffu, own.re, 1), __shfl_xor_sync(0xffffffffu, own.im, 1));
+            xv = pcr_scale(nmsub(nmsub(xv, Aj, Xm), Cj, Xp), pv);
             sts_volatile(wr + o_val, xv);
             sts_volatile(wr + o_own, own);  // (not needed after the last level; kept for uniformity)
             cur ^= 1;
