@@ -8,7 +8,7 @@ All numerical work happens in hand-written CUDA kernels reached through the C AB
 ``include/fem_helmholtz.h``; importing the package does not need a GPU, calling it does.
 """
 from . import _lib  # noqa: F401
-from .fem1d import (TridiagonalSystem, analytical_solution, assemble_bands, assembly,  # noqa: F401
+from .fem1d import (TridiagonalSystem, analytical_solution, assemble_and_solve, assemble_bands, assembly,  # noqa: F401
                     boundary_matrices, compute_L2_error, convergence_test, create_mesh, element_matrices, gauss_point, gauss_weight,
                     shape_functions, solve_helmholtz_fem, solve_helmholtz_sweep, solve_tridiagonal,
                     tridiagonal_residual)

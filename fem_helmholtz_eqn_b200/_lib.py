@@ -51,6 +51,8 @@ _SIGNATURES = {
                                                 C.c_size_t, _P]),
     "fh_helmholtz1d_sweep_fused_c128": (C.c_int, [C.POINTER(Problem1d), _P, _P, C.c_int64, _P, _P, _P,
                                                   C.c_size_t, _P]),
+    "fh_helmholtz1d_sweep_assemble_solve_c128": (C.c_int, [C.POINTER(Problem1d), _P, _P, C.c_int64, _P, _P, _P, _P, _P,
+                                                           _P, _P, C.c_size_t, _P]),
     "fh_tridiag_solve_large_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "fh_tridiag_solve_large_c128": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P, _P, C.c_size_t, _P]),
     "fh_helmholtz1d_solve_large_fused_c128": (C.c_int, [C.POINTER(Problem1d), C.c_double, C.c_double, _P, _P, _P,

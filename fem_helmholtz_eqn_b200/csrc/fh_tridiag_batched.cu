@@ -350,6 +350,32 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
             fa = map.dir > 0 ? lo : hi, fc = map.dir > 0 ? hi : lo;
             if (CLUSTER == 1) row_values(src.p, sm.bgeom[1], n - 1, hs.k, hs.k2, la, lb, lc, ld);
         }
+        // A is kept (kStoreBands): on a uniform mesh every interior row of a system holds the same four numbers, so the
+        // rows a thread WRITES need not be the rows it eliminates -- consecutive lanes write consecutive rows (512
+        // contiguous bytes per warp and array), straight from registers.  The values are those of fh_assemble_1d_c128
+        // bit for bit (same generator); only the two mesh-boundary rows differ.  The stores are spread over the steps
+        // of phase 1 (group q = rows g_begin + t + q kT): issued in one burst they would sit in front of the
+        // elimination chain while the store queue drains.
+        cplx r0l, r0d, r0u, r0b, rNl, rNd, rNu, rNb;
+        if constexpr (Source::kStoreBands) {
+            row_values(src.p, sm.bgeom[0], 0, hs.k, hs.k2, r0l, r0d, r0u, r0b);
+            row_values(src.p, sm.bgeom[1], n - 1, hs.k, hs.k2, rNl, rNd, rNu, rNb);
+        }
+        auto store_group = [&](int q) {
+            if constexpr (Source::kStoreBands) {
+                const int64_t g_begin = rank == 0 ? 0 : n - map.n_loc;
+                const int64_t g_end = rank == 0 ? map.n_loc + (has_cut ? 1 : 0) : n;   // rank 0 also writes the cut row
+                const int64_t g = g_begin + t + (int64_t)q * kT;
+                if (g < g_end) {
+                    cplx vl = hs.il, vd = hs.id, vu = hs.iu, vb = hs.ib;
+                    if (g == 0) vl = r0l, vd = r0d, vu = r0u, vb = r0b;
+                    if (g == n - 1) vl = rNl, vd = rNd, vu = rNu, vb = rNb;
+                    const int64_t o = sys * n + g;
+                    stg_stream(src.out_dl + o, vl), stg_stream(src.out_d + o, vd);
+                    stg_stream(src.out_du + o, vu), stg_stream(src.out_b + o, vb);
+                }
+            }
+        };
         auto load_row = [&](int i) {
             if (!active) {
                 a[i] = czero(), b[i] = cone(), c[i] = czero(), d[i] = czero();
@@ -373,6 +399,8 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
         };
         load_row(0);
         load_row(1);
+        store_group(0);
+        store_group(1);
 
         // ---- head rows (far end, at most 8): serial Thomas by one thread, folded into its row 0 ------
         cplx hcp[kHeadMax], hdp[kHeadMax];
@@ -406,6 +434,7 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
 #pragma unroll
         for (int i = 1; i < kM; ++i) {
             if (i + 1 < kM) load_row(i + 1);
+            store_group(i + 1);  // (groups 2 .. kM: rows up to 2048 + 256 past the CTA's first -- head rows, cut row)
             if (i == kM - 1) a7o = a[i], b7o = b[i], c7o = c[i], d7o = d[i];
             const cplx w = a[i] * b[i - 1];
             b[i] = nmsub(b[i], w, c[i - 1]);
@@ -791,13 +820,44 @@ int fh_helmholtz1d_sweep_fused_c128(const fh_problem1d *prob_host, const double 
     if (p.h_mode == FH_H_SCALAR && p.n_elem >= 2) {  // uniform mesh: the fast generator
         HelmSourceT<true> src;
         src.p = p, src.ks = ks, src.k2s = k2s;
+        src.out_dl = src.out_d = src.out_du = src.out_b = nullptr;
         if (n <= kStageRows) return launch_batched<1>(src, none, out, n, n_k, status, st);
         return launch_batched<2>(src, none, out, n, n_k, status, st);
     }
     HelmSourceT<false> src;
     src.p = p, src.ks = ks, src.k2s = k2s;
+    src.out_dl = src.out_d = src.out_du = src.out_b = nullptr;
     if (n <= kStageRows) return launch_batched<1>(src, none, out, n, n_k, status, st);
     return launch_batched<2>(src, none, out, n, n_k, status, st);
+}
+
+int fh_helmholtz1d_sweep_assemble_solve_c128(const fh_problem1d *prob_host, const double *ks, const double *k2s,
+                                             int64_t n_k, fh_c128 *dl, fh_c128 *d, fh_c128 *du, fh_c128 *b, fh_c128 *u,
+                                             int32_t *status, void *workspace, size_t workspace_bytes,
+                                             fh_stream_t stream) {
+    using namespace fh;
+    (void)workspace, (void)workspace_bytes;
+    Problem1d p;
+    int rc = problem_from_host(prob_host, p);
+    if (rc != FH_OK) return rc;
+    FH_REQUIRE(n_k >= 0, "n_k must be >= 0");
+    if (n_k == 0) return FH_OK;
+    FH_REQUIRE(ks && k2s && dl && d && du && b && u, "NULL device pointer");
+    const int64_t n = p.n_elem + 1;
+    if (n > kBatchedMaxN || p.h_mode != FH_H_SCALAR || p.n_elem < 2) {
+        set_error("the one-pass assemble+solve covers uniform meshes of 3 .. %lld nodes; call fh_assemble_1d_c128 and "
+                  "fh_tridiag_solve_batched_c128 otherwise", (long long)kBatchedMaxN);
+        return FH_E_UNSUPPORTED;
+    }
+    HelmSourceT<true, true> src;
+    src.p = p, src.ks = ks, src.k2s = k2s;
+    src.out_dl = reinterpret_cast<cplx *>(dl), src.out_d = reinterpret_cast<cplx *>(d);
+    src.out_du = reinterpret_cast<cplx *>(du), src.out_b = reinterpret_cast<cplx *>(b);
+    const cplx *const bands[4] = {src.out_dl, src.out_d, src.out_du, src.out_b};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cplx *out = reinterpret_cast<cplx *>(u);
+    if (n <= kStageRows) return launch_batched<1>(src, bands, out, n, n_k, status, st);
+    return launch_batched<2>(src, bands, out, n, n_k, status, st);
 }
 
 }  // extern "C"

@@ -100,6 +100,7 @@ struct BandSource {  // staged pipeline: bands live in global memory
     static constexpr bool kStaged = true;
     static constexpr bool kUniform = false;
     static constexpr bool kSubset = false;
+    static constexpr bool kStoreBands = false;
 };
 
 // Refinement of a SUBSET of a batch (fh_tridiag_refine_flagged_c128): the matrix of compact system i is system
@@ -115,13 +116,17 @@ struct BandSubsetSource : BandSource {
 // fused pipeline: bands are generated, never stored.  UNIFORM = scalar-h mesh with at least two elements: every
 // interior row of a system is the same, only the two mesh-boundary rows differ (compile-time switch: the generic
 // generator, with its per-row geometry and IEEE divisions, stays out of the fast kernel).
-template <bool UNIFORM>
+// STORE: the generated bands are also written out (dl, d, du, b -- what fh_assemble_1d_c128 would have stored, bit for
+// bit), so that "assemble, keep A, solve" costs 64 + 16 bytes per row of HBM traffic instead of 64 + 64 + 16.
+template <bool UNIFORM, bool STORE = false>
 struct HelmSourceT {
     Problem1d p;
     const double *ks, *k2s;
+    cplx *out_dl, *out_d, *out_du, *out_b;  // STORE only
     static constexpr bool kStaged = false;
     static constexpr bool kUniform = UNIFORM;
     static constexpr bool kSubset = false;
+    static constexpr bool kStoreBands = STORE;
 };
 
 struct HelmState {  // per-thread state of the generator

@@ -387,6 +387,38 @@ def solve_helmholtz_sweep(N, ks, L=1.0, theta=0.0, *, bc_left="neumann", bc_righ
     return (nodes, U, status) if return_status else (nodes, U)
 
 
+def assemble_and_solve(N, ks, L=1.0, theta=0.0, *, bc_left="neumann", bc_right="sommerfeld", g_left=1.0, g_right=0.0,
+                       out_bands=None, out=None, refine=True):
+    """``A, b = assembly(...)`` followed by ``u = np.linalg.solve(A, b)`` (nb:203-204) for every wavenumber in ``ks``, in
+    ONE pass: the kernel generates the rows, stores them as the bands ``assemble_bands`` would have stored (bit for
+    bit) and solves from its registers, so ``A`` is written once and never read back.  Returns
+    ``((dl, d, du, b), U, status)`` -- CUDA tensors complex128[n_k, N+1].  Uniform meshes up to the batched solver's
+    size; longer or non-uniform meshes take the two-kernel path."""
+    lib = _lib.require_cuda()
+    ks_h, k2s_h, _ = _host_k_and_k2(ks)
+    n_k, n = len(ks_h), int(N) + 1
+    dev = _lib.device()
+    if n > lib.fh_tridiag_batched_max_n() or N < 2:
+        bands = assemble_bands(N, (ks_h, k2s_h), L / N, theta, bc_left=bc_left, bc_right=bc_right, g_left=g_left,
+                               g_right=g_right, out=out_bands)
+        U, status = solve_tridiagonal(*bands, out=out, refine=refine)
+        return bands, U, status
+    ks_d, k2s_d = _lib.as_device(ks_h, torch.float64), _lib.as_device(k2s_h, torch.float64)
+    B = out_bands if out_bands is not None else torch.empty((4, n_k, n), dtype=torch.complex128, device=dev)
+    assert B.shape == (4, n_k, n) and B.dtype == torch.complex128 and B.is_contiguous()
+    U = out if out is not None else torch.empty((n_k, n), dtype=torch.complex128, device=dev)
+    status = torch.empty(n_k, dtype=torch.int32, device=dev)
+    prob = _problem(N, L / N, theta, bc_left, bc_right, g_left, g_right, None)
+    check(lib.fh_helmholtz1d_sweep_assemble_solve_c128(C.byref(prob), ptr(ks_d), ptr(k2s_d), n_k, ptr(B[0]), ptr(B[1]),
+                                                       ptr(B[2]), ptr(B[3]), ptr(U), ptr(status), None, 0, stream_ptr()),
+          "fh_helmholtz1d_sweep_assemble_solve_c128")
+    bands = (B[0], B[1], B[2], B[3])
+    if refine:
+        resolve_nonfinite(*bands, U, status)
+        refine_flagged(*bands, U, status)
+    return bands, U, status
+
+
 class LargeMeshPlan:
     """One long mesh, many solves (BASELINE configs 2 and 5: N = 10^6, a new wavenumber per call).  At that size the
     work is 0.15 GB -- tens of microseconds of HBM time -- and the path is bound by its nine dependent kernel launches

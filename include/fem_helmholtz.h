@@ -101,6 +101,16 @@ FH_API int fh_tridiag_solve_batched_c128(const fh_c128 *dl, const fh_c128 *d, co
                                   int32_t *status, void *workspace, size_t workspace_bytes,
                                   fh_stream_t stream);
 
+/* ---- one-pass assemble + solve that KEEPS A (nb:203-204 `A, b = assembly(...)`; `u = np.linalg.solve(A, b)` for many k):
+ * the rows are generated in registers, written out as the bands fh_assemble_1d_c128 would have stored (bit for bit)
+ * and solved from the registers -- 64 + 16 bytes of HBM traffic per row instead of 64 + 64 + 16, A is never read
+ * back.  Uniform meshes (scalar h) of 3 .. fh_tridiag_batched_max_n() nodes; FH_E_UNSUPPORTED otherwise (use the two
+ * calls).  status as for fh_tridiag_solve_batched_c128; flagged systems are refined from the stored bands. */
+FH_API int fh_helmholtz1d_sweep_assemble_solve_c128(const fh_problem1d *prob_host, const double *ks, const double *k2s,
+                                             int64_t n_k, fh_c128 *dl, fh_c128 *d, fh_c128 *du, fh_c128 *b,
+                                             fh_c128 *u, int32_t *status, void *workspace, size_t workspace_bytes,
+                                             fh_stream_t stream);
+
 /* ---- fused assemble+solve sweep (nb:190-205 `solve_helmholtz_fem` for many k at once): the bands
  * are generated in registers and never stored; only u[n_k][N+1] is written. ----------------------- */
 FH_API int fh_helmholtz1d_sweep_fused_c128(const fh_problem1d *prob_host, const double *ks, const double *k2s,

@@ -308,3 +308,21 @@ def test_host_sweep_repairs_breakdowns_and_flagged_systems(fused):
     _, U_dev = fh.solve_helmholtz_sweep(N, ks, fused=fused)
     assert fh.tridiagonal_residual(dl, d, du, b, U_dev)["backward"].max() < 1e-13
     assert rel_err(U[-1], banded1d.solve_bands(*banded1d.assemble_bands(N, float(ks[-1]), 1.0 / N))) < 1e-11
+
+
+@pytest.mark.parametrize("N,bc", [(4096, {}), (4095, {}), (1000, {}), (2056, {}), (4111, {}), (64, {}),
+                                  (999, dict(bc_left="dirichlet", bc_right="dirichlet", g_left=1.0, g_right=0.0))])
+def test_one_pass_assemble_and_solve_keeps_identical_bands(N, bc):
+    """fh_helmholtz1d_sweep_assemble_solve_c128: the bands it writes are what fh_assemble_1d_c128 writes (bit for bit:
+    cut row, head rows, both cluster halves, single-CTA sizes, Dirichlet rows) and the solution is what the batched
+    solver computes from those bands (bit for bit)."""
+    ks = np.linspace(3.0, 700.0, 149 * 2 + 5)
+    bands, U, status = fh.assemble_and_solve(N, ks, refine=False, **bc)
+    ref = fh.assemble_bands(N, ks, 1.0 / N, **bc)
+    for got, want in zip(bands, ref):
+        assert torch.equal(got, want)
+    U2, st2 = fh.solve_tridiagonal(*ref, refine=False)
+    assert torch.equal(U, U2) and torch.equal(status, st2)
+    _, U3, st3 = fh.assemble_and_solve(N, ks, **bc)          # with refinement from the stored bands
+    assert int(st3.abs().sum()) == 0
+    assert fh.tridiagonal_residual(*ref, U3)["backward"].max() < 1e-13
