@@ -57,6 +57,9 @@ constexpr uint32_t kTileBytes = kSlots * sizeof(cplx);  // 32 KB per band tile
 // prefetch is issued by the first active thread (warp 0 for full systems), the solution store by warp 1, the exchange
 // barrier is armed by warp 2
 constexpr int kStoreThread = 32, kXchgThread = 64;
+constexpr int kBandStoreThread0 = 96;  // kStoreBands: lanes 0 of warps 3..6 store one band each
+constexpr int kBandTileChunks = 128;   // ... from a tile of 128 identical chunks (16 KB)
+constexpr uint32_t kBandTileBytes = kBandTileChunks * 128u;
 constexpr int kH = kT / 2;              // interface rows that survive the cyclic-reduction step
 constexpr int kHalfPad = kH / 2;        // zero rows on either side of a half-width array (largest PCR stride)
 constexpr int kHalfStride = kH + 2 * kHalfPad + 4;  // (+4 rows = 64 B: the two arrays a lane pair touches together
@@ -128,6 +131,9 @@ struct HostMap {  // the same numbers, computed on the host for the tensor maps
     int n_loc[2], head[2], chunks[2];
     int row0[2];  // first row of the chunk grid of each rank (origin of its tensor maps)
     int cut;      // 1: row n_loc[0] is the cut row
+    // does the first / last chunk of a rank's grid hold a mesh-boundary row (row 0 / row n - 1)?  (They are the only
+    // chunks of a uniform mesh whose rows are not all alike: the one-pass assemble+solve writes them separately.)
+    int front[2], back[2];
 };
 __host__ __device__ inline HostMap host_map(int64_t n, int cluster) {
     HostMap m;
@@ -142,6 +148,10 @@ __host__ __device__ inline HostMap host_map(int64_t n, int cluster) {
     }
     m.row0[0] = m.head[0];               // rank 0: head rows first, then the chunks
     m.row0[1] = m.n_loc[0] + m.cut;      // rank 1 (reversed): chunks first in memory, head rows at the far end
+    m.front[0] = m.head[0] == 0 && m.chunks[0] > 0;
+    m.back[0] = cluster == 1 && m.chunks[0] > 0;
+    m.front[1] = 0;
+    m.back[1] = cluster == 2 && m.head[1] == 0 && m.chunks[1] > 0;
     return m;
 }
 
@@ -350,23 +360,33 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
             fa = map.dir > 0 ? lo : hi, fc = map.dir > 0 ? hi : lo;
             if (CLUSTER == 1) row_values(src.p, sm.bgeom[1], n - 1, hs.k, hs.k2, la, lb, lc, ld);
         }
-        // A is kept (kStoreBands): on a uniform mesh every interior row of a system holds the same four numbers, so the
-        // rows a thread WRITES need not be the rows it eliminates -- consecutive lanes write consecutive rows (512
-        // contiguous bytes per warp and array), straight from registers.  The values are those of fh_assemble_1d_c128
-        // bit for bit (same generator); only the two mesh-boundary rows differ.  The stores are spread over the steps
-        // of phase 1 (group q = rows g_begin + t + q kT): issued in one burst they would sit in front of the
-        // elimination chain while the store queue drains.
-        cplx r0l, r0d, r0u, r0b, rNl, rNd, rNu, rNb;
+        // A is kept (kStoreBands): on a uniform mesh every interior row of a system holds the same four numbers, so
+        // what is written need not come from the rows a thread eliminates.  Four 16 KB tiles (128 chunks of 8 identical
+        // rows: dl, d, du, b) are filled once per system and sent to every block of 128 interior chunks by TMA stores
+        // (bigger blocks = fewer store operations: the TMA engine's cost per operation was measured to dominate with
+        // 4 KB blocks; smaller tiles = fewer shared-memory writes than staging the rows one by one);
+        // the few rows that differ or fall outside the chunk grid (the chunks holding mesh row 0 / n - 1, head rows, the
+        // cut row) are written by single lanes of warp 0.  Values = fh_assemble_1d_c128's, bit for bit (same generator).
         if constexpr (Source::kStoreBands) {
-            row_values(src.p, sm.bgeom[0], 0, hs.k, hs.k2, r0l, r0d, r0u, r0b);
-            row_values(src.p, sm.bgeom[1], n - 1, hs.k, hs.k2, rNl, rNd, rNu, rNb);
-        }
-        auto store_group = [&](int q) {
-            if constexpr (Source::kStoreBands) {
-                const int64_t g_begin = rank == 0 ? 0 : n - map.n_loc;
-                const int64_t g_end = rank == 0 ? map.n_loc + (has_cut ? 1 : 0) : n;   // rank 0 also writes the cut row
-                const int64_t g = g_begin + t + (int64_t)q * kT;
-                if (g < g_end) {
+            const HostMap hm = host_map(n, CLUSTER);
+            const uint32_t mini = smem_u32(&sm.stage[0][0]) + (uint32_t)t * 16u;   // [4 bands][128 chunks][128 B]
+#pragma unroll
+            for (uint32_t rep = 0; rep < kBandTileBytes; rep += kT * 16u) {
+                sts_volatile(mini + rep, hs.il), sts_volatile(mini + kBandTileBytes + rep, hs.id);
+                sts_volatile(mini + 2 * kBandTileBytes + rep, hs.iu), sts_volatile(mini + 3 * kBandTileBytes + rep, hs.ib);
+            }
+            fence_proxy_async();  // (the stores are issued after the next block barrier)
+            if (t < 32) {
+                cplx r0l, r0d, r0u, r0b, rNl, rNd, rNu, rNb;
+                row_values(src.p, sm.bgeom[0], 0, hs.k, hs.k2, r0l, r0d, r0u, r0b);
+                row_values(src.p, sm.bgeom[1], n - 1, hs.k, hs.k2, rNl, rNd, rNu, rNb);
+                int64_t g = -1;  // the special row of this lane, if any
+                const int64_t grid0 = hm.row0[rank];
+                if (t < map.head) g = map.global_row(t);                                        // lanes 0..7: head rows
+                if (t == 8 && has_cut && rank == 0) g = cut_row;                                // lane 8: the cut row
+                if (t >= 16 && t < 24 && hm.front[rank]) g = grid0 + (t - 16);                  // first chunk
+                if (t >= 24 && hm.back[rank]) g = grid0 + 8 * (int64_t)(map.chunks - 1) + (t - 24);  // last chunk
+                if (g >= 0) {
                     cplx vl = hs.il, vd = hs.id, vu = hs.iu, vb = hs.ib;
                     if (g == 0) vl = r0l, vd = r0d, vu = r0u, vb = r0b;
                     if (g == n - 1) vl = rNl, vd = rNd, vu = rNu, vb = rNb;
@@ -375,7 +395,7 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
                     stg_stream(src.out_du + o, vu), stg_stream(src.out_b + o, vb);
                 }
             }
-        };
+        }
         auto load_row = [&](int i) {
             if (!active) {
                 a[i] = czero(), b[i] = cone(), c[i] = czero(), d[i] = czero();
@@ -399,8 +419,6 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
         };
         load_row(0);
         load_row(1);
-        store_group(0);
-        store_group(1);
 
         // ---- head rows (far end, at most 8): serial Thomas by one thread, folded into its row 0 ------
         cplx hcp[kHeadMax], hdp[kHeadMax];
@@ -434,7 +452,6 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
 #pragma unroll
         for (int i = 1; i < kM; ++i) {
             if (i + 1 < kM) load_row(i + 1);
-            store_group(i + 1);  // (groups 2 .. kM: rows up to 2048 + 256 past the CTA's first -- head rows, cut row)
             if (i == kM - 1) a7o = a[i], b7o = b[i], c7o = c[i], d7o = d[i];
             const cplx w = a[i] * b[i - 1];
             b[i] = nmsub(b[i], w, c[i - 1]);
@@ -462,6 +479,17 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
         sm.row0[1][t] = c[0] * b[0];
         sm.row0[2][t] = d[0] * b[0];
         __syncthreads();
+        if constexpr (Source::kStoreBands) {
+            // one thread per band (four different warps) sends the tile to every block of 32 interior chunks
+            if (t >= kBandStoreThread0 && t < kBandStoreThread0 + 128 && (t & 31) == 0) {
+                const HostMap hm = host_map(n, CLUSTER);
+                const int q = (t - kBandStoreThread0) >> 5;
+                const int count = map.chunks - hm.front[rank] - hm.back[rank];
+                for (int c = 0; c < count; c += kBandTileChunks)
+                    tma_store_3d(&maps.band[rank][q], 0, c, (int)sys, &sm.stage[0][q * (kBandTileBytes / 16)]);
+                tma_store_commit();
+            }
+        }
         FH_TR(5);
         cplx rA, rC, rD, rV;
         {
@@ -623,6 +651,9 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
         }
         FH_TR(10);
         fence_proxy_async();  // make this thread's xs writes visible to the TMA engine
+        if constexpr (Source::kStoreBands) {  // the band tiles are refilled right after this barrier
+            if (t >= kBandStoreThread0 && t < kBandStoreThread0 + 128 && (t & 31) == 0) tma_store_wait_read();
+        }
         const int any_nonfinite = __syncthreads_or(bad ? 1 : 0);  // (returns a truth value, not a bit-wise OR)
         FH_TR(11);
         if (t == kStoreThread) {
@@ -696,6 +727,13 @@ static int launch_batched(const Source &src, const cplx *const bands[4], cplx *u
     for (int r = 0; r < CLUSTER; ++r) {  // every rank sees only its own chunks: loads zero-fill, stores clip
         int rc = make_tensor_map(&umaps.r[r], u, n, batch, h.row0[r], h.chunks[r], kChunks8);
         if (rc != FH_OK) return rc;
+        if (Source::kStoreBands) {  // store views over the interior chunks of the rank, in boxes of kBandTileChunks chunks
+            for (int i = 0; i < 4; ++i) {
+                rc = make_tensor_map(&maps.band[r][i], bands[i], n, batch, h.row0[r] + 8 * h.front[r],
+                                     h.chunks[r] - h.front[r] - h.back[r], kBandTileChunks);
+                if (rc != FH_OK) return rc;
+            }
+        }
         if (Source::kStaged) {
             for (int i = 0; i < 4; ++i) {
                 rc = make_tensor_map(&maps.band[r][i], bands[i], n, i < 3 ? batch_matrices : batch, h.row0[r],

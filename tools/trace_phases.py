@@ -27,7 +27,9 @@ def main():
     ks = torch.linspace(1.0, 1000.0, n_k, dtype=torch.float64)
     dl, d, du, b = fh.assemble_bands(4096, ks, 1.0 / 4096)
     fused = len(sys.argv) > 3 and sys.argv[3] == "fused"
+    onepass = len(sys.argv) > 3 and sys.argv[3] == "onepass"
     run = ((lambda: fh.solve_helmholtz_sweep(4096, ks, fused=True, check_singular=False)) if fused
+           else (lambda: fh.assemble_and_solve(4096, ks, refine=False)) if onepass
            else (lambda: fh.solve_tridiagonal(dl, d, du, b, refine=False)))
     run()
     torch.cuda.synchronize()
