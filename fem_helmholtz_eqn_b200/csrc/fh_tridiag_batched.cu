@@ -375,7 +375,7 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
                 sts_volatile(mini + rep, hs.il), sts_volatile(mini + kBandTileBytes + rep, hs.id);
                 sts_volatile(mini + 2 * kBandTileBytes + rep, hs.iu), sts_volatile(mini + 3 * kBandTileBytes + rep, hs.ib);
             }
-            fence_proxy_async();  // (the stores are issued after the next block barrier)
+            fence_proxy_async();  // (the stores are issued behind the block barrier below)
             if (t < 32) {
                 cplx r0l, r0d, r0u, r0b, rNl, rNd, rNu, rNb;
                 row_values(src.p, sm.bgeom[0], 0, hs.k, hs.k2, r0l, r0d, r0u, r0b);
@@ -394,6 +394,20 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
                     stg_stream(src.out_dl + o, vl), stg_stream(src.out_d + o, vd);
                     stg_stream(src.out_du + o, vu), stg_stream(src.out_b + o, vb);
                 }
+            }
+        }
+        if constexpr (Source::kStoreBands) {
+            // The stores are issued NOW, behind one extra block barrier: the TMA engine then reads the tiles while the
+            // CTA is busy with the register-only elimination phases.  (Issued after phase 2 the 128 KB of tile reads
+            // shared the shared-memory pipe with the interface solve and slowed every one of its levels.)
+            __syncthreads();
+            if (t >= kBandStoreThread0 && t < kBandStoreThread0 + 128 && (t & 31) == 0) {
+                const HostMap hm = host_map(n, CLUSTER);
+                const int q = (t - kBandStoreThread0) >> 5;
+                const int count = map.chunks - hm.front[rank] - hm.back[rank];
+                for (int c = 0; c < count; c += kBandTileChunks)
+                    tma_store_3d(&maps.band[rank][q], 0, c, (int)sys, &sm.stage[0][q * (kBandTileBytes / 16)]);
+                tma_store_commit();
             }
         }
         auto load_row = [&](int i) {
@@ -479,17 +493,6 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
         sm.row0[1][t] = c[0] * b[0];
         sm.row0[2][t] = d[0] * b[0];
         __syncthreads();
-        if constexpr (Source::kStoreBands) {
-            // one thread per band (four different warps) sends the tile to every block of 32 interior chunks
-            if (t >= kBandStoreThread0 && t < kBandStoreThread0 + 128 && (t & 31) == 0) {
-                const HostMap hm = host_map(n, CLUSTER);
-                const int q = (t - kBandStoreThread0) >> 5;
-                const int count = map.chunks - hm.front[rank] - hm.back[rank];
-                for (int c = 0; c < count; c += kBandTileChunks)
-                    tma_store_3d(&maps.band[rank][q], 0, c, (int)sys, &sm.stage[0][q * (kBandTileBytes / 16)]);
-                tma_store_commit();
-            }
-        }
         FH_TR(5);
         cplx rA, rC, rD, rV;
         {
