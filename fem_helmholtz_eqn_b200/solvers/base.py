@@ -242,9 +242,10 @@ class BaseSolver(ABC):
             Se = self._robin_matrices_device(outer, self._robin_gauss).reshape(-1)
             pat = self._segments("K+S", [None, outer], True)
             vals = self._segment_sum(torch.cat([Ke, Se]), pat)
-            # the reference also keeps S on its own (fem2d.py:141): same pattern, K part zeroed
-            self.S = CsrMatrix(pat["rowptr"], pat["colidx"], self._segment_sum(torch.cat([torch.zeros_like(Ke), Se]), pat),
-                               m["n"])
+            # the reference also keeps S on its own (fem2d.py:141): same pattern, K part zeroed -- summed on first
+            # access (``self.S``), not on every assemble(): it is a second full scatter that solve() never needs
+            self._S_lazy = (Ke.numel(), Se, pat, m["n"])
+            self._S = None
         else:
             pat = self._segments("K", [None], True)
             vals = self._segment_sum(Ke, pat)
@@ -258,6 +259,18 @@ class BaseSolver(ABC):
             self.N_global = F.cpu().numpy().copy()
         self._F_dev = F
         self.F = F.cpu().numpy()
+
+    @property
+    def S(self):
+        """Robin boundary matrix of the last ``assemble()`` (fem2d.py:141 keeps it as ``self.S``), on K's pattern."""
+        if getattr(self, "_S", None) is None:
+            lazy = getattr(self, "_S_lazy", None)
+            if lazy is None:
+                raise AttributeError("S is set by assemble() of the solver classes with a Robin boundary")
+            n_ke, Se, pat, n = lazy
+            zeros = torch.zeros(n_ke, dtype=Se.dtype, device=Se.device)
+            self._S = CsrMatrix(pat["rowptr"], pat["colidx"], self._segment_sum(torch.cat([zeros, Se]), pat), n)
+        return self._S
 
     def apply_boundary_conditions(self, A=None, b=None, tol: float = 1e-10):
         """Dirichlet row replacement (fem2d_dirichlet.py:11-29, fem2d_dirichlet_sommerfeld.py:12-24,

@@ -77,7 +77,7 @@ def test_kernel_algorithm_model_matches_lapack():
     from oracle import banded1d
     from models.partition_pcr_model import solve
     rng = np.random.default_rng(1)
-    for n in (1, 2, 9, 2048, 2050, 2056, 2057, 4097, 4112):
+    for n in (1, 2, 9, 17, 23, 2048, 2050, 2056, 2057, 2058, 3001, 4096, 4097, 4111, 4112):
         dl = rng.normal(size=n) + 1j * rng.normal(size=n)
         du = rng.normal(size=n) + 1j * rng.normal(size=n)
         d = 4 + rng.normal(size=n) + 1j * rng.normal(size=n)

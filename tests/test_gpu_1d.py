@@ -128,7 +128,7 @@ def test_fused_equals_staged(golden1d):
         assert rel_err(_np(Un), _np(Us)) < 1e-9
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 7, 8, 9, 63, 1000, 2047, 2048, 2049, 2055, 2056, 2057, 3001, 4097, 4112])
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 8, 9, 17, 23, 63, 1000, 2047, 2048, 2049, 2055, 2056, 2057, 3001, 4097, 4112])
 def test_random_systems_all_kernel_shapes(n):
     """Edge sizes of the kernel's slot map: < 1 chunk, chunk-aligned, head rows (2049..2056), the
     1-CTA/2-CTA switch (2056|2057), the flagship 4097 and the cluster maximum 4112."""

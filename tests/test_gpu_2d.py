@@ -129,3 +129,20 @@ def test_sparse_band_solver_reports_singular_matrices():
     s.K.vals.zero_()                                               # an exactly singular matrix
     with pytest.raises(np.linalg.LinAlgError):
         s._solve_device()
+
+
+def test_robin_matrix_S_is_available_on_demand(golden2d):
+    """fem2d.py:141 keeps the boundary matrix S next to K; here it is summed on first access.  K - S must be the
+    interior stiffness (no entry of S outside the outer-boundary nodes' rows and columns)."""
+    eqn, ri, ro = _eqn(golden2d, "m0")
+    s = get_solver("default", eqn, k_squared=5.0, abc_order=1, inner_radius=ri, outer_radius=ro)
+    s.assemble()
+    S, K = np.asarray(s.S), np.asarray(s.K)
+    outer = np.zeros(eqn.n_nodes, bool)
+    outer[np.asarray(eqn.outer_boundary_node_indices)] = True
+    assert np.abs(S[~outer]).max() == 0.0 and np.abs(S[:, ~outer]).max() == 0.0 and np.abs(S).max() > 0.0
+    plain = get_solver("dirichlet", eqn, k_squared=5.0, inner_radius=ri, outer_radius=ro)
+    plain.assemble()                                                   # same element matrices, no Robin term
+    assert np.allclose(K - S, np.asarray(plain.K), rtol=1e-14, atol=1e-14)
+    with pytest.raises(AttributeError):
+        plain.S
