@@ -13,7 +13,8 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libfemhelmholtz_b200.so")
+# (FH_LIB: development switch -- load another build of the same library, e.g. an instrumented one)
+LIB_PATH = os.environ.get("FH_LIB") or os.path.join(_HERE, "lib", "libfemhelmholtz_b200.so")
 
 FH_BC_NEUMANN, FH_BC_SOMMERFELD, FH_BC_DIRICHLET = 0, 1, 2
 FH_H_SCALAR, FH_H_NODAL = 0, 1
