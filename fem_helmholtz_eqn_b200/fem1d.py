@@ -431,7 +431,6 @@ class LargeMeshPlan:
         lib = _lib.require_cuda()
         self.N, self.n, self.L = int(N), int(N) + 1, float(L)
         dev = _lib.device()
-        self.k_host = torch.empty(2, dtype=torch.float64).pin_memory()
         self.k_dev = torch.zeros(2, dtype=torch.float64, device=dev)
         self.bands = torch.empty((4, 1, self.n), dtype=torch.complex128, device=dev)
         self.U = torch.empty((1, self.n), dtype=torch.complex128, device=dev)
@@ -454,8 +453,10 @@ class LargeMeshPlan:
                 self._launch()
 
     def _set_k(self, k):
-        self.k_host[0], self.k_host[1] = float(k), float(k**2)   # nb:185: k**2 evaluated on the host
-        self.k_dev.copy_(self.k_host, non_blocking=True)
+        # nb:185: k**2 evaluated on the host.  A plain (pageable) 16-byte copy: it is staged by the driver before the
+        # call returns, so a second solve() may overwrite the host values while the first replay is still queued
+        # (a pinned buffer copied with non_blocking=True could not be reused that way).
+        self.k_dev.copy_(torch.tensor([float(k), float(k**2)], dtype=torch.float64))
 
     def _launch(self):
         lib, B = _lib.load(), self.bands

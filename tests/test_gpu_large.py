@@ -206,3 +206,15 @@ def test_large_mesh_plan_replays_a_cuda_graph_bit_identically():
     assert banded1d.residual_metrics(*bands, u)[0] < 1e-15
     eager = fh.fem1d.LargeMeshPlan(N, use_graph=False)
     assert torch.equal(eager.solve(10.0), plan.solve(10.0))
+
+
+def test_large_mesh_plan_back_to_back_solves_do_not_race():
+    """solve() is stream-ordered: queuing several wavenumbers without synchronising in between must give each its own
+    answer (the wavenumber is handed to the graph through device memory)."""
+    N = 100_000
+    plan = fh.fem1d.LargeMeshPlan(N)
+    ks = [10.0, 250.0, 999.0, 3.5]
+    outs = [plan.solve(k).clone() for k in ks]          # clones are stream-ordered too: no host sync in the loop
+    torch.cuda.synchronize()
+    for k, u in zip(ks, outs):
+        assert torch.equal(u, fh.solve_helmholtz_sweep(N, [k])[1][0]), k
