@@ -69,6 +69,14 @@ __device__ __forceinline__ cplx nmsub(cplx c, cplx a, cplx b) {
     im = fma(-a.im, b.re, im);
     return mk(re, im);
 }
+// c + a*b  (4 FMAs)
+__device__ __forceinline__ cplx cmadd(cplx c, cplx a, cplx b) {
+    double re = fma(a.re, b.re, c.re);
+    re = fma(-a.im, b.im, re);
+    double im = fma(a.re, b.im, c.im);
+    im = fma(a.im, b.re, im);
+    return mk(re, im);
+}
 // 1/a.  The solver's pivots are O(1/h) .. O(k^2 h); |a|^2 neither over- nor underflows
 // in any configuration of interest, so the unscaled formula is used (cheaper than Smith's).
 __device__ __forceinline__ cplx crecip(cplx a) {

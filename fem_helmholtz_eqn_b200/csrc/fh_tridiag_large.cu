@@ -203,6 +203,242 @@ large_backsub_kernel(Source src, const cplx *__restrict__ xr, cplx *__restrict__
     }
 }
 
+// ---------------------------------------------------------------------------------------------- uniform meshes
+// Level 0 of a GENERATED system on a uniform mesh (scalar h: the reference's only mode, nb:158).  Every interior row
+// holds the same four numbers, so every full interior chunk reduces to the same two interface rows, and the
+// back-substitution of such a chunk is the same linear map of its two known end values:
+//     x_i = alpha_i x_first + beta_i x_last + gamma_i,      i = 1 .. 14
+// (alpha, beta, gamma: the chunk's Thomas sweep carried out once, symbolically in x_first / x_last).  What is left of
+// the two level-0 passes is a structured fill of the interface rows (8 B per row) and a streaming kernel that reads two
+// values per chunk and writes the solution (18 B per row) -- the elimination itself is unchanged, it is just not
+// repeated 2^23 times.  The chunks that are not "full interior" (those holding mesh row 0 or N, and the short / merged
+// chunk at the end of the last tile) take the generic sweeps, with rows generated on the fly.
+struct UniformRows {  // what HelmRows provides, with the interior row evaluated once on the host side of the launch
+    Problem1d p;
+    double k, k2;
+    int64_t g_off, n;
+    __device__ __forceinline__ void interior(cplx &lo, cplx &di, cplx &hi, cplx &rhs) const {
+        row_values(p, row_geom(p, 1), 1, k, k2, lo, di, hi, rhs);
+    }
+    __device__ __forceinline__ void row(int64_t g, const cplx in[4], cplx &lo, cplx &di, cplx &hi, cplx &rhs) const {
+        lo = in[0], di = in[1], hi = in[2], rhs = in[3];
+        if (g == 0 || g == p.n_elem) row_values(p, row_geom(p, g), g, k, k2, lo, di, hi, rhs);
+    }
+};
+
+struct ChunkPos {
+    int64_t r0;  // first row of the chunk inside the level
+    int len;     // rows (2 .. 17; 1 only if the level has a single row)
+    bool exists;
+};
+__device__ __forceinline__ ChunkPos chunk_pos(int64_t n, int64_t n_tiles, int64_t c) {
+    const int64_t tile = c / kLT;
+    const int t = (int)(c - tile * kLT);
+    const int rows = tile_rows(n, n_tiles, tile);
+    const int nch = chunk_count(rows);
+    ChunkPos cp;
+    cp.exists = t < nch;
+    cp.r0 = tile * kLTile + (int64_t)t * kLM;
+    cp.len = cp.exists ? (t == nch - 1 ? rows - t * kLM : kLM) : 0;
+    return cp;
+}
+// full chunk of 16 interior rows?
+__device__ __forceinline__ bool chunk_is_plain(const UniformRows &u, const ChunkPos &cp) {
+    const int64_t g0 = u.g_off + cp.r0;
+    return cp.len == kLM && g0 != 0 && g0 + cp.len - 1 != u.p.n_elem;
+}
+
+// the two interface rows of a chunk whose rows come from `rowfn(i, a, b, c, d)` -- the arithmetic of large_reduce_kernel
+template <class RowFn>
+__device__ __forceinline__ void reduce_chunk(RowFn rowfn, int len, cplx out1[4], cplx out2[4]) {
+    cplx ra, rb, rc, rd;
+    if (len == 1) {
+        rowfn(0, ra, rb, rc, rd);
+        out1[0] = ra, out1[1] = rb, out1[2] = czero(), out1[3] = rd;
+        out2[0] = czero(), out2[1] = cone(), out2[2] = czero(), out2[3] = czero();
+        return;
+    }
+    {  // downward from row 1: fill-in couples to x_first
+        cplx pa, pb, pc, pd;
+        rowfn(1, pa, pb, pc, pd);
+        for (int i = 2; i < len; ++i) {
+            rowfn(i, ra, rb, rc, rd);
+            const cplx w = ra * frecip(pb);
+            const cplx nb = nmsub(rb, w, pc), nd = nmsub(rd, w, pd);
+            pa = -(w * pa), pb = nb, pc = rc, pd = nd;
+        }
+        out2[0] = pa, out2[1] = pb, out2[2] = pc, out2[3] = pd;
+    }
+    {  // upward from row len-2: fill-in couples to x_last
+        cplx qa, qb, qc, qd;
+        rowfn(len - 2, qa, qb, qc, qd);
+        for (int i = len - 3; i >= 0; --i) {
+            rowfn(i, ra, rb, rc, rd);
+            const cplx w = rc * frecip(qb);
+            const cplx nb = nmsub(rb, w, qa), nd = nmsub(rd, w, qd);
+            qc = -(w * qc), qb = nb, qa = ra, qd = nd;
+        }
+        out1[0] = qa, out1[1] = qb, out1[2] = qc, out1[3] = qd;
+    }
+}
+
+constexpr int kUniThreads = 256;
+
+// Which chunks the streaming kernels cover: every chunk of the full tiles (tiles 0 .. n_tiles - 2 hold exactly 64 chunks
+// of 16 rows: chunk c = rows 16 c .. 16 c + 15), except chunk 0 when it holds mesh row 0.  The last tile (whose last
+// chunk may be short or merged, and which holds mesh row N when the slab ends the mesh) and that first chunk go to the
+// one-thread-per-chunk kernels below.
+struct UniformSpan {
+    int64_t c_lo, c_hi;  // streaming chunks [c_lo, c_hi)
+};
+__host__ __device__ __forceinline__ UniformSpan uniform_span(int64_t g_off, int64_t n) {
+    UniformSpan sp;
+    sp.c_lo = g_off == 0 ? 1 : 0;
+    sp.c_hi = (tile_count(n) - 1) * kLT;
+    if (sp.c_hi < sp.c_lo) sp.c_hi = sp.c_lo;
+    return sp;
+}
+// special chunk number `idx` (0 .. kLT): the chunks of the last tile, then chunk 0 (when it is not a streaming chunk
+// and not part of the last tile)
+__device__ __forceinline__ int64_t special_chunk(const UniformRows &u, int idx) {
+    const int64_t n_tiles = tile_count(u.n);
+    if (idx < kLT) return (n_tiles - 1) * kLT + idx;
+    if (idx == kLT && n_tiles > 1 && u.g_off == 0) return 0;
+    return -1;
+}
+
+// Structured fill: the interface rows of a plain chunk, computed once per CTA, written for every streaming chunk;
+// every CTA owns a contiguous range of chunks.
+__global__ void __launch_bounds__(kUniThreads)
+uniform_reduce_kernel(UniformRows u, int64_t per_block, cplx *__restrict__ ra, cplx *__restrict__ rb,
+                      cplx *__restrict__ rc, cplx *__restrict__ rd) {
+    __shared__ cplx plain[2][4];
+    if (threadIdx.x == 0) {
+        cplx in[4], p1[4], p2[4];
+        u.interior(in[0], in[1], in[2], in[3]);
+        reduce_chunk([&](int, cplx &a, cplx &b, cplx &c, cplx &d) { a = in[0], b = in[1], c = in[2], d = in[3]; }, kLM,
+                     p1, p2);
+        for (int q = 0; q < 4; ++q) plain[0][q] = p1[q], plain[1][q] = p2[q];
+    }
+    __syncthreads();
+    // thread t writes entry o = 2 c + (t & 1) of the four interface arrays: consecutive lanes, consecutive entries
+    const int half = threadIdx.x & 1;
+    const cplx va = plain[half][0], vb = plain[half][1], vc = plain[half][2], vd = plain[half][3];
+    const UniformSpan sp = uniform_span(u.g_off, u.n);
+    const int64_t o_begin = 2 * sp.c_lo + (int64_t)blockIdx.x * per_block;
+    int64_t o_end = o_begin + per_block;
+    if (o_end > 2 * sp.c_hi) o_end = 2 * sp.c_hi;
+    for (int64_t o = o_begin + threadIdx.x; o < o_end; o += kUniThreads)   // (per_block is even: parity = t & 1)
+        stg_stream(ra + o, va), stg_stream(rb + o, vb), stg_stream(rc + o, vc), stg_stream(rd + o, vd);
+}
+
+// ... and the special chunks: generic sweeps, rows generated on the fly, one thread per chunk
+__global__ void uniform_special_reduce_kernel(UniformRows u, cplx *__restrict__ ra, cplx *__restrict__ rb,
+                                              cplx *__restrict__ rc, cplx *__restrict__ rd) {
+    const int64_t c = special_chunk(u, (int)threadIdx.x);
+    if (c < 0) return;
+    const ChunkPos cp = chunk_pos(u.n, tile_count(u.n), c);
+    if (!cp.exists) return;
+    cplx in[4], o1[4], o2[4];
+    u.interior(in[0], in[1], in[2], in[3]);
+    const int64_t g0 = u.g_off + cp.r0;
+    reduce_chunk([&](int i, cplx &a, cplx &b, cplx &c2, cplx &d) { u.row(g0 + i, in, a, b, c2, d); }, cp.len, o1, o2);
+    const int64_t o = 2 * c;
+    ra[o] = o1[0], rb[o] = o1[1], rc[o] = o1[2], rd[o] = o1[3];
+    ra[o + 1] = o2[0], rb[o + 1] = o2[1], rc[o + 1] = o2[2], rd[o + 1] = o2[3];
+}
+
+// Streaming back-substitution: x(16 c + i) = alpha_i x_first(c) + beta_i x_last(c) + gamma_i.  Every CTA owns a
+// contiguous range of rows that starts on a chunk boundary; 256 threads = 16 chunks per pass, so a thread keeps the same
+// row-in-chunk i -- and with it (alpha_i, beta_i, gamma_i) in registers -- for its whole range.
+__global__ void __launch_bounds__(kUniThreads)
+uniform_backsub_kernel(UniformRows u, int64_t chunks_per_block, const cplx *__restrict__ xr, cplx *__restrict__ x,
+                       int32_t *__restrict__ status) {
+    __shared__ cplx tab[3][kLM], fwd[3][kLM];
+    if (threadIdx.x == 0) {
+        cplx in[4];
+        u.interior(in[0], in[1], in[2], in[3]);
+        // forward sweep with x_first as a symbol: dp_i = P_i x_first + G_i;  backward with x_last as a symbol
+        cplx cp = czero(), Pp = cone(), Gp = czero();
+        for (int i = 1; i <= kLM - 2; ++i) {
+            const cplx inv = frecip(nmsub(in[1], in[0], cp));
+            Pp = -((in[0] * Pp) * inv);
+            Gp = nmsub(in[3], in[0], Gp) * inv;
+            cp = in[2] * inv;
+            fwd[0][i] = cp, fwd[1][i] = Pp, fwd[2][i] = Gp;
+        }
+        cplx al = czero(), be = cone(), ga = czero();
+        tab[0][kLM - 1] = al, tab[1][kLM - 1] = be, tab[2][kLM - 1] = ga;  // x_15 = x_last
+        for (int i = kLM - 2; i >= 1; --i) {
+            al = nmsub(fwd[1][i], fwd[0][i], al);
+            be = -(fwd[0][i] * be);
+            ga = nmsub(fwd[2][i], fwd[0][i], ga);
+            tab[0][i] = al, tab[1][i] = be, tab[2][i] = ga;
+        }
+        tab[0][0] = cone(), tab[1][0] = czero(), tab[2][0] = czero();       // x_0 = x_first
+    }
+    __syncthreads();
+    const int i = threadIdx.x & (kLM - 1);
+    const cplx al = tab[0][i], be = tab[1][i], ga = tab[2][i];
+    const UniformSpan sp = uniform_span(u.g_off, u.n);
+    const int64_t c_begin = sp.c_lo + (int64_t)blockIdx.x * chunks_per_block;
+    int64_t c_end = c_begin + chunks_per_block;
+    if (c_end > sp.c_hi) c_end = sp.c_hi;
+    bool bad = false;
+    constexpr int kStep = kUniThreads / kLM, kFly = 8;  // 8 passes in flight: the end-value loads overlap
+    for (int64_t c0 = c_begin + (threadIdx.x >> 4); c0 < c_end; c0 += kFly * kStep) {
+        cplx x0[kFly], xl[kFly];
+#pragma unroll
+        for (int q = 0; q < kFly; ++q) {
+            const int64_t c = c0 + q * kStep;
+            if (c < c_end) x0[q] = xr[2 * c], xl[q] = xr[2 * c + 1];  // (16 lanes read the same pair: one request)
+        }
+#pragma unroll
+        for (int q = 0; q < kFly; ++q) {
+            const int64_t c = c0 + q * kStep;
+            if (c < c_end) {
+                const cplx xi = cmadd(cmadd(ga, al, x0[q]), be, xl[q]);
+                bad |= !cfinite(xi);
+                stg_stream(x + c * kLM + i, xi);
+            }
+        }
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0 && status != nullptr) atomicOr(status, 1);
+}
+
+// ... and the special chunks: Thomas sweep with generated rows, one thread per chunk
+__global__ void uniform_special_backsub_kernel(UniformRows u, const cplx *__restrict__ xr, cplx *__restrict__ x,
+                                               int32_t *__restrict__ status) {
+    const int64_t c = special_chunk(u, (int)threadIdx.x);
+    if (c < 0) return;
+    const ChunkPos cp = chunk_pos(u.n, tile_count(u.n), c);
+    if (!cp.exists) return;
+    cplx in[4];
+    u.interior(in[0], in[1], in[2], in[3]);
+    const int64_t g0 = u.g_off + cp.r0;
+    const cplx x0 = xr[2 * c], xl = cp.len > 1 ? xr[2 * c + 1] : x0;
+    bool bad = !cfinite(x0) || !cfinite(xl);
+    cplx cs[kLM + 1], ds[kLM + 1];
+    cplx cpv = czero(), dpv = x0;
+    for (int i = 1; i <= cp.len - 2; ++i) {
+        cplx a, b, cc, d;
+        u.row(g0 + i, in, a, b, cc, d);
+        const cplx inv = frecip(nmsub(b, a, cpv));
+        dpv = nmsub(d, a, dpv) * inv;
+        cpv = cc * inv;
+        cs[i] = cpv, ds[i] = dpv;
+    }
+    cplx xn = xl;
+    if (cp.len > 1) x[cp.r0 + cp.len - 1] = xl;
+    for (int i = cp.len - 2; i >= 1; --i) {
+        xn = nmsub(ds[i], cs[i], xn);
+        bad |= !cfinite(xn);
+        x[cp.r0 + i] = xn;
+    }
+    x[cp.r0] = x0;
+    if (bad && status != nullptr) atomicOr(status, 1);
+}
+
 // Tiny dense solve of the gathered interface system (2P rows, P = number of ranks): one thread,
 // Gaussian elimination with partial pivoting.  iface: [P][4][2] = per rank (a, b, c, d) x (first, last).
 constexpr int kIfaceMax = 32;  // up to 16 ranks (one NVSwitch domain)
@@ -302,6 +538,51 @@ static int launch_backsub(const Source &src, const cplx *xr, cplx *x, int32_t *s
     FH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LargeSmem)));
     kern<<<grid_for(src.n), kLT, sizeof(LargeSmem), st>>>(src, xr, x, status);
     FH_LAUNCH_CHECK("large_backsub_kernel");
+    return FH_OK;
+}
+
+// generated rows on a uniform mesh: the structured level-0 kernels
+static bool uniform_rows(const HelmRows &src) { return src.p.h_mode == FH_H_SCALAR && src.p.n_elem >= 2; }
+static UniformRows as_uniform(const HelmRows &src) {
+    UniformRows u;
+    u.p = src.p, u.k = src.k, u.k2 = src.k2, u.g_off = src.g_off, u.n = src.n;
+    return u;
+}
+// contiguous ranges: `units` pieces of work over at most 8 CTAs per SM; returns the grid, sets units per CTA (a
+// multiple of `granule`)
+static unsigned uniform_grid(int64_t units, int64_t granule, int64_t *per_block) {
+    const int64_t want = 8ll * sm_count();
+    int64_t per = (units + want - 1) / want;
+    per = ((per + granule - 1) / granule) * granule;
+    if (per < granule) per = granule;
+    *per_block = per;
+    const int64_t blocks = (units + per - 1) / per;
+    return (unsigned)(blocks < 1 ? 1 : blocks);
+}
+static int launch_reduce(const HelmRows &src, const LevelPtrs &out, cudaStream_t st) {
+    if (!uniform_rows(src)) return launch_reduce<HelmRows>(src, out, st);
+    const UniformRows u = as_uniform(src);
+    const UniformSpan sp = uniform_span(u.g_off, u.n);
+    if (sp.c_hi > sp.c_lo) {
+        int64_t per;
+        const unsigned grid = uniform_grid(2 * (sp.c_hi - sp.c_lo), 2 * kUniThreads, &per);
+        uniform_reduce_kernel<<<grid, kUniThreads, 0, st>>>(u, per, out.a, out.b, out.c, out.d);
+    }
+    uniform_special_reduce_kernel<<<1, 96, 0, st>>>(u, out.a, out.b, out.c, out.d);
+    FH_LAUNCH_CHECK("uniform_reduce_kernel");
+    return FH_OK;
+}
+static int launch_backsub(const HelmRows &src, const cplx *xr, cplx *x, int32_t *status, cudaStream_t st) {
+    if (!uniform_rows(src)) return launch_backsub<HelmRows>(src, xr, x, status, st);
+    const UniformRows u = as_uniform(src);
+    const UniformSpan sp = uniform_span(u.g_off, u.n);
+    if (sp.c_hi > sp.c_lo) {
+        int64_t per;
+        const unsigned grid = uniform_grid(sp.c_hi - sp.c_lo, kUniThreads / kLM, &per);
+        uniform_backsub_kernel<<<grid, kUniThreads, 0, st>>>(u, per, xr, x, status);
+    }
+    uniform_special_backsub_kernel<<<1, 96, 0, st>>>(u, xr, x, status);
+    FH_LAUNCH_CHECK("uniform_backsub_kernel");
     return FH_OK;
 }
 

@@ -57,15 +57,18 @@ def test_large_solver_batch_of_long_systems():
 
 @pytest.mark.parametrize("N,k", [(16384, 1000.0), (1_000_000, 10.0), (1_000_000, 1000.0)])
 def test_helmholtz_large_mesh_staged_and_fused(N, k):
-    """BASELINE configs 2 and 5 (N = 1e6; k = 1000 with the Robin row): staged (bands stored) and fused
-    (rows generated) agree bit for bit; checked against LAPACK zgtsv on the oracle's bands, the exact
-    discrete solution, and by backward error."""
+    """BASELINE configs 2 and 5 (N = 1e6; k = 1000 with the Robin row): staged (bands stored, generic level-0 sweeps)
+    and fused (rows generated; on a uniform mesh the structured level-0 kernels) are both checked against LAPACK zgtsv
+    on the oracle's bands, the exact discrete solution, and by backward error.  (They carry out the same elimination
+    but round differently -- the fused path evaluates a chunk's sweep once, symbolically in its end values -- so they
+    agree to cond(A) * eps, not bit for bit.)"""
     nodes, u = fh.solve_helmholtz_fem(N, k)
     nodes_f, u_f = fh.solve_helmholtz_fem(N, k, fused=True)
-    assert np.array_equal(u, u_f)
     bands = banded1d.assemble_bands(N, k, 1.0 / N)
     be, _ = banded1d.residual_metrics(*bands, u)
     assert be < 1e-14, be  # bar 1e-10; LAPACK reaches ~2e-17
+    be_f, _ = banded1d.residual_metrics(*bands, u_f)
+    assert be_f < 1e-14, be_f
     ref = banded1d.solve_bands(*bands)
     ex = banded1d.discrete_exact(N, k)
     # The forward error is conditioning-limited at this size: cond(A)*eps ~ 5e-9 (k=1000) .. 5e-6 (k=10).
@@ -73,6 +76,7 @@ def test_helmholtz_large_mesh_staged_and_fused(N, k):
     # (7e-11) while any other elimination order sits at the bound (measured 2e-9 here, backward error
     # 5e-17).  Gate: within 100x of LAPACK's distance to the exact discrete solution.
     assert rel_err(u, ex) < max(1e-10, 100 * rel_err(ref, ex)), (rel_err(u, ex), rel_err(ref, ex))
+    assert rel_err(u_f, ex) < max(1e-10, 100 * rel_err(ref, ex)), (rel_err(u_f, ex), rel_err(ref, ex))
 
 
 def _emulated_ranks_fused(N, k, world):
