@@ -91,6 +91,48 @@ assemble1d_scalar_kernel(Problem1d p, const double *__restrict__ ks, const doubl
     }
 }
 
+// Non-uniform meshes (FH_H_NODAL), many wavenumbers: the same structured fill, with the k-independent geometry of every
+// row (six numbers, IEEE divisions) evaluated ONCE into a small table (48 B per row: L2-resident) instead of once per
+// CTA row-tile, so that every CTA can stream contiguous slabs of the four arrays like the scalar-h kernel does.
+__global__ void __launch_bounds__(kAsmThreads)
+row_geometry_kernel(Problem1d p, double *__restrict__ geom /* [6][n] */) {
+    const int64_t n = p.n_elem + 1;
+    const int64_t j = static_cast<int64_t>(blockIdx.x) * kAsmThreads + threadIdx.x;
+    if (j >= n) return;
+    const RowGeom g = row_geom(p, j);
+    geom[j] = g.Kd, geom[n + j] = g.Md, geom[2 * n + j] = g.Kl, geom[3 * n + j] = g.Ml;
+    geom[4 * n + j] = g.Ku, geom[5 * n + j] = g.Mu;
+}
+
+__global__ void __launch_bounds__(kAsmThreads)
+assemble1d_table_kernel(Problem1d p, const double *__restrict__ geom, const double *__restrict__ ks,
+                        const double *__restrict__ k2s, int64_t n_k, int64_t per_block, cplx *__restrict__ dl,
+                        cplx *__restrict__ d, cplx *__restrict__ du, cplx *__restrict__ b) {
+    const int64_t n = p.n_elem + 1;
+    const int64_t o_begin = static_cast<int64_t>(blockIdx.x) * per_block;
+    const int64_t o_end = min(n_k * n, o_begin + per_block);
+    if (o_begin >= o_end) return;
+    int64_t o = o_begin + threadIdx.x;
+    int64_t s = o / n;      // wavenumber index; (s, j) follow o incrementally from here on
+    int64_t j = o - s * n;  // row
+    int64_t s_cached = -1;
+    double k = 0.0, k2 = 0.0;
+    for (; o < o_end; o += kAsmThreads) {
+        if (s != s_cached) k = __ldg(ks + s), k2 = __ldg(k2s + s), s_cached = s;
+        RowGeom g;
+        g.Kd = __ldg(geom + j), g.Md = __ldg(geom + n + j), g.Kl = __ldg(geom + 2 * n + j);
+        g.Ml = __ldg(geom + 3 * n + j), g.Ku = __ldg(geom + 4 * n + j), g.Mu = __ldg(geom + 5 * n + j);
+        cplx vl, vd, vu, vb;
+        row_values(p, g, j, k, k2, vl, vd, vu, vb);
+        stg_stream(dl + o, vl);
+        stg_stream(d + o, vd);
+        stg_stream(du + o, vu);
+        stg_stream(b + o, vb);
+        j += kAsmThreads;
+        while (j >= n) j -= n, ++s;
+    }
+}
+
 __global__ void shape1d_kernel(double xi, double *phi, double *dphi) {
     double a[2], c[2];
     shape1d(xi, a, c);
@@ -165,6 +207,36 @@ int fh_assemble_1d_c128(const fh_problem1d *prob_host, const double *ks, const d
     }
     const int64_t row_blocks = (n + fh::kAsmThreads - 1) / fh::kAsmThreads;
     FH_REQUIRE(row_blocks < (1ll << 31), "mesh too large for one launch");
+    if (n_k >= 8) {  // many wavenumbers: geometry table (stream-ordered scratch, 48 B per row) + structured fill
+        {   // keep freed scratch in the device's default pool (released at synchronisation points otherwise: every call
+            // would go back to the driver for 200 KB)
+            static int configured_device = -1;
+            int dev = 0;
+            cudaMemPool_t pool;
+            if (cudaGetDevice(&dev) == cudaSuccess && dev != configured_device &&
+                cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                unsigned long long keep = 64ull << 20;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+                configured_device = dev;
+            }
+        }
+        double *geom = nullptr;
+        if (cudaMallocAsync(reinterpret_cast<void **>(&geom), sizeof(double) * 6 * (size_t)n, st) == cudaSuccess) {
+            fh::row_geometry_kernel<<<(unsigned)row_blocks, fh::kAsmThreads, 0, st>>>(p, geom);
+            const int64_t total = n_k * n;
+            int64_t slabs = 8ll * fh::sm_count();
+            int64_t per = (total + slabs - 1) / slabs;
+            per = ((per + fh::kAsmThreads - 1) / fh::kAsmThreads) * fh::kAsmThreads;
+            slabs = (total + per - 1) / per;
+            fh::assemble1d_table_kernel<<<(unsigned)slabs, fh::kAsmThreads, 0, st>>>(
+                p, geom, ks, k2s, n_k, per, reinterpret_cast<fh::cplx *>(dl), reinterpret_cast<fh::cplx *>(d),
+                reinterpret_cast<fh::cplx *>(du), reinterpret_cast<fh::cplx *>(b));
+            FH_CUDA(cudaFreeAsync(geom, st));
+            FH_LAUNCH_CHECK("assemble1d_table_kernel");
+            return FH_OK;
+        }
+        (void)cudaGetLastError();  // no stream-ordered allocator: fall through to the row-tiled kernel
+    }
     // Split the k range so that the grid covers every SM several times even for short meshes,
     // while each thread still amortises its geometry over a slab of wavenumbers.
     const int64_t want_blocks = 8ll * fh::sm_count();

@@ -100,6 +100,20 @@ def test_assembly_nodal_h_mode_bit_exact():
         assert all(np.array_equal(a, b) for a, b in zip(got, want))
 
 
+def test_assembly_nodal_h_many_wavenumbers_bit_exact():
+    """n_k >= 8 takes the geometry-table kernel (slabs cut across system boundaries); same bits as the oracle."""
+    rng = np.random.default_rng(1)
+    for N, n_k in ((1000, 8), (37, 300), (4096, 11)):
+        x = np.linspace(0.0, 1.0, N + 1)
+        x[1:-1] += rng.uniform(-0.25, 0.25, N - 1) / N
+        ks = np.linspace(1.0, 400.0, n_k)
+        for bc in (dict(), dict(bc_left="dirichlet", bc_right="dirichlet", g_left=1.0, g_right=0.5j)):
+            got = [_np(t) for t in fh.assemble_bands(N, ks, 1.0 / N, 0.3, nodes=x, **bc)]
+            for i in (0, 1, n_k // 2, n_k - 1):
+                want = banded1d.assemble_bands(N, float(ks[i]), 1.0 / N, 0.3, x=x, **bc)
+                assert all(np.array_equal(a[i], b) for a, b in zip(got, want)), (N, n_k, i, bc)
+
+
 def test_solve_matches_reference_solution(golden1d):
     g = golden1d
     for idx, N, k, L in golden_cases(g):
