@@ -204,16 +204,22 @@ large_backsub_kernel(Source src, const cplx *__restrict__ xr, cplx *__restrict__
 }
 
 // ---------------------------------------------------------------------------------------------- uniform meshes
-// Level 0 of a GENERATED system on a uniform mesh (scalar h: the reference's only mode, nb:158).  Every interior row
-// holds the same four numbers, so every full interior chunk reduces to the same two interface rows, and the
-// back-substitution of such a chunk is the same linear map of its two known end values:
-//     x_i = alpha_i x_first + beta_i x_last + gamma_i,      i = 1 .. 14
-// (alpha, beta, gamma: the chunk's Thomas sweep carried out once, symbolically in x_first / x_last).  What is left of
-// the two level-0 passes is a structured fill of the interface rows (8 B per row) and a streaming kernel that reads two
-// values per chunk and writes the solution (18 B per row) -- the elimination itself is unchanged, it is just not
-// repeated 2^23 times.  The chunks that are not "full interior" (those holding mesh row 0 or N, and the short / merged
-// chunk at the end of the last tile) take the generic sweeps, with rows generated on the fly.
-struct UniformRows {  // what HelmRows provides, with the interior row evaluated once on the host side of the launch
+// A GENERATED system on a uniform mesh (scalar h: the reference's only mode, nb:158) is periodic at every level of
+// the recursion.  Level 0: every interior row holds the same four numbers, so every full interior chunk reduces to
+// the same two interface rows (E1, O1).  Level 1 therefore reads E1 O1 E1 O1 ..., every full chunk of THAT reduces to
+// the same (E2, O2), and so on: at level l the "plain" rows alternate between two constant rows (E_l at even, O_l at
+// odd positions; E_0 = O_0).  Only the chunks that touch a mesh end or the ragged end of a level ("special" chunks: at
+// most one at the front and two or three at the back of each level) hold anything else.  Hence
+//   reduce   : nothing is streamed.  ONE single-CTA kernel walks down the levels; per level one lane reduces the plain
+//              chunk (-> E_{l+1}, O_{l+1}), one lane per special chunk reduces that chunk (rows = constants, generated
+//              mesh-end rows, or special rows of the level, which are the only entries of the level arrays ever written),
+//              and one lane carries out the chunk's Thomas sweep symbolically in its two end values:
+//                  x_i = alpha_i x_first + beta_i x_last + gamma_i,      i = 0 .. 15;
+//   back-sub : plain chunks are a streaming map of the two end values through (alpha, beta, gamma) -- 2 B read + 16 B
+//              written per row --, special chunks take the generic sweep.  Levels of <= 2^14 rows are handled inside
+//              one single-CTA kernel, the larger ones take one launch each.
+// The elimination arithmetic is that of large_reduce_kernel / large_backsub_kernel; it is just not repeated 2^23 times.
+struct UniformRows {  // what HelmRows provides
     Problem1d p;
     double k, k2;
     int64_t g_off, n;
@@ -231,7 +237,7 @@ struct ChunkPos {
     int len;     // rows (2 .. 17; 1 only if the level has a single row)
     bool exists;
 };
-__device__ __forceinline__ ChunkPos chunk_pos(int64_t n, int64_t n_tiles, int64_t c) {
+__host__ __device__ __forceinline__ ChunkPos chunk_pos(int64_t n, int64_t n_tiles, int64_t c) {
     const int64_t tile = c / kLT;
     const int t = (int)(c - tile * kLT);
     const int rows = tile_rows(n, n_tiles, tile);
@@ -242,150 +248,182 @@ __device__ __forceinline__ ChunkPos chunk_pos(int64_t n, int64_t n_tiles, int64_
     cp.len = cp.exists ? (t == nch - 1 ? rows - t * kLM : kLM) : 0;
     return cp;
 }
-// full chunk of 16 interior rows?
-__device__ __forceinline__ bool chunk_is_plain(const UniformRows &u, const ChunkPos &cp) {
-    const int64_t g0 = u.g_off + cp.r0;
-    return cp.len == kLM && g0 != 0 && g0 + cp.len - 1 != u.p.n_elem;
-}
 
-// the two interface rows of a chunk whose rows come from `rowfn(i, a, b, c, d)` -- the arithmetic of large_reduce_kernel
+// the two interface rows of a chunk whose rows come from `rowfn(i, a, b, c, d)` -- the arithmetic of large_reduce_kernel,
+// one sweep per call (the two sweeps are independent: they run in different warps)
 template <class RowFn>
-__device__ __forceinline__ void reduce_chunk(RowFn rowfn, int len, cplx out1[4], cplx out2[4]) {
-    cplx ra, rb, rc, rd;
-    if (len == 1) {
-        rowfn(0, ra, rb, rc, rd);
-        out1[0] = ra, out1[1] = rb, out1[2] = czero(), out1[3] = rd;
-        out2[0] = czero(), out2[1] = cone(), out2[2] = czero(), out2[3] = czero();
-        return;
+__device__ __forceinline__ void reduce_chunk_down(RowFn rowfn, int len, cplx out2[4]) {  // -> row in the LAST unknown
+    cplx ra, rb, rc, rd, pa, pb, pc, pd;
+    rowfn(1, pa, pb, pc, pd);
+    for (int i = 2; i < len; ++i) {  // fill-in couples to x_first
+        rowfn(i, ra, rb, rc, rd);
+        const cplx w = ra * frecip(pb);
+        const cplx nb = nmsub(rb, w, pc), nd = nmsub(rd, w, pd);
+        pa = -(w * pa), pb = nb, pc = rc, pd = nd;
     }
-    {  // downward from row 1: fill-in couples to x_first
-        cplx pa, pb, pc, pd;
-        rowfn(1, pa, pb, pc, pd);
-        for (int i = 2; i < len; ++i) {
-            rowfn(i, ra, rb, rc, rd);
-            const cplx w = ra * frecip(pb);
-            const cplx nb = nmsub(rb, w, pc), nd = nmsub(rd, w, pd);
-            pa = -(w * pa), pb = nb, pc = rc, pd = nd;
-        }
-        out2[0] = pa, out2[1] = pb, out2[2] = pc, out2[3] = pd;
+    out2[0] = pa, out2[1] = pb, out2[2] = pc, out2[3] = pd;
+}
+template <class RowFn>
+__device__ __forceinline__ void reduce_chunk_up(RowFn rowfn, int len, cplx out1[4]) {  // -> row in the FIRST unknown
+    cplx ra, rb, rc, rd, qa, qb, qc, qd;
+    rowfn(len - 2, qa, qb, qc, qd);
+    for (int i = len - 3; i >= 0; --i) {  // fill-in couples to x_last
+        rowfn(i, ra, rb, rc, rd);
+        const cplx w = rc * frecip(qb);
+        const cplx nb = nmsub(rb, w, qa), nd = nmsub(rd, w, qd);
+        qc = -(w * qc), qb = nb, qa = ra, qd = nd;
     }
-    {  // upward from row len-2: fill-in couples to x_last
-        cplx qa, qb, qc, qd;
-        rowfn(len - 2, qa, qb, qc, qd);
-        for (int i = len - 3; i >= 0; --i) {
-            rowfn(i, ra, rb, rc, rd);
-            const cplx w = rc * frecip(qb);
-            const cplx nb = nmsub(rb, w, qa), nd = nmsub(rd, w, qd);
-            qc = -(w * qc), qb = nb, qa = ra, qd = nd;
-        }
-        out1[0] = qa, out1[1] = qb, out1[2] = qc, out1[3] = qd;
-    }
+    out1[0] = qa, out1[1] = qb, out1[2] = qc, out1[3] = qd;
 }
 
-constexpr int kUniThreads = 256;
-
-// Which chunks the streaming kernels cover: every chunk of the full tiles (tiles 0 .. n_tiles - 2 hold exactly 64 chunks
-// of 16 rows: chunk c = rows 16 c .. 16 c + 15), except chunk 0 when it holds mesh row 0.  The last tile (whose last
-// chunk may be short or merged, and which holds mesh row N when the slab ends the mesh) and that first chunk go to the
-// one-thread-per-chunk kernels below.
-struct UniformSpan {
-    int64_t c_lo, c_hi;  // streaming chunks [c_lo, c_hi)
+struct LevelPtrs {
+    cplx *a, *b, *c, *d, *x;
 };
-__host__ __device__ __forceinline__ UniformSpan uniform_span(int64_t g_off, int64_t n) {
-    UniformSpan sp;
-    sp.c_lo = g_off == 0 ? 1 : 0;
-    sp.c_hi = (tile_count(n) - 1) * kLT;
-    if (sp.c_hi < sp.c_lo) sp.c_hi = sp.c_lo;
-    return sp;
-}
-// special chunk number `idx` (0 .. kLT): the chunks of the last tile, then chunk 0 (when it is not a streaming chunk
-// and not part of the last tile)
-__device__ __forceinline__ int64_t special_chunk(const UniformRows &u, int idx) {
-    const int64_t n_tiles = tile_count(u.n);
-    if (idx < kLT) return (n_tiles - 1) * kLT + idx;
-    if (idx == kLT && n_tiles > 1 && u.g_off == 0) return 0;
-    return -1;
-}
 
-// Structured fill: the interface rows of a plain chunk, computed once per CTA, written for every streaming chunk;
-// every CTA owns a contiguous range of chunks.
-__global__ void __launch_bounds__(kUniThreads)
-uniform_reduce_kernel(UniformRows u, int64_t per_block, cplx *__restrict__ ra, cplx *__restrict__ rb,
-                      cplx *__restrict__ rc, cplx *__restrict__ rd) {
-    __shared__ cplx plain[2][4];
-    if (threadIdx.x == 0) {
-        cplx in[4], p1[4], p2[4];
-        u.interior(in[0], in[1], in[2], in[3]);
-        reduce_chunk([&](int, cplx &a, cplx &b, cplx &c, cplx &d) { a = in[0], b = in[1], c = in[2], d = in[3]; }, kLM,
-                     p1, p2);
-        for (int q = 0; q < 4; ++q) plain[0][q] = p1[q], plain[1][q] = p2[q];
+constexpr int kDeepThreads = 256;
+constexpr int kDeepSpecialMax = 7;        // special chunks per level the kernels accept (there are at most two)
+constexpr int64_t kDeepSmall = 1 << 14;   // levels up to this many rows are back-substituted inside the single-CTA kernel
+
+struct DeepLevel {
+    int64_t n, chunks;  // rows, chunks
+    int64_t plo, phi;   // plain rows  [plo, phi): row r holds E (r even) / O (r odd)
+    int64_t clo, chi;   // plain chunks [clo, chi): 16 plain rows each
+};
+struct DeepPlan {  // host-computed geometry of the recursion + where the level arrays live (kernel parameter)
+    int levels;                          // level `levels` has exactly 2 rows
+    DeepLevel lv[kMaxLevels + 1];
+    LevelPtrs ptr[kMaxLevels + 1];       // levels >= 1 (ptr[0] is unused: level-0 rows are generated, its x is the caller's)
+};
+struct DeepConsts {  // per level, written by the reduce kernel, read by the back-substitution
+    cplx eo[2][4];        // E, O: (a, b, c, d)
+    cplx tab[3][kLM];     // alpha, beta, gamma
+};
+
+__device__ __forceinline__ int deep_special_count(const DeepLevel &L) { return (int)(L.clo + (L.chunks - L.chi)); }
+__device__ __forceinline__ int64_t deep_special_chunk(const DeepLevel &L, int s) {
+    return s < L.clo ? (int64_t)s : L.chi + (s - L.clo);
+}
+// row r of level l
+__device__ __forceinline__ void deep_row(const UniformRows &u, const DeepPlan &dp, const DeepConsts *cs, int l, int64_t r,
+                                         cplx &a, cplx &b, cplx &c, cplx &d) {
+    const DeepLevel &L = dp.lv[l];
+    if (r >= L.plo && r < L.phi) {
+        const cplx *e = cs[l].eo[r & 1];
+        a = e[0], b = e[1], c = e[2], d = e[3];
+    } else if (l == 0) {
+        u.row(u.g_off + r, cs[0].eo[0], a, b, c, d);
+    } else {
+        const LevelPtrs &p = dp.ptr[l];
+        a = p.a[r], b = p.b[r], c = p.c[r], d = p.d[r];
     }
-    __syncthreads();
-    // thread t writes entry o = 2 c + (t & 1) of the four interface arrays: consecutive lanes, consecutive entries
-    const int half = threadIdx.x & 1;
-    const cplx va = plain[half][0], vb = plain[half][1], vc = plain[half][2], vd = plain[half][3];
-    const UniformSpan sp = uniform_span(u.g_off, u.n);
-    const int64_t o_begin = 2 * sp.c_lo + (int64_t)blockIdx.x * per_block;
-    int64_t o_end = o_begin + per_block;
-    if (o_end > 2 * sp.c_hi) o_end = 2 * sp.c_hi;
-    for (int64_t o = o_begin + threadIdx.x; o < o_end; o += kUniThreads)   // (per_block is even: parity = t & 1)
-        stg_stream(ra + o, va), stg_stream(rb + o, vb), stg_stream(rc + o, vc), stg_stream(rd + o, vd);
 }
 
-// ... and the special chunks: generic sweeps, rows generated on the fly, one thread per chunk
-__global__ void uniform_special_reduce_kernel(UniformRows u, cplx *__restrict__ ra, cplx *__restrict__ rb,
-                                              cplx *__restrict__ rc, cplx *__restrict__ rd) {
-    const int64_t c = special_chunk(u, (int)threadIdx.x);
-    if (c < 0) return;
-    const ChunkPos cp = chunk_pos(u.n, tile_count(u.n), c);
-    if (!cp.exists) return;
-    cplx in[4], o1[4], o2[4];
-    u.interior(in[0], in[1], in[2], in[3]);
-    const int64_t g0 = u.g_off + cp.r0;
-    reduce_chunk([&](int i, cplx &a, cplx &b, cplx &c2, cplx &d) { u.row(g0 + i, in, a, b, c2, d); }, cp.len, o1, o2);
-    const int64_t o = 2 * c;
-    ra[o] = o1[0], rb[o] = o1[1], rc[o] = o1[2], rd[o] = o1[3];
-    ra[o + 1] = o2[0], rb[o + 1] = o2[1], rc[o + 1] = o2[2], rd[o + 1] = o2[3];
+typedef cplx DeepRows[kLM + 1][4];  // the (a, b, c, d) rows of one chunk, staged in shared memory
+struct DeepStage {
+    DeepRows rows[kDeepSpecialMax + 1];
+    int len[kDeepSpecialMax + 1];
+};
+// All threads: the rows of the special chunks of level l -- and, with_plain, of a plain chunk as entry number ns -- go to
+// shared memory with every load in flight at once (inside the sweeps each row would cost a dependent L2 round trip).
+__device__ __forceinline__ void deep_stage(const UniformRows &u, const DeepPlan &dp, const DeepConsts *cs, int l,
+                                           bool with_plain, DeepStage &sg) {
+    const DeepLevel &L = dp.lv[l];
+    const int ns = deep_special_count(L);
+    const int total = (ns + (with_plain ? 1 : 0)) * (kLM + 1);
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int s = idx / (kLM + 1), i = idx - s * (kLM + 1);
+        cplx a, b, c, d;
+        if (s == ns) {
+            if (i == 0) sg.len[s] = kLM;
+            if (i >= kLM) continue;
+            const cplx *e = cs[l].eo[i & 1];
+            a = e[0], b = e[1], c = e[2], d = e[3];
+        } else {
+            const ChunkPos cp = chunk_pos(L.n, tile_count(L.n), deep_special_chunk(L, s));
+            if (i == 0) sg.len[s] = cp.len;
+            if (i >= cp.len) continue;
+            deep_row(u, dp, cs, l, cp.r0 + i, a, b, c, d);
+        }
+        sg.rows[s][i][0] = a, sg.rows[s][i][1] = b, sg.rows[s][i][2] = c, sg.rows[s][i][3] = d;
+    }
 }
 
-// Streaming back-substitution: x(16 c + i) = alpha_i x_first(c) + beta_i x_last(c) + gamma_i.  Every CTA owns a
-// contiguous range of rows that starts on a chunk boundary; 256 threads = 16 chunks per pass, so a thread keeps the same
-// row-in-chunk i -- and with it (alpha_i, beta_i, gamma_i) in registers -- for its whole range.
-__global__ void __launch_bounds__(kUniThreads)
-uniform_backsub_kernel(UniformRows u, int64_t chunks_per_block, const cplx *__restrict__ xr, cplx *__restrict__ x,
-                       int32_t *__restrict__ status) {
-    __shared__ cplx tab[3][kLM], fwd[3][kLM];
-    if (threadIdx.x == 0) {
+// All reductions, level 0 down to the 2-row level, by ONE CTA.  Warp 0 runs the downward sweeps (lane s < ns: special
+// chunk s, lane ns: the plain chunk), warp 1 the upward sweeps, lane 0 of warp 2 the symbolic Thomas sweep.
+// cs: per-level constants in global memory (visible to the whole CTA after each level's barrier).
+__device__ void deep_reduce_levels(const UniformRows &u, const DeepPlan &dp, DeepConsts *cs, DeepStage &sg) {
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    if (t == 0) {
         cplx in[4];
         u.interior(in[0], in[1], in[2], in[3]);
-        // forward sweep with x_first as a symbol: dp_i = P_i x_first + G_i;  backward with x_last as a symbol
-        cplx cp = czero(), Pp = cone(), Gp = czero();
-        for (int i = 1; i <= kLM - 2; ++i) {
-            const cplx inv = frecip(nmsub(in[1], in[0], cp));
-            Pp = -((in[0] * Pp) * inv);
-            Gp = nmsub(in[3], in[0], Gp) * inv;
-            cp = in[2] * inv;
-            fwd[0][i] = cp, fwd[1][i] = Pp, fwd[2][i] = Gp;
-        }
-        cplx al = czero(), be = cone(), ga = czero();
-        tab[0][kLM - 1] = al, tab[1][kLM - 1] = be, tab[2][kLM - 1] = ga;  // x_15 = x_last
-        for (int i = kLM - 2; i >= 1; --i) {
-            al = nmsub(fwd[1][i], fwd[0][i], al);
-            be = -(fwd[0][i] * be);
-            ga = nmsub(fwd[2][i], fwd[0][i], ga);
-            tab[0][i] = al, tab[1][i] = be, tab[2][i] = ga;
-        }
-        tab[0][0] = cone(), tab[1][0] = czero(), tab[2][0] = czero();       // x_0 = x_first
+        for (int q = 0; q < 4; ++q) cs[0].eo[0][q] = cs[0].eo[1][q] = in[q];
     }
     __syncthreads();
+    for (int l = 0; l < dp.levels; ++l) {
+        const DeepLevel &L = dp.lv[l];
+        const int ns = deep_special_count(L);
+        deep_stage(u, dp, cs, l, true, sg);
+        __syncthreads();
+        if (warp < 2 && lane <= ns) {
+            cplx out[4];
+            const DeepRows &R = sg.rows[lane];
+            auto rowfn = [&](int i, cplx &a, cplx &b, cplx &c, cplx &d) { a = R[i][0], b = R[i][1], c = R[i][2], d = R[i][3]; };
+            if (warp == 0) reduce_chunk_down(rowfn, sg.len[lane], out);
+            else reduce_chunk_up(rowfn, sg.len[lane], out);
+            if (lane == ns) {
+                for (int q = 0; q < 4; ++q) cs[l + 1].eo[warp == 0 ? 1 : 0][q] = out[q];
+            } else {
+                const LevelPtrs &p = dp.ptr[l + 1];
+                const int64_t o = 2 * deep_special_chunk(L, lane) + (warp == 0 ? 1 : 0);
+                p.a[o] = out[0], p.b[o] = out[1], p.c[o] = out[2], p.d[o] = out[3];
+            }
+        }
+        if (t == 64) {  // x_i = alpha_i x_first + beta_i x_last + gamma_i for a plain chunk of this level
+            const DeepRows &R = sg.rows[ns];
+            cplx fc[kLM], fP[kLM], fG[kLM];
+            cplx cp = czero(), Pp = cone(), Gp = czero();
+#pragma unroll
+            for (int i = 1; i <= kLM - 2; ++i) {  // forward sweep with x_first as a symbol: dp_i = P_i x_first + G_i
+                const cplx inv = frecip(nmsub(R[i][1], R[i][0], cp));
+                Pp = -((R[i][0] * Pp) * inv);
+                Gp = nmsub(R[i][3], R[i][0], Gp) * inv;
+                cp = R[i][2] * inv;
+                fc[i] = cp, fP[i] = Pp, fG[i] = Gp;
+            }
+            cplx al = czero(), be = cone(), ga = czero();  // backward sweep with x_last as a symbol
+            cs[l].tab[0][kLM - 1] = al, cs[l].tab[1][kLM - 1] = be, cs[l].tab[2][kLM - 1] = ga;  // x_15 = x_last
+#pragma unroll
+            for (int i = kLM - 2; i >= 1; --i) {
+                al = nmsub(fP[i], fc[i], al);
+                be = -(fc[i] * be);
+                ga = nmsub(fG[i], fc[i], ga);
+                cs[l].tab[0][i] = al, cs[l].tab[1][i] = be, cs[l].tab[2][i] = ga;
+            }
+            cs[l].tab[0][0] = cone(), cs[l].tab[1][0] = czero(), cs[l].tab[2][0] = czero();  // x_0 = x_first
+        }
+        __syncthreads();
+    }
+    // the 2-row level in full: plain positions are filled in, so that its four arrays (a[2] b[2] c[2] d[2], contiguous)
+    // are the slab's interface rows
+    const DeepLevel &T = dp.lv[dp.levels];
+    if (t < T.n && t >= T.plo && t < T.phi) {
+        const LevelPtrs &p = dp.ptr[dp.levels];
+        const cplx *e = cs[dp.levels].eo[t & 1];
+        p.a[t] = e[0], p.b[t] = e[1], p.c[t] = e[2], p.d[t] = e[3];
+    }
+    __syncthreads();
+}
+
+// Plain chunks [c_begin, c_end) of one level: x(16 c + i) = alpha_i xr(2 c) + beta_i xr(2 c + 1) + gamma_i.  256 threads
+// = 16 chunks per pass, 8 passes in flight (the end-value loads overlap): one "round" writes 128 chunks = 32 KB of
+// contiguous solution.  A thread keeps the same row-in-chunk i throughout.
+// (xr is NOT __restrict__ / read-only-cached: inside the single-CTA kernel it was written a level earlier)
+__device__ __forceinline__ bool deep_backsub_plain(const DeepConsts &C, int64_t c_begin, int64_t c_end,
+                                                   const cplx *xr, cplx *x) {
     const int i = threadIdx.x & (kLM - 1);
-    const cplx al = tab[0][i], be = tab[1][i], ga = tab[2][i];
-    const UniformSpan sp = uniform_span(u.g_off, u.n);
-    const int64_t c_begin = sp.c_lo + (int64_t)blockIdx.x * chunks_per_block;
-    int64_t c_end = c_begin + chunks_per_block;
-    if (c_end > sp.c_hi) c_end = sp.c_hi;
+    const cplx al = C.tab[0][i], be = C.tab[1][i], ga = C.tab[2][i];
     bool bad = false;
-    constexpr int kStep = kUniThreads / kLM, kFly = 8;  // 8 passes in flight: the end-value loads overlap
+    constexpr int kStep = kDeepThreads / kLM, kFly = 8;
     for (int64_t c0 = c_begin + (threadIdx.x >> 4); c0 < c_end; c0 += kFly * kStep) {
         cplx x0[kFly], xl[kFly];
 #pragma unroll
@@ -403,40 +441,120 @@ uniform_backsub_kernel(UniformRows u, int64_t chunks_per_block, const cplx *__re
             }
         }
     }
+    return bad;
+}
+// special chunk number s of level l (rows staged by deep_stage): Thomas sweep between the two known end values, one
+// thread; c', d' overwrite the staged rows
+__device__ __forceinline__ bool deep_backsub_special(const DeepLevel &L, DeepStage &sg, int s, const cplx *xr, cplx *x) {
+    const int64_t c = deep_special_chunk(L, s), r0 = c * kLM;
+    const int len = sg.len[s];
+    DeepRows &R = sg.rows[s];
+    const cplx x0 = xr[2 * c], xl = xr[2 * c + 1];
+    bool bad = !cfinite(x0) || !cfinite(xl);
+    cplx cpv = czero(), dpv = x0;  // "row 0" acts as x_0 = x0
+    for (int i = 1; i <= len - 2; ++i) {
+        const cplx a = R[i][0];
+        const cplx inv = frecip(nmsub(R[i][1], a, cpv));
+        dpv = nmsub(R[i][3], a, dpv) * inv;
+        cpv = R[i][2] * inv;
+        R[i][2] = cpv, R[i][3] = dpv;
+    }
+    cplx xn = xl;
+    x[r0 + len - 1] = xl;
+    for (int i = len - 2; i >= 1; --i) {
+        xn = nmsub(R[i][3], R[i][2], xn);
+        bad |= !cfinite(xn);
+        x[r0 + i] = xn;
+    }
+    x[r0] = x0;
+    return bad;
+}
+__device__ __forceinline__ const cplx *deep_xr(const DeepPlan &dp, int l) { return dp.ptr[l + 1].x; }
+__device__ __forceinline__ cplx *deep_x(const DeepPlan &dp, int l, cplx *u_out) { return l == 0 ? u_out : dp.ptr[l].x; }
+
+// levels `levels - 1`, `levels - 2`, ... while they are small (<= kDeepSmall rows), by ONE CTA
+__device__ void deep_backsub_small_levels(const UniformRows &u, const DeepPlan &dp, const DeepConsts *cs, DeepStage &sg,
+                                          cplx *u_out, int32_t *status) {
+    bool bad = false;
+    for (int l = dp.levels - 1; l >= 0 && dp.lv[l].n <= kDeepSmall; --l) {
+        const DeepLevel &L = dp.lv[l];
+        const cplx *xr = deep_xr(dp, l);
+        cplx *x = deep_x(dp, l, u_out);
+        deep_stage(u, dp, cs, l, false, sg);
+        __syncthreads();
+        // the special chunks go to lane 0 of the last warps, ahead of their share of the streaming part (the sweep is
+        // the critical path of the level)
+        const int w = (kDeepThreads >> 5) - 1 - (int)(threadIdx.x >> 5);
+        if (w < deep_special_count(L) && (threadIdx.x & 31) == 0) bad |= deep_backsub_special(L, sg, w, xr, x);
+        __syncwarp();
+        bad |= deep_backsub_plain(cs[l], L.clo, L.chi, xr, x);
+        __syncthreads();
+    }
     if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0 && status != nullptr) atomicOr(status, 1);
 }
 
-// ... and the special chunks: Thomas sweep with generated rows, one thread per chunk
-__global__ void uniform_special_backsub_kernel(UniformRows u, const cplx *__restrict__ xr, cplx *__restrict__ x,
-                                               int32_t *__restrict__ status) {
-    const int64_t c = special_chunk(u, (int)threadIdx.x);
-    if (c < 0) return;
-    const ChunkPos cp = chunk_pos(u.n, tile_count(u.n), c);
-    if (!cp.exists) return;
-    cplx in[4];
-    u.interior(in[0], in[1], in[2], in[3]);
-    const int64_t g0 = u.g_off + cp.r0;
-    const cplx x0 = xr[2 * c], xl = cp.len > 1 ? xr[2 * c + 1] : x0;
-    bool bad = !cfinite(x0) || !cfinite(xl);
-    cplx cs[kLM + 1], ds[kLM + 1];
-    cplx cpv = czero(), dpv = x0;
-    for (int i = 1; i <= cp.len - 2; ++i) {
-        cplx a, b, cc, d;
-        u.row(g0 + i, in, a, b, cc, d);
-        const cplx inv = frecip(nmsub(b, a, cpv));
-        dpv = nmsub(d, a, dpv) * inv;
-        cpv = cc * inv;
-        cs[i] = cpv, ds[i] = dpv;
+// multi-GPU piece 1: reduce the slab to its two interface rows (iface8 = a[2] b[2] c[2] d[2])
+__global__ void __launch_bounds__(kDeepThreads)
+deep_reduce_kernel(UniformRows u, const __grid_constant__ DeepPlan dp, DeepConsts *cs, cplx *__restrict__ iface8) {
+    __shared__ DeepStage sg;
+    deep_reduce_levels(u, dp, cs, sg);
+    if (threadIdx.x < 8) iface8[threadIdx.x] = dp.ptr[dp.levels].a[threadIdx.x];
+}
+// multi-GPU piece 2: seed the 2-row level with the slab's end values, back-substitute the small levels
+__global__ void __launch_bounds__(kDeepThreads)
+deep_backsub_small_kernel(UniformRows u, const __grid_constant__ DeepPlan dp, const DeepConsts *cs,
+                          const cplx *__restrict__ x_first_last, cplx *__restrict__ u_out, int32_t *__restrict__ status) {
+    __shared__ DeepStage sg;
+    if (threadIdx.x < 2) dp.ptr[dp.levels].x[threadIdx.x] = x_first_last[threadIdx.x];
+    __syncthreads();
+    deep_backsub_small_levels(u, dp, cs, sg, u_out, status);
+}
+// single GPU: both pieces in one kernel; the 2-row system in between is solved with partial pivoting
+__global__ void __launch_bounds__(kDeepThreads)
+deep_solve_small_kernel(UniformRows u, const __grid_constant__ DeepPlan dp, DeepConsts *cs, cplx *__restrict__ u_out,
+                        int32_t *__restrict__ status) {
+    __shared__ DeepStage sg;
+    deep_reduce_levels(u, dp, cs, sg);
+    if (threadIdx.x == 0) {  // [b0 c0; a1 b1] x = [d0; d1]  (a0 and c1 are the exact zeros of the mesh ends)
+        const LevelPtrs &p = dp.ptr[dp.levels];
+        cplx b0 = p.b[0], c0 = p.c[0], d0 = p.d[0], a1 = p.a[1], b1 = p.b[1], d1 = p.d[1];
+        auto abs2 = [](cplx z) { return fma(z.re, z.re, z.im * z.im); };
+        if (abs2(a1) > abs2(b0)) {
+            cplx tmp = b0; b0 = a1, a1 = tmp;
+            tmp = c0, c0 = b1, b1 = tmp;
+            tmp = d0, d0 = d1, d1 = tmp;
+        }
+        const cplx inv0 = crecip(b0), m = a1 * inv0;
+        const cplx x1 = nmsub(d1, m, d0) * crecip(nmsub(b1, m, c0));
+        const cplx x0 = nmsub(d0, c0, x1) * inv0;
+        p.x[0] = x0, p.x[1] = x1;
+        if ((!cfinite(x0) || !cfinite(x1)) && status != nullptr) atomicOr(status, 1);
     }
-    cplx xn = xl;
-    if (cp.len > 1) x[cp.r0 + cp.len - 1] = xl;
-    for (int i = cp.len - 2; i >= 1; --i) {
-        xn = nmsub(ds[i], cs[i], xn);
-        bad |= !cfinite(xn);
-        x[cp.r0 + i] = xn;
+    __syncthreads();
+    deep_backsub_small_levels(u, dp, cs, sg, u_out, status);
+}
+// one large level: CTA 0 takes the special chunks, every other CTA streams `per` contiguous rounds of plain chunks
+// (measured on one slab of config 4, level 0 = 268 MB: capping the registers for 3 or 4 resident CTAs costs more than it
+// buys -- 150 / 205 us per slab against 105 --, and contiguous ranges beat a round-robin over the rounds)
+__global__ void __launch_bounds__(kDeepThreads)
+deep_backsub_level_kernel(UniformRows u, const __grid_constant__ DeepPlan dp, const DeepConsts *cs, int l, int64_t per,
+                          cplx *__restrict__ u_out, int32_t *__restrict__ status) {
+    __shared__ DeepStage sg;
+    const DeepLevel &L = dp.lv[l];
+    const cplx *xr = deep_xr(dp, l);
+    cplx *x = deep_x(dp, l, u_out);
+    bool bad = false;
+    if (blockIdx.x == 0) {
+        deep_stage(u, dp, cs, l, false, sg);
+        __syncthreads();
+        if ((int)threadIdx.x < deep_special_count(L)) bad = deep_backsub_special(L, sg, threadIdx.x, xr, x);
+    } else {
+        const int64_t b = blockIdx.x - 1;
+        int64_t c_end = L.clo + (b + 1) * per * 128;
+        if (c_end > L.chi) c_end = L.chi;
+        bad = deep_backsub_plain(cs[l], L.clo + b * per * 128, c_end, xr, x);
     }
-    x[cp.r0] = x0;
-    if (bad && status != nullptr) atomicOr(status, 1);
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0 && status != nullptr) atomicOr(status, 1);
 }
 
 // Tiny dense solve of the gathered interface system (2P rows, P = number of ranks): one thread,
@@ -509,9 +627,6 @@ static LevelPlan plan_levels(int64_t n0, int64_t stop_at) {
     return pl;
 }
 
-struct LevelPtrs {
-    cplx *a, *b, *c, *d, *x;
-};
 static LevelPtrs level_ptrs(void *ws, const LevelPlan &pl, int l) {
     cplx *base = reinterpret_cast<cplx *>(static_cast<char *>(ws) + pl.off[l]);
     const int64_t n = pl.n[l];
@@ -541,48 +656,63 @@ static int launch_backsub(const Source &src, const cplx *xr, cplx *x, int32_t *s
     return FH_OK;
 }
 
-// generated rows on a uniform mesh: the structured level-0 kernels
+// ---- generated rows on a uniform mesh: the periodic recursion ---------------------------------------------------------
 static bool uniform_rows(const HelmRows &src) { return src.p.h_mode == FH_H_SCALAR && src.p.n_elem >= 2; }
 static UniformRows as_uniform(const HelmRows &src) {
     UniformRows u;
     u.p = src.p, u.k = src.k, u.k2 = src.k2, u.g_off = src.g_off, u.n = src.n;
     return u;
 }
-// contiguous ranges: `units` pieces of work over at most 8 CTAs per SM; returns the grid, sets units per CTA (a
-// multiple of `granule`)
-static unsigned uniform_grid(int64_t units, int64_t granule, int64_t *per_block) {
-    const int64_t want = 8ll * sm_count();
-    int64_t per = (units + want - 1) / want;
-    per = ((per + granule - 1) / granule) * granule;
-    if (per < granule) per = granule;
-    *per_block = per;
-    const int64_t blocks = (units + per - 1) / per;
-    return (unsigned)(blocks < 1 ? 1 : blocks);
+// the per-level constants live behind the level arrays of the workspace
+static size_t deep_consts_offset(const LevelPlan &pl) { return (pl.total + 255) & ~(size_t)255; }
+static size_t deep_workspace_bytes(int64_t n) {
+    return deep_consts_offset(plan_levels(n, 2)) + sizeof(DeepConsts) * (kMaxLevels + 1);
 }
-static int launch_reduce(const HelmRows &src, const LevelPtrs &out, cudaStream_t st) {
-    if (!uniform_rows(src)) return launch_reduce<HelmRows>(src, out, st);
-    const UniformRows u = as_uniform(src);
-    const UniformSpan sp = uniform_span(u.g_off, u.n);
-    if (sp.c_hi > sp.c_lo) {
-        int64_t per;
-        const unsigned grid = uniform_grid(2 * (sp.c_hi - sp.c_lo), 2 * kUniThreads, &per);
-        uniform_reduce_kernel<<<grid, kUniThreads, 0, st>>>(u, per, out.a, out.b, out.c, out.d);
+// Geometry of the recursion for the rows [g_off, g_off + n) of a mesh with n_elem elements: which rows / chunks of every
+// level are plain.  Only the last chunk of a level can be irregular (short, or 17 rows after a merge), and a chunk is
+// plain when it has 16 rows, all of them plain.  false: not applicable (the caller takes the generic kernels).
+static bool deep_plan(const HelmRows &src, void *ws, size_t ws_bytes, DeepPlan &dp, DeepConsts *&cs) {
+    if (!uniform_rows(src) || ws == nullptr) return false;
+    const LevelPlan pl = plan_levels(src.n, 2);
+    if (pl.levels < 1 || pl.n[pl.levels] != 2 || ws_bytes < deep_workspace_bytes(src.n)) return false;
+    memset(&dp, 0, sizeof(dp));
+    dp.levels = pl.levels;
+    int64_t plo = src.g_off == 0 ? 1 : 0;                                     // mesh row 0 has its own coefficients
+    int64_t phi = src.n - (src.g_off + src.n - 1 == src.p.n_elem ? 1 : 0);    // ... and so has mesh row N
+    for (int l = 0; l <= pl.levels; ++l) {
+        DeepLevel &L = dp.lv[l];
+        L.n = pl.n[l];
+        const int64_t nt = tile_count(L.n);
+        const int last_rows = tile_rows(L.n, nt, nt - 1), nch_last = chunk_count(last_rows);
+        L.chunks = (nt - 1) * kLT + nch_last;
+        const int last_len = last_rows - (nch_last - 1) * kLM;
+        L.plo = plo, L.phi = phi;
+        int64_t clo = (plo + kLM - 1) / kLM, chi = phi / kLM;
+        const int64_t regular = L.chunks - (last_len != kLM ? 1 : 0);
+        if (chi > regular) chi = regular;
+        if (clo > L.chunks) clo = L.chunks;
+        if (chi < clo) chi = clo;
+        L.clo = clo, L.chi = chi;
+        if (l < pl.levels && clo + (L.chunks - chi) > kDeepSpecialMax) return false;
+        plo = 2 * clo, phi = 2 * chi;
+        if (l >= 1) dp.ptr[l] = level_ptrs(ws, pl, l);
     }
-    uniform_special_reduce_kernel<<<1, 96, 0, st>>>(u, out.a, out.b, out.c, out.d);
-    FH_LAUNCH_CHECK("uniform_reduce_kernel");
-    return FH_OK;
+    cs = reinterpret_cast<DeepConsts *>(static_cast<char *>(ws) + deep_consts_offset(pl));
+    return true;
 }
-static int launch_backsub(const HelmRows &src, const cplx *xr, cplx *x, int32_t *status, cudaStream_t st) {
-    if (!uniform_rows(src)) return launch_backsub<HelmRows>(src, xr, x, status, st);
-    const UniformRows u = as_uniform(src);
-    const UniformSpan sp = uniform_span(u.g_off, u.n);
-    if (sp.c_hi > sp.c_lo) {
-        int64_t per;
-        const unsigned grid = uniform_grid(sp.c_hi - sp.c_lo, kUniThreads / kLM, &per);
-        uniform_backsub_kernel<<<grid, kUniThreads, 0, st>>>(u, per, xr, x, status);
+// the levels the single-CTA kernel leaves over, largest last
+static int deep_backsub_big_levels(const UniformRows &u, const DeepPlan &dp, const DeepConsts *cs, cplx *u_out,
+                                   int32_t *status, cudaStream_t st) {
+    int l = dp.levels - 1;
+    while (l >= 0 && dp.lv[l].n <= kDeepSmall) --l;
+    for (; l >= 0; --l) {
+        const int64_t rounds = (dp.lv[l].chi - dp.lv[l].clo + 127) / 128;  // 32 KB of solution each
+        const int64_t want = 16ll * sm_count();                              // a few waves of 2 resident CTAs per SM
+        const int64_t per = rounds > want ? (rounds + want - 1) / want : 1;
+        const int64_t ctas = (rounds + per - 1) / per;
+        deep_backsub_level_kernel<<<(unsigned)(ctas + 1), kDeepThreads, 0, st>>>(u, dp, cs, l, per, u_out, status);
     }
-    uniform_special_backsub_kernel<<<1, 96, 0, st>>>(u, xr, x, status);
-    FH_LAUNCH_CHECK("uniform_backsub_kernel");
+    FH_LAUNCH_CHECK("deep_backsub_level_kernel");
     return FH_OK;
 }
 
@@ -636,7 +766,10 @@ static int solve_large_any(const Source0 &src0, cplx *u, int64_t n, int32_t *sta
     return backsub_all(src0, pl, ws, 0, 0, u, status, st);
 }
 
-size_t solve_large_workspace_bytes(int64_t n) { return plan_levels(n, kCoarseMax).total; }
+size_t solve_large_workspace_bytes(int64_t n) {  // stored bands, or generated rows (periodic recursion)
+    const size_t a = plan_levels(n, kCoarseMax).total, b = deep_workspace_bytes(n);
+    return a > b ? a : b;
+}
 
 int solve_large(const cplx *dl, const cplx *d, const cplx *du, const cplx *b, cplx *u, int64_t n, int32_t *status,
                 void *workspace, size_t workspace_bytes, cudaStream_t stream) {
@@ -684,12 +817,24 @@ int fh_helmholtz1d_solve_large_fused_c128(const fh_problem1d *prob_host, double 
     HelmRows src;
     int rc = helm_rows_from(prob_host, k, k2, 0, prob_host->n_elem + 1, src);
     if (rc != FH_OK) return rc;
-    return solve_large_any(src, reinterpret_cast<cplx *>(u), src.n, status, workspace, workspace_bytes,
-                           static_cast<cudaStream_t>(stream));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DeepPlan dp;
+    DeepConsts *cs = nullptr;
+    if (deep_plan(src, workspace, workspace_bytes, dp, cs)) {  // uniform mesh: the periodic recursion
+        if (status != nullptr) FH_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
+        const UniformRows ur = as_uniform(src);
+        deep_solve_small_kernel<<<1, kDeepThreads, 0, st>>>(ur, dp, cs, reinterpret_cast<cplx *>(u), status);
+        FH_LAUNCH_CHECK("deep_solve_small_kernel");
+        return deep_backsub_big_levels(ur, dp, cs, reinterpret_cast<cplx *>(u), status, st);
+    }
+    return solve_large_any(src, reinterpret_cast<cplx *>(u), src.n, status, workspace, workspace_bytes, st);
 }
 
 // ---- multi-GPU SPIKE pieces: every rank owns the contiguous rows [row_begin, row_begin + n_rows) ------------
-size_t fh_spike_workspace_bytes(int64_t n_rows) { return fh::plan_levels(n_rows, 2).total; }
+size_t fh_spike_workspace_bytes(int64_t n_rows) {
+    const size_t a = fh::plan_levels(n_rows, 2).total, b = fh::deep_workspace_bytes(n_rows);
+    return a > b ? a : b;
+}
 
 int fh_spike_reduce_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c128 *du, const fh_c128 *b, int64_t n_rows,
                          int open_first, int open_last, void *workspace, size_t workspace_bytes, fh_c128 *iface8,
@@ -736,6 +881,13 @@ int fh_helmholtz1d_spike_reduce_c128(const fh_problem1d *prob_host, double k, do
         return FH_E_WORKSPACE;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DeepPlan dp;
+    DeepConsts *cs = nullptr;
+    if (deep_plan(src, workspace, workspace_bytes, dp, cs)) {  // uniform mesh: the periodic recursion, one launch
+        deep_reduce_kernel<<<1, kDeepThreads, 0, st>>>(as_uniform(src), dp, cs, reinterpret_cast<cplx *>(iface8));
+        FH_LAUNCH_CHECK("deep_reduce_kernel");
+        return FH_OK;
+    }
     rc = reduce_all(src, pl, workspace, 1, 1, st);  // generated rows carry exact zeros at the mesh ends
     if (rc != FH_OK) return rc;
     const LevelPtrs top = level_ptrs(workspace, pl, pl.levels);
@@ -796,6 +948,15 @@ int fh_helmholtz1d_spike_backsub_c128(const fh_problem1d *prob_host, double k, d
     const LevelPlan pl = plan_levels(n_rows, 2);
     FH_REQUIRE(workspace_bytes >= pl.total && pl.levels > 0, "workspace too small: need %zu bytes", pl.total);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DeepPlan dp;
+    DeepConsts *cs = nullptr;
+    if (deep_plan(src, workspace, workspace_bytes, dp, cs)) {  // (the same decision as in the reduce call)
+        const UniformRows ur = as_uniform(src);
+        deep_backsub_small_kernel<<<1, kDeepThreads, 0, st>>>(ur, dp, cs, reinterpret_cast<const cplx *>(x_first_last),
+                                                              reinterpret_cast<cplx *>(u), status);
+        FH_LAUNCH_CHECK("deep_backsub_small_kernel");
+        return deep_backsub_big_levels(ur, dp, cs, reinterpret_cast<cplx *>(u), status, st);
+    }
     rc = spike_seed_top(pl, workspace, x_first_last, st);
     if (rc != FH_OK) return rc;
     return backsub_all(src, pl, workspace, 1, 1, reinterpret_cast<cplx *>(u), status, st);

@@ -79,6 +79,38 @@ def test_helmholtz_large_mesh_staged_and_fused(N, k):
     assert rel_err(u_f, ex) < max(1e-10, 100 * rel_err(ref, ex)), (rel_err(u_f, ex), rel_err(ref, ex))
 
 
+def _solve_large_fused_direct(N, k, **bc):
+    """fh_helmholtz1d_solve_large_fused_c128 called directly (solve_helmholtz_sweep only routes n > 4112 to it)."""
+    import ctypes as C
+    lib = fh._lib.require_cuda()
+    prob = fh.fem1d._problem(N, 1.0 / N, 0.0, bc.get("bc_left", "neumann"), bc.get("bc_right", "sommerfeld"),
+                             bc.get("g_left", 1.0), bc.get("g_right", 0.0), None)
+    ws_bytes = lib.fh_tridiag_solve_large_workspace_bytes(N + 1)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device="cuda")
+    u = torch.empty(N + 1, dtype=torch.complex128, device="cuda")
+    status = torch.ones(1, dtype=torch.int32, device="cuda")
+    check(lib.fh_helmholtz1d_solve_large_fused_c128(C.byref(prob), float(k), float(k**2), ptr(u), ptr(status), ptr(ws),
+                                                    ws_bytes, stream_ptr()), "fh_helmholtz1d_solve_large_fused_c128")
+    assert int(status[0]) == 0
+    return _np(u)
+
+
+@pytest.mark.parametrize("N", [2, 3, 15, 16, 17, 31, 32, 33, 255, 256, 257, 1023, 1024, 1025, 1040, 2048, 4111, 4112,
+                               16 * 1024, 16 * 1024 + 1, 8 * 16384 - 1, 8 * 16384 + 16, 131089, 1024 * 1024 + 1])
+def test_periodic_recursion_ragged_sizes(N):
+    """Generated rows on a uniform mesh: every level of the recursion is 2-periodic apart from <= 2 special chunks; sizes
+    that put the ragged end of a level in every position (short last chunk, merged 17-row chunk, merged 1025-row tile,
+    levels of 2, 3, 4 rows), down to a 3-node mesh."""
+    for k, bc in ((40.0, {}), (3.0, dict(bc_left="dirichlet", bc_right="dirichlet", g_left=1.0, g_right=0.5)),
+                  (150.0, dict(bc_left="dirichlet", g_left=2.0))):
+        if k * (1.0 / N) > 1.5:
+            k = 1.0 * N  # stay on a resolvable wavenumber for the tiny meshes
+        u = _solve_large_fused_direct(N, k, **bc)
+        bands = banded1d.assemble_bands(N, k, 1.0 / N, **bc)
+        be, _ = banded1d.residual_metrics(*bands, u)
+        assert be < 1e-13, (N, k, bc, be)
+
+
 def _emulated_ranks_fused(N, k, world):
     """The per-rank sequence of distributed.solve_partitioned, ranks run one after the other on one GPU."""
     n = N + 1
