@@ -58,6 +58,7 @@ _SIGNATURES = {
     "fh_tridiag_solve_large_c128": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, _P, _P, C.c_size_t, _P]),
     "fh_helmholtz1d_solve_large_fused_c128": (C.c_int, [C.POINTER(Problem1d), C.c_double, C.c_double, _P, _P, _P,
                                                         C.c_size_t, _P]),
+    "fh_helmholtz1d_solve_large_fused_kdev_c128": (C.c_int, [C.POINTER(Problem1d), _P, _P, _P, _P, C.c_size_t, _P]),
     "fh_spike_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "fh_spike_reduce_c128": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, _P, C.c_size_t, _P, _P]),
     "fh_helmholtz1d_spike_reduce_c128": (C.c_int, [C.POINTER(Problem1d), C.c_double, C.c_double, C.c_int64,
@@ -67,6 +68,10 @@ _SIGNATURES = {
                                         _P]),
     "fh_helmholtz1d_spike_backsub_c128": (C.c_int, [C.POINTER(Problem1d), C.c_double, C.c_double, C.c_int64,
                                                     C.c_int64, _P, C.c_size_t, _P, _P, _P, _P]),
+    "fh_helmholtz1d_spike_reduce_kdev_c128": (C.c_int, [C.POINTER(Problem1d), _P, C.c_int64, C.c_int64, _P, C.c_size_t,
+                                                        _P, _P]),
+    "fh_helmholtz1d_spike_backsub_kdev_c128": (C.c_int, [C.POINTER(Problem1d), _P, C.c_int64, C.c_int64, _P, C.c_size_t,
+                                                         _P, _P, _P, _P]),
     "fh_q4_element_matrices_c128": (C.c_int, [_P, _P, C.c_int64, C.c_double, _P, _P, _P, _P]),
     "fh_q4_edge_geometry": (C.c_int, [_P, _P, _P, C.c_int64, C.c_double, _P, _P, _P]),
     "fh_q4_robin_edge_matrices_c128": (C.c_int, [_P, _P, C.c_int64, C.c_double, C.c_double, _P, _P, C.c_int, _P, _P]),

@@ -86,6 +86,7 @@ struct GlobalBands {  // rows of a level stored in global memory
 struct HelmRows {  // level-0 rows generated from the Helmholtz problem: local row j <-> mesh row g_off + j
     Problem1d p;
     double k, k2;
+    const double *kk = nullptr;  // device-resident (k, k**2): the periodic recursion only (see UniformRows)
     int64_t g_off, n;
     __device__ __forceinline__ void fill(LargeSmem &sm, int64_t row0, int rows) const {
         // scalar-h (the reference's mode): every interior row is the same -- evaluate it once per thread
@@ -222,7 +223,11 @@ large_backsub_kernel(Source src, const cplx *__restrict__ xr, cplx *__restrict__
 struct UniformRows {  // what HelmRows provides
     Problem1d p;
     double k, k2;
+    const double *kk;  // != NULL: (k, k**2) are read from device memory when the kernel starts (CUDA-graph replays)
     int64_t g_off, n;
+    __device__ __forceinline__ void fetch_k() {
+        if (kk != nullptr) k = kk[0], k2 = kk[1];
+    }
     __device__ __forceinline__ void interior(cplx &lo, cplx &di, cplx &hi, cplx &rhs) const {
         row_values(p, row_geom(p, 1), 1, k, k2, lo, di, hi, rhs);
     }
@@ -497,6 +502,7 @@ __device__ void deep_backsub_small_levels(const UniformRows &u, const DeepPlan &
 __global__ void __launch_bounds__(kDeepThreads)
 deep_reduce_kernel(UniformRows u, const __grid_constant__ DeepPlan dp, DeepConsts *cs, cplx *__restrict__ iface8) {
     __shared__ DeepStage sg;
+    u.fetch_k();
     deep_reduce_levels(u, dp, cs, sg);
     if (threadIdx.x < 8) iface8[threadIdx.x] = dp.ptr[dp.levels].a[threadIdx.x];
 }
@@ -505,6 +511,7 @@ __global__ void __launch_bounds__(kDeepThreads)
 deep_backsub_small_kernel(UniformRows u, const __grid_constant__ DeepPlan dp, const DeepConsts *cs,
                           const cplx *__restrict__ x_first_last, cplx *__restrict__ u_out, int32_t *__restrict__ status) {
     __shared__ DeepStage sg;
+    u.fetch_k();
     if (threadIdx.x < 2) dp.ptr[dp.levels].x[threadIdx.x] = x_first_last[threadIdx.x];
     __syncthreads();
     deep_backsub_small_levels(u, dp, cs, sg, u_out, status);
@@ -514,6 +521,7 @@ __global__ void __launch_bounds__(kDeepThreads)
 deep_solve_small_kernel(UniformRows u, const __grid_constant__ DeepPlan dp, DeepConsts *cs, cplx *__restrict__ u_out,
                         int32_t *__restrict__ status) {
     __shared__ DeepStage sg;
+    u.fetch_k();
     deep_reduce_levels(u, dp, cs, sg);
     if (threadIdx.x == 0) {  // [b0 c0; a1 b1] x = [d0; d1]  (a0 and c1 are the exact zeros of the mesh ends)
         const LevelPtrs &p = dp.ptr[dp.levels];
@@ -533,13 +541,53 @@ deep_solve_small_kernel(UniformRows u, const __grid_constant__ DeepPlan dp, Deep
     __syncthreads();
     deep_backsub_small_levels(u, dp, cs, sg, u_out, status);
 }
+// The streaming part of one LARGE level.  The end values of 128 chunks (256 consecutive entries of xr, 4 KB) arrive by
+// one cp.async per thread, kDeepStages rounds ahead of their use, so the kernel is a pure store stream: with the loads
+// issued by the consuming threads themselves (deep_backsub_plain) every round paid an L2 / DRAM round trip -- under
+// write load a long one -- before its 32 KB of stores could go out (measured: 4.3 TB/s on the 2.1 GB of N = 2^27).
+constexpr int kDeepStages = 4;
+struct DeepRing {
+    cplx buf[kDeepStages][2 * 128];
+};
+__device__ __forceinline__ bool deep_backsub_plain_staged(const DeepConsts &C, int64_t c_begin, int64_t c_end,
+                                                          const cplx *__restrict__ xr, cplx *__restrict__ x,
+                                                          DeepRing &ring) {
+    const int t = threadIdx.x, i = t & (kLM - 1), cl = t >> 4;
+    const cplx al = C.tab[0][i], be = C.tab[1][i], ga = C.tab[2][i];
+    const int64_t rounds = (c_end - c_begin + 127) / 128;
+    auto fetch = [&](int64_t r) {  // (an empty group keeps the group count in step with the rounds)
+        const int64_t e = 2 * (c_begin + r * 128) + t;
+        if (r < rounds && e < 2 * c_end) cp_async16(&ring.buf[r % kDeepStages][t], xr + e);
+        cp_async_commit();
+    };
+    for (int r = 0; r < kDeepStages - 1; ++r) fetch(r);
+    bool bad = false;
+    for (int64_t r = 0; r < rounds; ++r) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(kDeepStages - 2) : "memory");  // this thread's share of round r
+        __syncthreads();  // everybody's share has landed, and everybody is done with round r - 1 ...
+        fetch(r + kDeepStages - 1);  // ... whose buffer is refilled
+        const cplx *b = ring.buf[r % kDeepStages];
+        const int64_t c0 = c_begin + r * 128 + cl;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int64_t c = c0 + 16 * q;
+            if (c < c_end) {
+                const cplx xi = cmadd(cmadd(ga, al, b[2 * (cl + 16 * q)]), be, b[2 * (cl + 16 * q) + 1]);
+                bad |= !cfinite(xi);
+                stg_stream(x + c * kLM + i, xi);
+            }
+        }
+    }
+    return bad;
+}
+
 // one large level: CTA 0 takes the special chunks, every other CTA streams `per` contiguous rounds of plain chunks
-// (measured on one slab of config 4, level 0 = 268 MB: capping the registers for 3 or 4 resident CTAs costs more than it
-// buys -- 150 / 205 us per slab against 105 --, and contiguous ranges beat a round-robin over the rounds)
 __global__ void __launch_bounds__(kDeepThreads)
 deep_backsub_level_kernel(UniformRows u, const __grid_constant__ DeepPlan dp, const DeepConsts *cs, int l, int64_t per,
                           cplx *__restrict__ u_out, int32_t *__restrict__ status) {
     __shared__ DeepStage sg;
+    __shared__ DeepRing ring;
+    u.fetch_k();
     const DeepLevel &L = dp.lv[l];
     const cplx *xr = deep_xr(dp, l);
     cplx *x = deep_x(dp, l, u_out);
@@ -552,7 +600,7 @@ deep_backsub_level_kernel(UniformRows u, const __grid_constant__ DeepPlan dp, co
         const int64_t b = blockIdx.x - 1;
         int64_t c_end = L.clo + (b + 1) * per * 128;
         if (c_end > L.chi) c_end = L.chi;
-        bad = deep_backsub_plain(cs[l], L.clo + b * per * 128, c_end, xr, x);
+        bad = deep_backsub_plain_staged(cs[l], L.clo + b * per * 128, c_end, xr, x, ring);
     }
     if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0 && status != nullptr) atomicOr(status, 1);
 }
@@ -660,7 +708,7 @@ static int launch_backsub(const Source &src, const cplx *xr, cplx *x, int32_t *s
 static bool uniform_rows(const HelmRows &src) { return src.p.h_mode == FH_H_SCALAR && src.p.n_elem >= 2; }
 static UniformRows as_uniform(const HelmRows &src) {
     UniformRows u;
-    u.p = src.p, u.k = src.k, u.k2 = src.k2, u.g_off = src.g_off, u.n = src.n;
+    u.p = src.p, u.k = src.k, u.k2 = src.k2, u.kk = src.kk, u.g_off = src.g_off, u.n = src.n;
     return u;
 }
 // the per-level constants live behind the level arrays of the workspace
@@ -789,6 +837,11 @@ static int helm_rows_from(const fh_problem1d *prob_host, double k, double k2, in
     src.k = k, src.k2 = k2, src.g_off = row_begin, src.n = n_rows;
     return FH_OK;
 }
+static int kdev_unsupported() {
+    set_error("a device-resident wavenumber needs a uniform mesh (scalar h, >= 2 elements) and a workspace of "
+              "fh_spike_workspace_bytes / fh_tridiag_solve_large_workspace_bytes");
+    return FH_E_UNSUPPORTED;
+}
 
 }  // namespace fh
 
@@ -809,14 +862,15 @@ int fh_tridiag_solve_large_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c1
                        static_cast<cudaStream_t>(stream));
 }
 
-int fh_helmholtz1d_solve_large_fused_c128(const fh_problem1d *prob_host, double k, double k2, fh_c128 *u,
-                                          int32_t *status, void *workspace, size_t workspace_bytes,
-                                          fh_stream_t stream) {
+// kk != NULL: (k, k**2) live in device memory (uniform meshes only: the periodic recursion)
+static int helm_solve_large_fused(const fh_problem1d *prob_host, double k, double k2, const double *kk, fh_c128 *u,
+                                  int32_t *status, void *workspace, size_t workspace_bytes, fh_stream_t stream) {
     using namespace fh;
     FH_REQUIRE(prob_host != nullptr && u != nullptr, "NULL pointer");
     HelmRows src;
     int rc = helm_rows_from(prob_host, k, k2, 0, prob_host->n_elem + 1, src);
     if (rc != FH_OK) return rc;
+    src.kk = kk;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     DeepPlan dp;
     DeepConsts *cs = nullptr;
@@ -827,7 +881,19 @@ int fh_helmholtz1d_solve_large_fused_c128(const fh_problem1d *prob_host, double 
         FH_LAUNCH_CHECK("deep_solve_small_kernel");
         return deep_backsub_big_levels(ur, dp, cs, reinterpret_cast<cplx *>(u), status, st);
     }
+    if (kk != nullptr) return kdev_unsupported();
     return solve_large_any(src, reinterpret_cast<cplx *>(u), src.n, status, workspace, workspace_bytes, st);
+}
+int fh_helmholtz1d_solve_large_fused_c128(const fh_problem1d *prob_host, double k, double k2, fh_c128 *u,
+                                          int32_t *status, void *workspace, size_t workspace_bytes,
+                                          fh_stream_t stream) {
+    return helm_solve_large_fused(prob_host, k, k2, nullptr, u, status, workspace, workspace_bytes, stream);
+}
+int fh_helmholtz1d_solve_large_fused_kdev_c128(const fh_problem1d *prob_host, const double *k_k2_dev, fh_c128 *u,
+                                               int32_t *status, void *workspace, size_t workspace_bytes,
+                                               fh_stream_t stream) {
+    FH_REQUIRE(k_k2_dev != nullptr, "NULL pointer");
+    return helm_solve_large_fused(prob_host, 0.0, 0.0, k_k2_dev, u, status, workspace, workspace_bytes, stream);
 }
 
 // ---- multi-GPU SPIKE pieces: every rank owns the contiguous rows [row_begin, row_begin + n_rows) ------------
@@ -866,15 +932,16 @@ int fh_spike_reduce_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c128 *du,
     return FH_OK;
 }
 
-int fh_helmholtz1d_spike_reduce_c128(const fh_problem1d *prob_host, double k, double k2, int64_t row_begin,
-                                     int64_t n_rows, void *workspace, size_t workspace_bytes, fh_c128 *iface8,
-                                     fh_stream_t stream) {
+static int helm_spike_reduce(const fh_problem1d *prob_host, double k, double k2, const double *kk, int64_t row_begin,
+                             int64_t n_rows, void *workspace, size_t workspace_bytes, fh_c128 *iface8,
+                             fh_stream_t stream) {
     using namespace fh;
     FH_REQUIRE(prob_host != nullptr && iface8 != nullptr, "NULL pointer");
     FH_REQUIRE(n_rows > 2, "a generated slab needs more than 2 rows");
     HelmRows src;
     int rc = helm_rows_from(prob_host, k, k2, row_begin, n_rows, src);
     if (rc != FH_OK) return rc;
+    src.kk = kk;
     const LevelPlan pl = plan_levels(n_rows, 2);
     if (workspace_bytes < pl.total || !workspace) {
         set_error("workspace too small: need %zu bytes", pl.total);
@@ -888,11 +955,24 @@ int fh_helmholtz1d_spike_reduce_c128(const fh_problem1d *prob_host, double k, do
         FH_LAUNCH_CHECK("deep_reduce_kernel");
         return FH_OK;
     }
+    if (kk != nullptr) return kdev_unsupported();
     rc = reduce_all(src, pl, workspace, 1, 1, st);  // generated rows carry exact zeros at the mesh ends
     if (rc != FH_OK) return rc;
     const LevelPtrs top = level_ptrs(workspace, pl, pl.levels);
     FH_CUDA(cudaMemcpyAsync(iface8, top.a, 8 * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
     return FH_OK;
+}
+int fh_helmholtz1d_spike_reduce_c128(const fh_problem1d *prob_host, double k, double k2, int64_t row_begin,
+                                     int64_t n_rows, void *workspace, size_t workspace_bytes, fh_c128 *iface8,
+                                     fh_stream_t stream) {
+    return helm_spike_reduce(prob_host, k, k2, nullptr, row_begin, n_rows, workspace, workspace_bytes, iface8, stream);
+}
+int fh_helmholtz1d_spike_reduce_kdev_c128(const fh_problem1d *prob_host, const double *k_k2_dev, int64_t row_begin,
+                                          int64_t n_rows, void *workspace, size_t workspace_bytes, fh_c128 *iface8,
+                                          fh_stream_t stream) {
+    FH_REQUIRE(k_k2_dev != nullptr, "NULL pointer");
+    return helm_spike_reduce(prob_host, 0.0, 0.0, k_k2_dev, row_begin, n_rows, workspace, workspace_bytes, iface8,
+                             stream);
 }
 
 int fh_spike_solve_interface_c128(const fh_c128 *iface_all, int n_ranks, fh_c128 *x_iface, int32_t *status,
@@ -937,14 +1017,15 @@ int fh_spike_backsub_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c128 *du
     return backsub_all(src, pl, workspace, open_first, open_last, reinterpret_cast<cplx *>(u), status, st);
 }
 
-int fh_helmholtz1d_spike_backsub_c128(const fh_problem1d *prob_host, double k, double k2, int64_t row_begin,
-                                      int64_t n_rows, void *workspace, size_t workspace_bytes,
-                                      const fh_c128 *x_first_last, fh_c128 *u, int32_t *status, fh_stream_t stream) {
+static int helm_spike_backsub(const fh_problem1d *prob_host, double k, double k2, const double *kk, int64_t row_begin,
+                              int64_t n_rows, void *workspace, size_t workspace_bytes, const fh_c128 *x_first_last,
+                              fh_c128 *u, int32_t *status, fh_stream_t stream) {
     using namespace fh;
     FH_REQUIRE(prob_host && x_first_last && u, "NULL pointer");
     HelmRows src;
     int rc = helm_rows_from(prob_host, k, k2, row_begin, n_rows, src);
     if (rc != FH_OK) return rc;
+    src.kk = kk;
     const LevelPlan pl = plan_levels(n_rows, 2);
     FH_REQUIRE(workspace_bytes >= pl.total && pl.levels > 0, "workspace too small: need %zu bytes", pl.total);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -957,9 +1038,24 @@ int fh_helmholtz1d_spike_backsub_c128(const fh_problem1d *prob_host, double k, d
         FH_LAUNCH_CHECK("deep_backsub_small_kernel");
         return deep_backsub_big_levels(ur, dp, cs, reinterpret_cast<cplx *>(u), status, st);
     }
+    if (kk != nullptr) return kdev_unsupported();
     rc = spike_seed_top(pl, workspace, x_first_last, st);
     if (rc != FH_OK) return rc;
     return backsub_all(src, pl, workspace, 1, 1, reinterpret_cast<cplx *>(u), status, st);
+}
+int fh_helmholtz1d_spike_backsub_c128(const fh_problem1d *prob_host, double k, double k2, int64_t row_begin,
+                                      int64_t n_rows, void *workspace, size_t workspace_bytes,
+                                      const fh_c128 *x_first_last, fh_c128 *u, int32_t *status, fh_stream_t stream) {
+    return helm_spike_backsub(prob_host, k, k2, nullptr, row_begin, n_rows, workspace, workspace_bytes, x_first_last, u,
+                              status, stream);
+}
+int fh_helmholtz1d_spike_backsub_kdev_c128(const fh_problem1d *prob_host, const double *k_k2_dev, int64_t row_begin,
+                                           int64_t n_rows, void *workspace, size_t workspace_bytes,
+                                           const fh_c128 *x_first_last, fh_c128 *u, int32_t *status,
+                                           fh_stream_t stream) {
+    FH_REQUIRE(k_k2_dev != nullptr, "NULL pointer");
+    return helm_spike_backsub(prob_host, 0.0, 0.0, k_k2_dev, row_begin, n_rows, workspace, workspace_bytes, x_first_last,
+                              u, status, stream);
 }
 
 }  // extern "C"

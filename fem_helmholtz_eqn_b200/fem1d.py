@@ -424,18 +424,23 @@ class LargeMeshPlan:
     work is 0.15 GB -- tens of microseconds of HBM time -- and the path is bound by its nine dependent kernel launches
     (assembly, three reduction levels, the coarse cluster solve, three back-substitution levels).  The plan owns the
     buffers and a captured CUDA graph of the whole sequence; ``solve(k)`` updates (k, k**2) in device memory and
-    replays it.  Results are bit-identical to ``solve_helmholtz_sweep(N, [k])``."""
+    replays it.  Results are bit-identical to ``solve_helmholtz_sweep(N, [k])``.
+
+    ``fused=True``: A is never stored -- the rows are generated (``solve_helmholtz_sweep(..., fused=True)``); on the
+    reference's uniform mesh that is the periodic recursion of fh_tridiag_large.cu: one single-CTA kernel plus one
+    streaming launch per large level, 16 B written per node."""
 
     def __init__(self, N, L=1.0, theta=0.0, *, bc_left="neumann", bc_right="sommerfeld", g_left=1.0, g_right=0.0,
-                 use_graph=True):
+                 use_graph=True, fused=False):
         lib = _lib.require_cuda()
-        self.N, self.n, self.L = int(N), int(N) + 1, float(L)
+        self.N, self.n, self.L, self.fused = int(N), int(N) + 1, float(L), bool(fused)
         dev = _lib.device()
         self.k_dev = torch.zeros(2, dtype=torch.float64, device=dev)
-        self.bands = torch.empty((4, 1, self.n), dtype=torch.complex128, device=dev)
+        self.bands = None if fused else torch.empty((4, 1, self.n), dtype=torch.complex128, device=dev)
         self.U = torch.empty((1, self.n), dtype=torch.complex128, device=dev)
         self.status = torch.zeros(1, dtype=torch.int32, device=dev)
-        ws_bytes = lib.fh_tridiag_solve_batched_workspace_bytes(self.n, 1)
+        ws_bytes = (lib.fh_tridiag_solve_large_workspace_bytes(self.n) if fused
+                    else lib.fh_tridiag_solve_batched_workspace_bytes(self.n, 1))
         self.ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
         self._prob = _problem(N, L / N, theta, bc_left, bc_right, g_left, g_right, None)
         self.graph = None
@@ -460,6 +465,12 @@ class LargeMeshPlan:
 
     def _launch(self):
         lib, B = _lib.load(), self.bands
+        if self.fused:
+            check(lib.fh_helmholtz1d_solve_large_fused_kdev_c128(C.byref(self._prob), ptr(self.k_dev), ptr(self.U),
+                                                                 ptr(self.status), ptr(self.ws), self.ws.numel(),
+                                                                 stream_ptr()),
+                  "fh_helmholtz1d_solve_large_fused_kdev_c128")
+            return
         check(lib.fh_assemble_1d_c128(C.byref(self._prob), ptr(self.k_dev[0:1]), ptr(self.k_dev[1:2]), 1, ptr(B[0]),
                                       ptr(B[1]), ptr(B[2]), ptr(B[3]), stream_ptr()), "fh_assemble_1d_c128")
         check(lib.fh_tridiag_solve_batched_c128(ptr(B[0]), ptr(B[1]), ptr(B[2]), ptr(B[3]), ptr(self.U), self.n, 1,

@@ -130,6 +130,13 @@ FH_API int fh_helmholtz1d_solve_large_fused_c128(const fh_problem1d *prob_host, 
                                           int32_t *status, void *workspace, size_t workspace_bytes,
                                           fh_stream_t stream);
 
+/* ... and with the wavenumber in device memory (k_k2_dev = device fp64[2] = {k, k**2}, read when the kernels run), so
+ * that a captured CUDA graph of the call can be replayed for another k.  Uniform meshes only (FH_E_UNSUPPORTED
+ * otherwise).  The reference's sweep loop nb:300-317 / nb:469-471 on one long mesh. */
+FH_API int fh_helmholtz1d_solve_large_fused_kdev_c128(const fh_problem1d *prob_host, const double *k_k2_dev, fh_c128 *u,
+                                               int32_t *status, void *workspace, size_t workspace_bytes,
+                                               fh_stream_t stream);
+
 /* ---- multi-GPU SPIKE-style partitioned solve (single mesh split into contiguous slabs, one per rank) ------
  * Per rank:  1. *_spike_reduce   : slab [row_begin, row_begin+n_rows) -> its 2 interface rows,
  *                                  iface8 = device complex128[4][2] = (dl, d, du, b) x (first row, last row);
@@ -156,6 +163,17 @@ FH_API int fh_helmholtz1d_spike_backsub_c128(const fh_problem1d *prob_host, doub
                                       int64_t n_rows, void *workspace, size_t workspace_bytes,
                                       const fh_c128 *x_first_last, fh_c128 *u, int32_t *status,
                                       fh_stream_t stream);
+
+/* Steps 1 and 4 on generated rows with the wavenumber in device memory (see fh_helmholtz1d_solve_large_fused_kdev_c128):
+ * the whole reduce -> all-gather -> interface solve -> back-substitution sequence can be captured once as a CUDA graph
+ * and replayed per wavenumber. */
+FH_API int fh_helmholtz1d_spike_reduce_kdev_c128(const fh_problem1d *prob_host, const double *k_k2_dev, int64_t row_begin,
+                                          int64_t n_rows, void *workspace, size_t workspace_bytes, fh_c128 *iface8,
+                                          fh_stream_t stream);
+FH_API int fh_helmholtz1d_spike_backsub_kdev_c128(const fh_problem1d *prob_host, const double *k_k2_dev,
+                                           int64_t row_begin, int64_t n_rows, void *workspace,
+                                           size_t workspace_bytes, const fh_c128 *x_first_last, fh_c128 *u,
+                                           int32_t *status, fh_stream_t stream);
 
 /* ---- residual / parity metrics on device -------------------------------------------------------
  * out[s] = { ||b - A u||_2^2, ||u||_2^2, ||b||_2^2, ||A||_inf } for each system s (device fp64[batch][4]). */

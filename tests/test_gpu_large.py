@@ -214,6 +214,12 @@ def test_nccl_partitioned_two_gpus(tmp_path):
         "bands = banded1d.assemble_bands(N, k, 1.0 / N)\n"
         "be = banded1d.residual_metrics(*bands, u.cpu().numpy())[0]\n"
         "assert be < 1e-14, be\n"
+        "plan = D.PartitionedPlan(N)\n"
+        "for kk in (1000.0, 37.5):\n"
+        "    b, e, ul = plan.solve(kk)\n"
+        "    b2, e2, ref = D.solve_partitioned(N, kk)\n"
+        "    assert (b, e) == (b2, e2) and torch.equal(ul, ref) and not plan.singular(), kk\n"
+        "print('rank', r, 'plan graph', plan.graph is not None)\n"
         "lo, hi, U = D.sweep_sharded(4096, np.linspace(1, 1000, 64))\n"
         "assert U.shape == (32, 4097)\n"
         "dist.destroy_process_group(); print('rank', r, 'ok', be)\n")
@@ -242,6 +248,29 @@ def test_large_mesh_plan_replays_a_cuda_graph_bit_identically():
     assert banded1d.residual_metrics(*bands, u)[0] < 1e-15
     eager = fh.fem1d.LargeMeshPlan(N, use_graph=False)
     assert torch.equal(eager.solve(10.0), plan.solve(10.0))
+
+
+def test_fused_plans_replay_a_cuda_graph_with_the_wavenumber_in_device_memory():
+    """LargeMeshPlan(fused=True) and distributed.PartitionedPlan (one rank): the *_kdev entry points read (k, k**2)
+    from device memory, so one captured graph serves every wavenumber -- same bits as the by-value calls."""
+    N = 300_017
+    plan = fh.fem1d.LargeMeshPlan(N, fused=True)
+    part = fh_dist.PartitionedPlan(N)
+    assert plan.graph is not None and part.graph is not None
+    for k in (10.0, 1000.0, 37.25):
+        u = plan.solve(k).clone()
+        _, U = fh.solve_helmholtz_sweep(N, [k], fused=True)
+        assert torch.equal(u, U[0])
+        begin, end, up = part.solve(k)
+        _, _, ref = fh_dist.solve_partitioned(N, k)
+        assert (begin, end) == (0, N + 1) and torch.equal(up, ref) and not part.singular()
+        bands = banded1d.assemble_bands(N, k, 1.0 / N)
+        assert banded1d.residual_metrics(*bands, _np(u))[0] < 1e-14
+        assert banded1d.residual_metrics(*bands, _np(up))[0] < 1e-14
+    # Dirichlet rows, eager path
+    eager = fh.fem1d.LargeMeshPlan(N, fused=True, use_graph=False, bc_left="dirichlet", bc_right="dirichlet", g_right=0.5)
+    bands = banded1d.assemble_bands(N, 20.0, 1.0 / N, bc_left="dirichlet", bc_right="dirichlet", g_right=0.5)
+    assert banded1d.residual_metrics(*bands, _np(eager.solve(20.0)))[0] < 1e-14
 
 
 def test_large_mesh_plan_back_to_back_solves_do_not_race():

@@ -65,6 +65,12 @@ def main():
             out[name + "_graph"] = {"assemble_plus_solve_ms_cold_l2": med_g, "min_ms": min_g, "warm_l2_ms": warm_g,
                                     "dof_per_s": (N + 1) / (med_g * 1e-3)}
             del plan
+            plan_f = fh.fem1d.LargeMeshPlan(N, fused=True)   # A never stored: the periodic recursion on generated rows
+            med_fg, min_fg = timed(lambda: plan_f.solve(k), flush=flush)
+            warm_fg, _ = timed(lambda: plan_f.solve(k), reps=20)
+            out[name + "_fused_graph"] = {"solve_ms_cold_l2": med_fg, "min_ms": min_fg, "warm_l2_ms": warm_fg,
+                                          "dof_per_s": (N + 1) / (med_fg * 1e-3)}
+            del plan_f
             out[name] = {"assemble_ms": med_a, "solve_large_ms": med_s, "solve_large_min_ms": min_s,
                          "fused_ms": med_f, "fused_min_ms": min_f,
                          "staged_dof_per_s": (N + 1) / ((med_a + med_s) * 1e-3), "fused_dof_per_s": (N + 1) / (med_f * 1e-3)}
@@ -81,6 +87,12 @@ def main():
         med_b, _ = timed(lambda: ops.backsub(x[0:2]), reps=5)
         out["c4_one_slab_of_8"] = {"rows": e0 - b0, "reduce_ms": med_r, "backsub_ms": med_b,
                                    "dof_per_s_per_gpu": (e0 - b0) / ((med_r + med_b) * 1e-3)}
+        del ops
+        plan = D.PartitionedPlan(N)                           # the whole mesh on one GPU, graph replay
+        med_p, min_p = timed(lambda: plan.solve(k), reps=10)
+        out["c4_whole_mesh_one_gpu_plan"] = {"rows": n, "graph": plan.graph is not None, "median_ms": med_p,
+                                             "min_ms": min_p, "dof_per_s": n / (med_p * 1e-3),
+                                             "write_gbs": 16 * n / (med_p * 1e-3) / 1e9}
     else:
         import torch.distributed as dist
         def run():
@@ -99,7 +111,29 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
             ts.append(float(dt.item()))
         out["c4_partitioned"] = {"ranks": world, "median_ms": float(np.median(ts)) * 1e3,
-                                 "dof_per_s": n / float(np.median(ts))}
+                                 "dof_per_s": n / float(np.median(ts)), "timing": "host wall clock, call by call"}
+        # the same through PartitionedPlan (buffers kept, k in device memory, one CUDA graph per rank): device time by
+        # CUDA events, max over ranks
+        plan = D.PartitionedPlan(N)
+        for name, use in (("c4_partitioned_plan", plan),):
+            use.solve(k)
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(10):
+                dist.barrier()
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                use.solve(k)
+                b.record()
+                torch.cuda.synchronize()
+                dt = torch.tensor([a.elapsed_time(b)], device="cuda")
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+                ts.append(float(dt.item()))
+            out[name] = {"ranks": world, "graph": use.graph is not None, "median_ms": float(np.median(ts)),
+                         "min_ms": float(np.min(ts)), "dof_per_s": n / (float(np.median(ts)) * 1e-3),
+                         "write_gbs_per_gpu": 16 * n / world / (float(np.median(ts)) * 1e-3) / 1e9,
+                         "singular": use.singular(), "timing": "CUDA events, max over ranks"}
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(out))
