@@ -101,9 +101,13 @@ class PartitionedPlan:
     and the sequence  reduce -> all-gather (128 B per rank, NCCL) -> interface solve -> back-substitution  is captured
     once as a CUDA graph: ``solve(k)`` costs one 16-byte copy and one graph launch per rank instead of a dozen host
     calls (at 2^24 rows per GPU the device work is ~0.1 ms -- less than issuing it call by call takes).
-    Results are bit-identical to ``solve_partitioned(N, k)``.  Uniform meshes (the reference's only mode)."""
+    Results are bit-identical to ``solve_partitioned(N, k)``.  Uniform meshes (the reference's only mode).
 
-    def __init__(self, N, L=1.0, theta=0.0, *, group=None, use_graph=True, **bc):
+    With more than one rank the graph holds NCCL kernels: it is opt-in there (``use_graph=True``; measured on 2 x B200:
+    0.32 ms against 0.35 ms call by call at N = 2^27), and :meth:`close` must run before
+    ``dist.destroy_process_group()`` -- tearing the communicator down under a live graph blocks."""
+
+    def __init__(self, N, L=1.0, theta=0.0, *, group=None, use_graph=None, **bc):
         self.lib = _lib.require_cuda()
         self.N, self.n, self.L, self.group = int(N), int(N) + 1, float(L), group
         self.world, self.rank = _world(group)
@@ -123,6 +127,8 @@ class PartitionedPlan:
         self.status = torch.zeros(2, dtype=torch.int32, device=dev)
         self.u = torch.empty(self.n_rows, dtype=torch.complex128, device=dev)
         self.graph = None
+        if use_graph is None:                # default: graph on one rank; with a collective inside it is opt-in
+            use_graph = self.world == 1
         self._set_k(1.0)
         self._launch()                       # warm-up: module load, NCCL communicator, driver entry points
         torch.cuda.synchronize()
@@ -175,6 +181,19 @@ class PartitionedPlan:
 
     def singular(self):
         return bool(torch.any(self.status != 0).item())
+
+    def close(self):
+        """Drop the captured graph (required before the process group is destroyed when it holds a collective)."""
+        if self.graph is not None:
+            torch.cuda.synchronize()
+            self.graph.reset()
+            self.graph = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown
+            pass
 
 
 def solve_partitioned(N, k, L=1.0, theta=0.0, *, group=None, ops=None, gather=False, **bc):

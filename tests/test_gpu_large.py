@@ -214,12 +214,12 @@ def test_nccl_partitioned_two_gpus(tmp_path):
         "bands = banded1d.assemble_bands(N, k, 1.0 / N)\n"
         "be = banded1d.residual_metrics(*bands, u.cpu().numpy())[0]\n"
         "assert be < 1e-14, be\n"
-        "plan = D.PartitionedPlan(N)\n"
+        "plan = D.PartitionedPlan(N)  # (more than one rank: call by call unless use_graph=True)\n"
         "for kk in (1000.0, 37.5):\n"
         "    b, e, ul = plan.solve(kk)\n"
         "    b2, e2, ref = D.solve_partitioned(N, kk)\n"
         "    assert (b, e) == (b2, e2) and torch.equal(ul, ref) and not plan.singular(), kk\n"
-        "print('rank', r, 'plan graph', plan.graph is not None)\n"
+        "plan.close()\n"
         "lo, hi, U = D.sweep_sharded(4096, np.linspace(1, 1000, 64))\n"
         "assert U.shape == (32, 4097)\n"
         "dist.destroy_process_group(); print('rank', r, 'ok', be)\n")
@@ -227,7 +227,7 @@ def test_nccl_partitioned_two_gpus(tmp_path):
     env = dict(os.environ, FH_ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", "29731", str(script)], env=env,
-                         capture_output=True, text=True, timeout=600)
+                         capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
 
 

@@ -114,7 +114,7 @@ def main():
                                  "dof_per_s": n / float(np.median(ts)), "timing": "host wall clock, call by call"}
         # the same through PartitionedPlan (buffers kept, k in device memory, one CUDA graph per rank): device time by
         # CUDA events, max over ranks
-        plan = D.PartitionedPlan(N)
+        plan = D.PartitionedPlan(N, use_graph=True)
         for name, use in (("c4_partitioned_plan", plan),):
             use.solve(k)
             torch.cuda.synchronize()
@@ -134,6 +134,7 @@ def main():
                          "min_ms": float(np.min(ts)), "dof_per_s": n / (float(np.median(ts)) * 1e-3),
                          "write_gbs_per_gpu": 16 * n / world / (float(np.median(ts)) * 1e-3) / 1e9,
                          "singular": use.singular(), "timing": "CUDA events, max over ranks"}
+        plan.close()
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(out))
