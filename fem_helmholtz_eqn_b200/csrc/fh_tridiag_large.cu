@@ -719,14 +719,12 @@ static size_t deep_workspace_bytes(int64_t n) {
 // Geometry of the recursion for the rows [g_off, g_off + n) of a mesh with n_elem elements: which rows / chunks of every
 // level are plain.  Only the last chunk of a level can be irregular (short, or 17 rows after a merge), and a chunk is
 // plain when it has 16 rows, all of them plain.  false: not applicable (the caller takes the generic kernels).
-static bool deep_plan(const HelmRows &src, void *ws, size_t ws_bytes, DeepPlan &dp, DeepConsts *&cs) {
-    if (!uniform_rows(src) || ws == nullptr) return false;
-    const LevelPlan pl = plan_levels(src.n, 2);
-    if (pl.levels < 1 || pl.n[pl.levels] != 2 || ws_bytes < deep_workspace_bytes(src.n)) return false;
+static bool deep_geometry(int64_t g_off, int64_t n, int64_t n_elem, const LevelPlan &pl, DeepPlan &dp) {
+    if (pl.levels < 1 || pl.n[pl.levels] != 2) return false;
     memset(&dp, 0, sizeof(dp));
     dp.levels = pl.levels;
-    int64_t plo = src.g_off == 0 ? 1 : 0;                                     // mesh row 0 has its own coefficients
-    int64_t phi = src.n - (src.g_off + src.n - 1 == src.p.n_elem ? 1 : 0);    // ... and so has mesh row N
+    int64_t plo = g_off == 0 ? 1 : 0;                         // mesh row 0 has its own coefficients
+    int64_t phi = n - (g_off + n - 1 == n_elem ? 1 : 0);      // ... and so has mesh row N
     for (int l = 0; l <= pl.levels; ++l) {
         DeepLevel &L = dp.lv[l];
         L.n = pl.n[l];
@@ -743,8 +741,14 @@ static bool deep_plan(const HelmRows &src, void *ws, size_t ws_bytes, DeepPlan &
         L.clo = clo, L.chi = chi;
         if (l < pl.levels && clo + (L.chunks - chi) > kDeepSpecialMax) return false;
         plo = 2 * clo, phi = 2 * chi;
-        if (l >= 1) dp.ptr[l] = level_ptrs(ws, pl, l);
     }
+    return true;
+}
+static bool deep_plan(const HelmRows &src, void *ws, size_t ws_bytes, DeepPlan &dp, DeepConsts *&cs) {
+    if (!uniform_rows(src) || ws == nullptr) return false;
+    const LevelPlan pl = plan_levels(src.n, 2);
+    if (ws_bytes < deep_workspace_bytes(src.n) || !deep_geometry(src.g_off, src.n, src.p.n_elem, pl, dp)) return false;
+    for (int l = 1; l <= pl.levels; ++l) dp.ptr[l] = level_ptrs(ws, pl, l);
     cs = reinterpret_cast<DeepConsts *>(static_cast<char *>(ws) + deep_consts_offset(pl));
     return true;
 }
@@ -848,6 +852,24 @@ static int kdev_unsupported() {
 extern "C" {
 
 size_t fh_tridiag_solve_large_workspace_bytes(int64_t n) { return fh::solve_large_workspace_bytes(n); }
+
+int fh_large_uniform_plan(int64_t n_elem, int64_t row_begin, int64_t n_rows, int64_t *out6, int max_levels) {
+    using namespace fh;
+    FH_REQUIRE(out6 != nullptr && n_elem >= 2 && row_begin >= 0 && n_rows > 2 && row_begin + n_rows <= n_elem + 1,
+               "bad row range or NULL output");
+    DeepPlan dp;
+    if (!deep_geometry(row_begin, n_rows, n_elem, plan_levels(n_rows, 2), dp)) {
+        set_error("the periodic recursion does not apply to this row range");
+        return FH_E_UNSUPPORTED;
+    }
+    FH_REQUIRE(max_levels > dp.levels, "out6 holds %d levels, the plan has %d", max_levels, dp.levels + 1);
+    for (int l = 0; l <= dp.levels; ++l) {
+        const DeepLevel &L = dp.lv[l];
+        int64_t *o = out6 + 6 * l;
+        o[0] = L.n, o[1] = L.chunks, o[2] = L.plo, o[3] = L.phi, o[4] = L.clo, o[5] = L.chi;
+    }
+    return dp.levels + 1;
+}
 
 int fh_tridiag_solve_large_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c128 *du, const fh_c128 *b, fh_c128 *u,
                                 int64_t n, int32_t *status, void *workspace, size_t workspace_bytes,

@@ -130,6 +130,13 @@ FH_API int fh_helmholtz1d_solve_large_fused_c128(const fh_problem1d *prob_host, 
                                           int32_t *status, void *workspace, size_t workspace_bytes,
                                           fh_stream_t stream);
 
+/* Host-side planning of that solver on a uniform mesh (no device work; what the CPU tests check against a brute-force
+ * model): for the rows [row_begin, row_begin + n_rows) of a mesh with n_elem elements, level l of the recursion has
+ * out6[6 l ..] = { rows, chunks, first plain row, end of the plain rows, first plain chunk, end of the plain chunks }
+ * ("plain" rows alternate between two constant rows; everything else is a "special" chunk).  Returns the number of
+ * levels written (the last one has 2 rows), or FH_E_UNSUPPORTED / FH_E_INVALID (negative). */
+FH_API int fh_large_uniform_plan(int64_t n_elem, int64_t row_begin, int64_t n_rows, int64_t *out6, int max_levels);
+
 /* ... and with the wavenumber in device memory (k_k2_dev = device fp64[2] = {k, k**2}, read when the kernels run), so
  * that a captured CUDA graph of the call can be replayed for another k.  Uniform meshes only (FH_E_UNSUPPORTED
  * otherwise).  The reference's sweep loop nb:300-317 / nb:469-471 on one long mesh. */
