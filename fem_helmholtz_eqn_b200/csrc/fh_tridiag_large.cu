@@ -286,7 +286,8 @@ struct LevelPtrs {
 };
 
 constexpr int kDeepThreads = 256;
-constexpr int kDeepSpecialMax = 7;        // special chunks per level the kernels accept (there are at most two)
+constexpr int kDeepSpecialMax = 2;        // special chunks per level: one at the front, one at the back (tests/test_large_plan_cpu.py)
+constexpr int kDeepSmallLevelsMax = 8;    // levels the single-CTA back-substitution stages at once (2^14 rows down to 4: five)
 constexpr int64_t kDeepSmall = 1 << 14;   // levels up to this many rows are back-substituted inside the single-CTA kernel
 
 struct DeepLevel {
@@ -308,15 +309,29 @@ __device__ __forceinline__ int deep_special_count(const DeepLevel &L) { return (
 __device__ __forceinline__ int64_t deep_special_chunk(const DeepLevel &L, int s) {
     return s < L.clo ? (int64_t)s : L.chi + (s - L.clo);
 }
-// row r of level l
-__device__ __forceinline__ void deep_row(const UniformRows &u, const DeepPlan &dp, const DeepConsts *cs, int l, int64_t r,
-                                         cplx &a, cplx &b, cplx &c, cplx &d) {
+// What one level of the single-CTA reduction hands to the next, kept in shared memory (no global round trip between
+// levels): the level's two constant rows and its special rows -- the interface rows (first, last) of the special chunks
+// of the level above, in order.
+struct DeepCarry {
+    cplx eo[2][4];
+    cplx spec[2 * kDeepSpecialMax][4];
+};
+// row r of level l; carry != NULL: the level's constants and special rows come from shared memory
+__device__ __forceinline__ void deep_row(const UniformRows &u, const DeepPlan &dp, const DeepConsts *cs,
+                                         const DeepCarry *carry, int l, int64_t r, cplx &a, cplx &b, cplx &c, cplx &d) {
     const DeepLevel &L = dp.lv[l];
+    const cplx(*eo)[4] = carry != nullptr ? carry->eo : cs[l].eo;
     if (r >= L.plo && r < L.phi) {
-        const cplx *e = cs[l].eo[r & 1];
+        const cplx *e = eo[r & 1];
         a = e[0], b = e[1], c = e[2], d = e[3];
     } else if (l == 0) {
-        u.row(u.g_off + r, cs[0].eo[0], a, b, c, d);
+        u.row(u.g_off + r, eo[0], a, b, c, d);
+    } else if (carry != nullptr) {
+        const DeepLevel &P = dp.lv[l - 1];  // row r is an interface row of chunk r / 2 of the level above
+        const int64_t pc = r >> 1;
+        const int ps = (int)(pc < P.clo ? pc : P.clo + (pc - P.chi));
+        const cplx *e = carry->spec[2 * ps + (int)(r & 1)];
+        a = e[0], b = e[1], c = e[2], d = e[3];
     } else {
         const LevelPtrs &p = dp.ptr[l];
         a = p.a[r], b = p.b[r], c = p.c[r], d = p.d[r];
@@ -330,24 +345,27 @@ struct DeepStage {
 };
 // All threads: the rows of the special chunks of level l -- and, with_plain, of a plain chunk as entry number ns -- go to
 // shared memory with every load in flight at once (inside the sweeps each row would cost a dependent L2 round trip).
-__device__ __forceinline__ void deep_stage(const UniformRows &u, const DeepPlan &dp, const DeepConsts *cs, int l,
-                                           bool with_plain, DeepStage &sg) {
+// first_thread: the thread that takes entry 0 (several levels staged back to back use different threads).
+__device__ __forceinline__ void deep_stage(const UniformRows &u, const DeepPlan &dp, const DeepConsts *cs,
+                                           const DeepCarry *carry, int l, bool with_plain, DeepStage &sg,
+                                           int first_thread = 0) {
     const DeepLevel &L = dp.lv[l];
     const int ns = deep_special_count(L);
     const int total = (ns + (with_plain ? 1 : 0)) * (kLM + 1);
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int nt = (int)blockDim.x;
+    for (int idx = ((int)threadIdx.x + nt - first_thread % nt) % nt; idx < total; idx += nt) {
         const int s = idx / (kLM + 1), i = idx - s * (kLM + 1);
         cplx a, b, c, d;
         if (s == ns) {
             if (i == 0) sg.len[s] = kLM;
             if (i >= kLM) continue;
-            const cplx *e = cs[l].eo[i & 1];
+            const cplx *e = carry != nullptr ? carry->eo[i & 1] : cs[l].eo[i & 1];
             a = e[0], b = e[1], c = e[2], d = e[3];
         } else {
             const ChunkPos cp = chunk_pos(L.n, tile_count(L.n), deep_special_chunk(L, s));
             if (i == 0) sg.len[s] = cp.len;
             if (i >= cp.len) continue;
-            deep_row(u, dp, cs, l, cp.r0 + i, a, b, c, d);
+            deep_row(u, dp, cs, carry, l, cp.r0 + i, a, b, c, d);
         }
         sg.rows[s][i][0] = a, sg.rows[s][i][1] = b, sg.rows[s][i][2] = c, sg.rows[s][i][3] = d;
     }
@@ -356,18 +374,21 @@ __device__ __forceinline__ void deep_stage(const UniformRows &u, const DeepPlan 
 // All reductions, level 0 down to the 2-row level, by ONE CTA.  Warp 0 runs the downward sweeps (lane s < ns: special
 // chunk s, lane ns: the plain chunk), warp 1 the upward sweeps, lane 0 of warp 2 the symbolic Thomas sweep.
 // cs: per-level constants in global memory (visible to the whole CTA after each level's barrier).
-__device__ void deep_reduce_levels(const UniformRows &u, const DeepPlan &dp, DeepConsts *cs, DeepStage &sg) {
+__device__ void deep_reduce_levels(const UniformRows &u, const DeepPlan &dp, DeepConsts *cs, DeepStage &sg,
+                                   DeepCarry carry[2]) {
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     if (t == 0) {
         cplx in[4];
         u.interior(in[0], in[1], in[2], in[3]);
-        for (int q = 0; q < 4; ++q) cs[0].eo[0][q] = cs[0].eo[1][q] = in[q];
+        for (int q = 0; q < 4; ++q) cs[0].eo[0][q] = cs[0].eo[1][q] = carry[0].eo[0][q] = carry[0].eo[1][q] = in[q];
     }
     __syncthreads();
     for (int l = 0; l < dp.levels; ++l) {
         const DeepLevel &L = dp.lv[l];
         const int ns = deep_special_count(L);
-        deep_stage(u, dp, cs, l, true, sg);
+        const DeepCarry &now = carry[l & 1];
+        DeepCarry &next = carry[(l + 1) & 1];
+        deep_stage(u, dp, cs, &now, l, true, sg);
         __syncthreads();
         if (warp < 2 && lane <= ns) {
             cplx out[4];
@@ -375,12 +396,14 @@ __device__ void deep_reduce_levels(const UniformRows &u, const DeepPlan &dp, Dee
             auto rowfn = [&](int i, cplx &a, cplx &b, cplx &c, cplx &d) { a = R[i][0], b = R[i][1], c = R[i][2], d = R[i][3]; };
             if (warp == 0) reduce_chunk_down(rowfn, sg.len[lane], out);
             else reduce_chunk_up(rowfn, sg.len[lane], out);
+            const int which = warp == 0 ? 1 : 0;  // downward sweep -> the row in the LAST unknown
             if (lane == ns) {
-                for (int q = 0; q < 4; ++q) cs[l + 1].eo[warp == 0 ? 1 : 0][q] = out[q];
-            } else {
+                for (int q = 0; q < 4; ++q) cs[l + 1].eo[which][q] = next.eo[which][q] = out[q];
+            } else {  // (to global memory for the back-substitution, to shared memory for the next level)
                 const LevelPtrs &p = dp.ptr[l + 1];
-                const int64_t o = 2 * deep_special_chunk(L, lane) + (warp == 0 ? 1 : 0);
+                const int64_t o = 2 * deep_special_chunk(L, lane) + which;
                 p.a[o] = out[0], p.b[o] = out[1], p.c[o] = out[2], p.d[o] = out[3];
+                for (int q = 0; q < 4; ++q) next.spec[2 * lane + which][q] = out[q];
             }
         }
         if (t == 64) {  // x_i = alpha_i x_first + beta_i x_last + gamma_i for a plain chunk of this level
@@ -477,20 +500,27 @@ __device__ __forceinline__ bool deep_backsub_special(const DeepLevel &L, DeepSta
 __device__ __forceinline__ const cplx *deep_xr(const DeepPlan &dp, int l) { return dp.ptr[l + 1].x; }
 __device__ __forceinline__ cplx *deep_x(const DeepPlan &dp, int l, cplx *u_out) { return l == 0 ? u_out : dp.ptr[l].x; }
 
-// levels `levels - 1`, `levels - 2`, ... while they are small (<= kDeepSmall rows), by ONE CTA
-__device__ void deep_backsub_small_levels(const UniformRows &u, const DeepPlan &dp, const DeepConsts *cs, DeepStage &sg,
+// levels `levels - 1`, `levels - 2`, ... while they are small (<= kDeepSmall rows), by ONE CTA.  The special rows of all
+// of them are staged first (one round of L2 latency for the lot).
+struct DeepStageSet {
+    DeepStage lv[kDeepSmallLevelsMax];
+};
+__device__ void deep_backsub_small_levels(const UniformRows &u, const DeepPlan &dp, const DeepConsts *cs, DeepStageSet &set,
                                           cplx *u_out, int32_t *status) {
     bool bad = false;
-    for (int l = dp.levels - 1; l >= 0 && dp.lv[l].n <= kDeepSmall; --l) {
+    int j = 0;
+    for (int l = dp.levels - 1; l >= 0 && dp.lv[l].n <= kDeepSmall; --l, ++j)
+        deep_stage(u, dp, cs, nullptr, l, false, set.lv[j], 32 * j);
+    __syncthreads();
+    j = 0;
+    for (int l = dp.levels - 1; l >= 0 && dp.lv[l].n <= kDeepSmall; --l, ++j) {
         const DeepLevel &L = dp.lv[l];
         const cplx *xr = deep_xr(dp, l);
         cplx *x = deep_x(dp, l, u_out);
-        deep_stage(u, dp, cs, l, false, sg);
-        __syncthreads();
         // the special chunks go to lane 0 of the last warps, ahead of their share of the streaming part (the sweep is
         // the critical path of the level)
         const int w = (kDeepThreads >> 5) - 1 - (int)(threadIdx.x >> 5);
-        if (w < deep_special_count(L) && (threadIdx.x & 31) == 0) bad |= deep_backsub_special(L, sg, w, xr, x);
+        if (w < deep_special_count(L) && (threadIdx.x & 31) == 0) bad |= deep_backsub_special(L, set.lv[j], w, xr, x);
         __syncwarp();
         bad |= deep_backsub_plain(cs[l], L.clo, L.chi, xr, x);
         __syncthreads();
@@ -502,27 +532,30 @@ __device__ void deep_backsub_small_levels(const UniformRows &u, const DeepPlan &
 __global__ void __launch_bounds__(kDeepThreads)
 deep_reduce_kernel(UniformRows u, const __grid_constant__ DeepPlan dp, DeepConsts *cs, cplx *__restrict__ iface8) {
     __shared__ DeepStage sg;
+    __shared__ DeepCarry carry[2];
     u.fetch_k();
-    deep_reduce_levels(u, dp, cs, sg);
+    deep_reduce_levels(u, dp, cs, sg, carry);
     if (threadIdx.x < 8) iface8[threadIdx.x] = dp.ptr[dp.levels].a[threadIdx.x];
 }
 // multi-GPU piece 2: seed the 2-row level with the slab's end values, back-substitute the small levels
 __global__ void __launch_bounds__(kDeepThreads)
 deep_backsub_small_kernel(UniformRows u, const __grid_constant__ DeepPlan dp, const DeepConsts *cs,
                           const cplx *__restrict__ x_first_last, cplx *__restrict__ u_out, int32_t *__restrict__ status) {
-    __shared__ DeepStage sg;
+    __shared__ DeepStageSet set;
     u.fetch_k();
     if (threadIdx.x < 2) dp.ptr[dp.levels].x[threadIdx.x] = x_first_last[threadIdx.x];
     __syncthreads();
-    deep_backsub_small_levels(u, dp, cs, sg, u_out, status);
+    deep_backsub_small_levels(u, dp, cs, set, u_out, status);
 }
 // single GPU: both pieces in one kernel; the 2-row system in between is solved with partial pivoting
 __global__ void __launch_bounds__(kDeepThreads)
 deep_solve_small_kernel(UniformRows u, const __grid_constant__ DeepPlan dp, DeepConsts *cs, cplx *__restrict__ u_out,
                         int32_t *__restrict__ status) {
     __shared__ DeepStage sg;
+    __shared__ DeepCarry carry[2];
+    __shared__ DeepStageSet set;
     u.fetch_k();
-    deep_reduce_levels(u, dp, cs, sg);
+    deep_reduce_levels(u, dp, cs, sg, carry);
     if (threadIdx.x == 0) {  // [b0 c0; a1 b1] x = [d0; d1]  (a0 and c1 are the exact zeros of the mesh ends)
         const LevelPtrs &p = dp.ptr[dp.levels];
         cplx b0 = p.b[0], c0 = p.c[0], d0 = p.d[0], a1 = p.a[1], b1 = p.b[1], d1 = p.d[1];
@@ -539,7 +572,7 @@ deep_solve_small_kernel(UniformRows u, const __grid_constant__ DeepPlan dp, Deep
         if ((!cfinite(x0) || !cfinite(x1)) && status != nullptr) atomicOr(status, 1);
     }
     __syncthreads();
-    deep_backsub_small_levels(u, dp, cs, sg, u_out, status);
+    deep_backsub_small_levels(u, dp, cs, set, u_out, status);
 }
 // The streaming part of one LARGE level.  The end values of 128 chunks (256 consecutive entries of xr, 4 KB) arrive by
 // one cp.async per thread, kDeepStages rounds ahead of their use, so the kernel is a pure store stream: with the loads
@@ -593,7 +626,7 @@ deep_backsub_level_kernel(UniformRows u, const __grid_constant__ DeepPlan dp, co
     cplx *x = deep_x(dp, l, u_out);
     bool bad = false;
     if (blockIdx.x == 0) {
-        deep_stage(u, dp, cs, l, false, sg);
+        deep_stage(u, dp, cs, nullptr, l, false, sg);
         __syncthreads();
         if ((int)threadIdx.x < deep_special_count(L)) bad = deep_backsub_special(L, sg, threadIdx.x, xr, x);
     } else {
@@ -742,7 +775,9 @@ static bool deep_geometry(int64_t g_off, int64_t n, int64_t n_elem, const LevelP
         if (l < pl.levels && clo + (L.chunks - chi) > kDeepSpecialMax) return false;
         plo = 2 * clo, phi = 2 * chi;
     }
-    return true;
+    int small = 0;
+    for (int l = 0; l < pl.levels; ++l) small += dp.lv[l].n <= kDeepSmall ? 1 : 0;
+    return small <= kDeepSmallLevelsMax;
 }
 static bool deep_plan(const HelmRows &src, void *ws, size_t ws_bytes, DeepPlan &dp, DeepConsts *&cs) {
     if (!uniform_rows(src) || ws == nullptr) return false;
