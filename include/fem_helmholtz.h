@@ -79,7 +79,10 @@ FH_API int fh_boundary_matrices_1d(double k, double cos_theta, fh_c128 *Ne2, fh_
 
 /* ---- assembly (replaces nb:134-187 `assembly`): A = -K + k^2 M + S as tridiagonal bands ---------
  * ks / k2s: device fp64[n_k]; k2s[i] must be the caller's k**2 (nb:185 evaluates it on the host).
- * dl, d, du, b: device complex128[n_k][N+1].  Values are bit-identical to the reference's dense A. */
+ * dl, d, du, b: device complex128[n_k][N+1].  Values are bit-identical to the reference's dense A.
+ * The one call that takes scratch space on its own: on a non-uniform mesh (FH_H_NODAL) with n_k >= 8 the k-independent
+ * geometry of the rows (48 B per mesh row) is tabulated in stream-ordered memory (cudaMallocAsync / cudaFreeAsync on
+ * `stream`, released inside the call; the device's default pool is told to keep 64 MB across synchronisations). */
 FH_API int fh_assemble_1d_c128(const fh_problem1d *prob_host, const double *ks, const double *k2s,
                         int64_t n_k, fh_c128 *dl, fh_c128 *d, fh_c128 *du, fh_c128 *b,
                         fh_stream_t stream);
