@@ -90,3 +90,35 @@ def test_planner_rejects_bad_ranges():
     assert lib.fh_large_uniform_plan(100, 0, 2, p, 20) < 0       # a slab needs more than 2 rows
     assert lib.fh_large_uniform_plan(100, 50, 60, p, 20) < 0     # beyond the mesh
     assert lib.fh_large_uniform_plan(1 << 20, 0, 1 << 20, p, 2) < 0  # output too short
+
+
+@pytest.mark.parametrize("N,k", [(40, 7.0), (1040, 30.0), (4111, 100.0), (16384, 250.0), (131088, 1000.0), (300_017, 37.25)])
+def test_periodic_recursion_model_solves_the_reference_system(N, k):
+    """The algorithm itself, in numpy on the planner's geometry (tests/models/periodic_recursion_model.py): constants
+    chain, <= 2 special chunks per level, symbolic Thomas tables -> the solution LAPACK gives for the oracle's bands."""
+    from models import periodic_recursion_model as prm
+    from oracle import banded1d
+    for bc in (dict(), dict(bc_left="dirichlet", bc_right="dirichlet", g_left=1.0, g_right=0.5)):
+        dl, d, du, b = banded1d.assemble_bands(N, k, 1.0 / N, **bc)
+        plan = _plan(N, 0, N + 1)
+        u = prm.solve(plan, (dl[1], d[1], du[1], b[1]), (dl[0], d[0], du[0], b[0]), (dl[N], d[N], du[N], b[N]))
+        be, _ = banded1d.residual_metrics(dl, d, du, b, u)
+        assert be < 1e-13, (N, k, bc, be)
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_periodic_recursion_model_partitioned(world):
+    """The same per slab, glued by the 2P-row interface system (what distributed.solve_partitioned does over NCCL)."""
+    from models import periodic_recursion_model as prm
+    from models.recursive_partition_model import slab_ranges, spike_solve_interface
+    from oracle import banded1d
+    N, k = 100_003, 400.0
+    dl, d, du, b = banded1d.assemble_bands(N, k, 1.0 / N)
+    interior, row0, rowN = (dl[1], d[1], du[1], b[1]), (dl[0], d[0], du[0], b[0]), (dl[N], d[N], du[N], b[N])
+    parts = []
+    for begin, end in slab_ranges(N + 1, world):
+        plan = _plan(N, begin, end - begin)
+        parts.append(prm.reduce_slab(plan, interior, row0, rowN, has_row0=begin == 0, has_rowN=end == N + 1))
+    x = spike_solve_interface([iface for iface, _ in parts])
+    u = np.concatenate([backsub(x[2 * r:2 * r + 2]) for r, (_, backsub) in enumerate(parts)])
+    assert banded1d.residual_metrics(dl, d, du, b, u)[0] < 1e-13
