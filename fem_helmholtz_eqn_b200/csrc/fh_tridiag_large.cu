@@ -300,6 +300,7 @@ struct DeepPlan {  // host-computed geometry of the recursion + where the level 
     DeepLevel lv[kMaxLevels + 1];
     LevelPtrs ptr[kMaxLevels + 1];       // levels >= 1 (ptr[0] is unused: level-0 rows are generated, its x is the caller's)
 };
+static_assert(sizeof(UniformRows) + sizeof(DeepPlan) + 64 <= 4096, "the plan travels in kernel parameter space");
 struct DeepConsts {  // per level, written by the reduce kernel, read by the back-substitution
     cplx eo[2][4];        // E, O: (a, b, c, d)
     cplx tab[3][kLM];     // alpha, beta, gamma
