@@ -172,6 +172,77 @@ def workload_config(n_gpus):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def other_configs(world, rank, dev, dist):
+    """The BASELINE configs that are not the headline workload, timed after it (they are parity tests in tests/; this
+    only records how long they take on this box): configs 2 / 5 (N = 1e6, one GPU) through fem1d.LargeMeshPlan, and
+    config 4 (N = 2^27, k = 1000) through distributed.PartitionedPlan -- the whole mesh on one GPU, or one slab per
+    rank with a 128-byte NCCL all-gather.  CUDA events around solve(k), max over ranks, median of 10."""
+    import torch
+
+    from fem_helmholtz_eqn_b200 import distributed as D
+    from fem_helmholtz_eqn_b200 import fem1d
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timed(fn, reps=10, cold=False):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            if cold:
+                flush.zero_()  # evicts L2
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+            if dist is not None:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ts.append(float(t.item()))
+        return statistics.median(ts)
+
+    res = {}
+    if world == 1:
+        N = 1_000_000
+        for name, k in (("config2_N1e6_k10", 10.0), ("config5_N1e6_k1000_robin", 1000.0)):
+            staged, fused = fem1d.LargeMeshPlan(N), fem1d.LargeMeshPlan(N, fused=True)
+            ms_s, ms_f = timed(lambda: staged.solve(k), cold=True), timed(lambda: fused.solve(k), cold=True)
+            dev_mod = float((fused.solve(k).abs() - 1.0).abs().max().item())  # exact discrete solution: |u_j| = 1
+            res[name] = {"staged_assemble_plus_solve_ms": ms_s, "staged_dof_per_s": (N + 1) / (ms_s * 1e-3),
+                         "fused_ms": ms_f, "fused_dof_per_s": (N + 1) / (ms_f * 1e-3),
+                         "max_dev_from_unit_modulus": dev_mod, "l2": "flushed between repetitions",
+                         "api": "fem1d.LargeMeshPlan(N).solve(k): one CUDA graph replay per wavenumber"}
+            del staged, fused
+    N4, k4 = 2**27, 1000.0
+    entry = {"ranks": world, "rows": N4 + 1, "api": "distributed.PartitionedPlan(N).solve(k), rows generated",
+             "timing": "CUDA events around solve(k), max over ranks, median of 10"}
+    plan = D.PartitionedPlan(N4, use_graph=False)
+    ms = timed(lambda: plan.solve(k4))
+    dev_mod = (plan.solve(k4)[2].abs() - 1.0).abs().max().reshape(1).to(torch.float64)
+    if dist is not None:
+        dist.all_reduce(dev_mod, op=dist.ReduceOp.MAX)
+    entry.update({"call_by_call_ms": ms, "call_by_call_dof_per_s": (N4 + 1) / (ms * 1e-3),
+                  "max_dev_from_unit_modulus": float(dev_mod.item()), "singular": plan.singular()})
+    del plan
+    plan = D.PartitionedPlan(N4, use_graph=True)
+    try:
+        captured = torch.tensor([1.0 if plan.graph is not None else 0.0], device=dev)
+        if dist is not None:
+            dist.all_reduce(captured, op=dist.ReduceOp.MIN)
+        if float(captured.item()) > 0:
+            ms = timed(lambda: plan.solve(k4))
+            entry.update({"graph_ms": ms, "graph_dof_per_s": (N4 + 1) / (ms * 1e-3),
+                          "graph_write_gbs_per_gpu": 16 * (N4 + 1) / world / (ms * 1e-3) / 1e9})
+    finally:
+        plan.close()  # a live graph with NCCL kernels would block destroy_process_group
+    res["config4_N2^27_k1000"] = entry
+    return res
+
+
 def run_gpu(args):
     import ctypes as C
 
@@ -317,6 +388,12 @@ def run_gpu(args):
     (total_ms, e2e_s, fused_ms, sol_mean, asm_mean, refined_max, backward_max, one_pass_ms,
      one_pass_berr) = vals.tolist()
 
+    configs = None
+    if not args.no_configs:  # every rank takes part (config 4 holds a collective)
+        del U
+        torch.cuda.empty_cache()
+        configs = other_configs(world, rank, dev, dist)
+
     if rank == 0:
         dof_rank = n_k * n
         dof_all = dof_rank * world
@@ -358,6 +435,8 @@ def run_gpu(args):
             "gpu_launches": sum(2 + 4 for r in refined),
             "clocks": clocks.summary(),
         }
+        if configs is not None:
+            out["other_configs"] = configs
         if e2e:
             out["e2e"] = {"value": dof_all / e2e_s, "unit": "DOF/s", "h2d_bytes_per_step": e2e["h2d"],
                           "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": 1e3 * e2e_s, "steps": e2e["steps"],
@@ -386,6 +465,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the timings of BASELINE configs 2, 4 and 5")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
