@@ -308,6 +308,24 @@ def test_zero_pivot_is_resolved_by_the_pivoted_fallback():
     assert int(st[0]) & 1
 
 
+def test_breakdown_flag_on_a_verified_solution_is_cleared_without_the_pivoted_resolve():
+    """resolve_nonfinite: a system that carries the breakdown bit but whose (refined) solution verifiably is at LAPACK
+    quality is kept; a real breakdown in the same batch still goes through the pivoted kernel."""
+    N, ks = 512, [3.0, 40.0, 77.0]
+    dl, d, du, b = fh.assemble_bands(N, ks, 1.0 / N)
+    u, status = fh.solve_tridiagonal(dl, d, du, b)
+    assert int(status.abs().sum()) == 0
+    ref = u.clone()
+    status[1] = 3              # as if the probe had found a severe defect and the refinement step had run since
+    u[2] = float("nan")        # a real breakdown
+    status[2] = 1
+    m = fh.fem1d.resolve_nonfinite(dl, d, du, b, u, status)
+    assert m in (1, 2) and int(status.abs().sum()) == 0
+    if m == 1:                 # (the usual case: the backward error of system 1 is ~2e-16, under the acceptance bar)
+        assert torch.equal(u[1], ref[1])
+    assert rel_err(_np(u[1]), _np(ref[1])) < 1e-10 and rel_err(_np(u[2]), _np(ref[2])) < 1e-10
+
+
 @pytest.mark.parametrize("fused", [False, True])
 def test_host_sweep_repairs_breakdowns_and_flagged_systems(fused):
     """solve_helmholtz_sweep_host and the fused sweep keep the accuracy of the staged device path: systems the
