@@ -3,7 +3,7 @@
 above 1e-10, and does ONE refinement step bring them to LAPACK quality (the acceptance check of
 fem1d.resolve_nonfinite)?  No GPU.  ~1.5 ms per system: split the 65,536 systems of a shard over the cores.
 
-    python tools/scan_shards_model.py WORLD RANK [first] [last]        # rank RANK of a WORLD-rank job: ks[RANK::WORLD]
+    python tests/tools/scan_shards_model.py WORLD RANK [first] [last]        # rank RANK of a WORLD-rank job: ks[RANK::WORLD]
 
 Round-1 result (WORLD = 1, 2, 4, every rank): the only such wavenumbers sit at k = 806.84 (one resonance of the
 8-row / 2048-row partition); worst raw backward error 4.6e-8 (WORLD = 4, RANK = 1), 9.2e-9 (WORLD = 2, RANK = 0: the
@@ -15,11 +15,11 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from models.partition_pcr_model import solve  # noqa: E402
-from oracle import banded1d  # noqa: E402  (a development tool: not part of the product path)
+from oracle import banded1d  # noqa: E402  (test infrastructure: lives under tests/ because it uses the oracle)
 
 N, N_K = 4096, 65536
 world, rank = int(sys.argv[1]), int(sys.argv[2])
