@@ -228,17 +228,16 @@ def other_configs(world, rank, dev, dist):
     entry.update({"call_by_call_ms": ms, "call_by_call_dof_per_s": (N4 + 1) / (ms * 1e-3),
                   "max_dev_from_unit_modulus": float(dev_mod.item()), "singular": plan.singular()})
     del plan
-    plan = D.PartitionedPlan(N4, use_graph=True)
-    try:
-        captured = torch.tensor([1.0 if plan.graph is not None else 0.0], device=dev)
-        if dist is not None:
-            dist.all_reduce(captured, op=dist.ReduceOp.MIN)
-        if float(captured.item()) > 0:
-            ms = timed(lambda: plan.solve(k4))
-            entry.update({"graph_ms": ms, "graph_dof_per_s": (N4 + 1) / (ms * 1e-3),
-                          "graph_write_gbs_per_gpu": 16 * (N4 + 1) / world / (ms * 1e-3) / 1e9})
-    finally:
-        plan.close()  # a live graph with NCCL kernels would block destroy_process_group
+    if world == 1:  # one CUDA graph per solve (with more ranks the graph holds NCCL kernels: measured with
+        # tools/plan_probe.py -- 2 / 4 GPUs: 0.32 / 0.22 ms --, kept out of the bench run)
+        plan = D.PartitionedPlan(N4, use_graph=True)
+        try:
+            if plan.graph is not None:
+                ms = timed(lambda: plan.solve(k4))
+                entry.update({"graph_ms": ms, "graph_dof_per_s": (N4 + 1) / (ms * 1e-3),
+                              "graph_write_gbs_per_gpu": 16 * (N4 + 1) / (ms * 1e-3) / 1e9})
+        finally:
+            plan.close()
     res["config4_N2^27_k1000"] = entry
     return res
 
