@@ -107,13 +107,47 @@ def cpu_threads():
         return os.cpu_count() or 1
 
 
+_literal = None
+
+
+def literal_reference():
+    """The reference's OWN 1D code, if build() staged it under baseline/_ref (git-ignored, shipped with the snapshot):
+    code cell 2 of notebooks/1D_soln.ipynb exec'd unmodified (matplotlib stubbed -- only the plotting helpers touch it).
+    Returns its namespace, or None (then the oracle's line-by-line port oracle/ref1d.py stands in)."""
+    global _literal
+    if _literal is None:
+        _literal = False
+        path = os.path.join(ROOT, "baseline", "_ref", "notebooks", "1D_soln.ipynb")
+        try:
+            import types
+
+            import numpy as np
+            nb = json.load(open(path))
+            code = [c for c in nb["cells"] if c["cell_type"] == "code"]
+            ns = {"np": np, "plt": types.ModuleType("matplotlib.pyplot"), "__name__": "reference_nb"}
+            exec(compile("".join(code[1]["source"]), "1D_soln.ipynb#cell2", "exec"), ns)
+            _literal = ns
+        except Exception:
+            _literal = False
+    return _literal or None
+
+
+def cpu_reference_kind():
+    return "reference" if literal_reference() is not None else "port"
+
+
 def cpu_reference_step(ks_sample):
-    """The reference's own algorithm (dense assembly + np.linalg.solve, oracle/ref1d.py restates nb:134-205)
-    on a bounded sample of the sweep.  Returns seconds."""
-    from oracle import ref1d
+    """The reference's own algorithm (dense assembly + np.linalg.solve, nb:134-205) on a bounded sample of the sweep:
+    the literal notebook code when staged, else its restatement oracle/ref1d.py.  Returns seconds."""
+    ns = literal_reference()
+    if ns is not None:
+        solve = ns["solve_helmholtz_fem"]
+    else:
+        from oracle import ref1d
+        solve = ref1d.solve_helmholtz_fem
     t0 = time.perf_counter()
     for k in ks_sample:
-        ref1d.solve_helmholtz_fem(N_ELEM, float(k))
+        solve(N_ELEM, float(k))
     return time.perf_counter() - t0
 
 
@@ -154,7 +188,9 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "complex128",
         "data": "synthetic", "config": workload_config(args.gpus),
         "solves_per_s": args.steps * per_step / t,
-        "cpu_baseline": {"value": value, "unit": "DOF/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "DOF/s", "cores": threads, "kind": cpu_reference_kind(), "sample": sample,
+                         "code": ("baseline/_ref/notebooks/1D_soln.ipynb cell 2, exec'd unmodified" if literal_reference()
+                                  else "oracle/ref1d.py (line-by-line port; the notebook was not staged)")},
         "e2e": {"value": value, "unit": "DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -298,22 +334,26 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def repair():
-        # Breakdowns of the unpivoted kernels (a non-finite value, or a probe defect beyond what one refinement step is
-        # trusted to repair: about one wavenumber in 10^5 -- none in the 65,536 of one GPU, one in rank 0's share of
-        # the 2-GPU sweep) go through fem1d.resolve_nonfinite, as in fem1d.solve_tridiagonal: kept if the refined
-        # solution verifiably is at LAPACK quality, else re-solved with partial pivoting (one thread per system:
-        # ~5 ms for a 4,097-row system).  Reading how many there are is the step's one host synchronisation.
-        return fem1d.resolve_nonfinite(bands[0], bands[1], bands[2], bands[3], U, status)
+    # workspaces of the two stream-ordered safety nets, allocated once (nothing is allocated inside the timed region)
+    refine_ws = torch.empty(lib.fh_tridiag_refine_flagged_workspace_bytes(n, n_k, max(256, n_k // 8)),
+                            dtype=torch.uint8, device=dev)
+    repair_ws = torch.empty(lib.fh_tridiag_repair_flagged_workspace_bytes(n, n_k, 16), dtype=torch.uint8, device=dev)
+
+    def safety_nets():
+        # (1) systems whose unpivoted elimination met a small pivot (status bit 1, 2-3 % of the sweep) get one step of
+        # iterative refinement; (2) breakdowns (status bit 0: a non-finite value, or a probe defect beyond what one
+        # refinement step is trusted to repair -- about one wavenumber in 10^5) are verified on the device and re-solved
+        # with partial pivoting unless the refined solution is within 1e-13.  Both are device-driven and stream-ordered:
+        # no host round trip, no allocation; the counters are read after the timed region.
+        fem1d.refine_flagged(bands[0], bands[1], bands[2], bands[3], U, status, sync=False, ws=refine_ws)
+        fem1d.repair_flagged(bands[0], bands[1], bands[2], bands[3], U, status, sync=False, ws=repair_ws)
 
     for _ in range(args.warmup):
         assemble()
         solve()
-        fem1d.refine_flagged(bands[0], bands[1], bands[2], bands[3], U, status)
-        repair()
+        safety_nets()
     barrier()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
-    refined, resolved = [], []
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
         t_begin.record()
@@ -323,16 +363,13 @@ def run_gpu(args):
             ev[s][1].record()
             solve()
             ev[s][2].record()
-            # systems whose unpivoted elimination met a small pivot get one refinement step (part of the step);
-            # stream-ordered, no host round trip: how many there were is read after the timed region
-            fem1d.refine_flagged(bands[0], bands[1], bands[2], bands[3], U, status, sync=False)
-            resolved.append(repair())
+            safety_nets()
             ev[s][3].record()
         t_end.record()
         barrier()
-    flagged, done = (int(v) for v in fem1d._refine_workspace(n, n_k, dev)[:8].view(torch.int32).tolist())
-    assert flagged == done, "more systems flagged than the workspace sized during warm-up holds"
-    refined = [done] * args.steps
+    flagged, done = (int(v) for v in refine_ws[:8].view(torch.int32).tolist())
+    assert flagged == done, "more systems flagged than the refinement workspace holds"
+    repaired = fem1d.repair_counts(repair_ws)  # of the last step (every step sees the same wavenumbers)
     total_ms = t_begin.elapsed_time(t_end)
     asm_ms = [e[0].elapsed_time(e[1]) for e in ev]
     sol_ms = [e[1].elapsed_time(e[2]) for e in ev]
@@ -361,8 +398,7 @@ def run_gpu(args):
         check(lib.fh_helmholtz1d_sweep_assemble_solve_c128(C.byref(prob), ptr(ks_d), ptr(k2s_d), n_k, ptr(bands[0]),
                                                            ptr(bands[1]), ptr(bands[2]), ptr(bands[3]), ptr(U),
                                                            ptr(status), None, 0, stream_ptr()), "one-pass")
-        fem1d.refine_flagged(bands[0], bands[1], bands[2], bands[3], U, status, sync=False)
-        repair()
+        safety_nets()
 
     for _ in range(2):
         one_pass()
@@ -395,11 +431,12 @@ def run_gpu(args):
     # max over ranks
     vals = torch.tensor([total_ms, e2e["seconds"] if e2e else 0.0, fused_ms,
                          statistics.mean(sol_ms), statistics.mean(asm_ms), float(done), backward_max, one_pass_ms,
-                         one_pass_berr], dtype=torch.float64, device=dev)
+                         one_pass_berr, float(repaired["flagged"]), float(repaired["kept"]), float(repaired["resolved"])],
+                        dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
     (total_ms, e2e_s, fused_ms, sol_mean, asm_mean, refined_max, backward_max, one_pass_ms,
-     one_pass_berr) = vals.tolist()
+     one_pass_berr, brk_flagged, brk_kept, brk_resolved) = vals.tolist()
 
     configs = None
     if not args.no_configs:  # every rank takes part (config 4 holds a collective)
@@ -432,8 +469,10 @@ def run_gpu(args):
                          "launch_ms": sol_mean},
             "stages": {"assembly_ms": asm_mean, "solve_ms": sol_mean, "refine_ms": statistics.mean(ref_ms),
                        "solve_ms_per_step": [round(v, 3) for v in sol_ms],
-                       "refined_per_step": refined, "pivoted_resolves_per_step": resolved,
-                       "refined_systems_per_step_max_over_ranks": int(refined_max), "refined_systems_per_step": statistics.mean(refined),
+                       "refined_systems_per_step_max_over_ranks": int(refined_max),
+                       "breakdown_flags_per_step_max_over_ranks": int(brk_flagged),
+                       "breakdowns_kept_after_verification_max_over_ranks": int(brk_kept),
+                       "pivoted_resolves_per_step_max_over_ranks": int(brk_resolved),
                        "assembly_gbs": BYTES_ASSEMBLY * dof_rank / (asm_mean * 1e-3) / 1e9,
                        "assembly_frac": BYTES_ASSEMBLY * dof_rank / (asm_mean * 1e-3) / 1e9 / peak,
                        "staged_gbs": (BYTES_ASSEMBLY + BYTES_SOLVE) * dof_rank / (ms_per_step * 1e-3) / 1e9,
@@ -445,7 +484,9 @@ def run_gpu(args):
                          "what": "fh_helmholtz1d_sweep_assemble_solve_c128 + refinement: A is written (bit-identical "
                                  "bands) and the systems are solved in the same pass, A is never read back"},
             "parity": {"backward_error_max": backward_max, "bar": 1e-10},
-            "gpu_launches": sum(2 + 4 + (1 if m else 0) for m in resolved),
+            # per step: assembly, solve, 4 refinement kernels (compact, residual, correction solve, update), 2 repair
+            # kernels (compact, verify-or-pivot)
+            "gpu_launches": 8 * args.steps,
             "clocks": clocks.summary(),
         }
         if configs is not None:
@@ -459,7 +500,7 @@ def run_gpu(args):
             cpu_reference_step(ks_cpu[:1])  # warm the BLAS threads
             t = cpu_reference_step(ks_cpu)
             out["cpu_baseline"] = {
-                "value": len(ks_cpu) * n / t, "unit": "DOF/s", "cores": cpu_threads(), "kind": "port",
+                "value": len(ks_cpu) * n / t, "unit": "DOF/s", "cores": cpu_threads(), "kind": cpu_reference_kind(),
                 "sample": f"{len(ks_cpu)} of the {n_k} wavenumbers (k = first, middle, last) at N={N_ELEM}: the "
                           f"reference's dense assembly + np.linalg.solve (oracle/ref1d.py), {t:.1f} s",
                 "banded_zgtsv_dof_per_s_1thread": cpu_banded_rate()}

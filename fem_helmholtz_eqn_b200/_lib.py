@@ -93,6 +93,9 @@ _SIGNATURES = {
                                             _P, _P]),
     "fh_tridiag_solve_pivoted_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "fh_tridiag_solve_pivoted_c128": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, _P, C.c_size_t, _P]),
+    "fh_tridiag_repair_flagged_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int64]),
+    "fh_tridiag_repair_flagged_c128": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, C.c_double, _P, C.c_size_t,
+                                                 _P]),
     "fh_tridiag_residual_vector_c128": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, _P]),
     "fh_tridiag_refine_flagged_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64, C.c_int64]),
     "fh_tridiag_refine_flagged_c128": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, _P, C.c_size_t, _P]),

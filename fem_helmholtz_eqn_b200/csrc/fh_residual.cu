@@ -275,58 +275,274 @@ extern "C" int fh_tridiag_refine_flagged_c128(const fh_c128 *dl, const fh_c128 *
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Pivoted fallback.  The fast solvers are unpivoted; a system on which they produce a non-finite value (an
-// exactly vanishing leading minor, e.g. k*h = 2 on the first element) is re-solved here the way LAPACK zgtsv
-// does it: Gaussian elimination with partial pivoting between adjacent rows, one thread per system, serial in
-// n.  It only ever sees the handful of systems the status flags name, so its speed does not matter; what
-// matters is that numpy.linalg.LinAlgError is raised for genuinely singular systems only, as the reference does.
+// Pivoted fallback.  The fast solvers are unpivoted; a system on which they break down (an exactly vanishing
+// leading minor, e.g. k*h = 2 on the first element, or a resonance of the partition that refinement does not repair)
+// is re-solved here the way LAPACK zgtsv does it: Gaussian elimination with partial pivoting between adjacent rows.
+// That recurrence is serial in n, so the kernel is built around its dependent chain:
+//   * one CTA per system; the elimination runs from BOTH ends at once ("burn at both ends"): lane 0 of warp 0 sweeps
+//     rows 0 .. m downwards, lane 0 of warp 1 rows n-1 .. m+1 upwards (the reversed system is tridiagonal too, with the
+//     sub- and super-diagonal exchanged); the two sweeps meet in a 2 x 2 system for (x_m, x_{m+1}), solved with
+//     pivoting, and both lanes back-substitute outwards.  Half the chain length, no loss of robustness.
+//   * the other threads are the memory system of the two sweepers: rows arrive in shared-memory tiles by cp.async one
+//     tile ahead (coalesced 16-byte requests), so the sweepers never wait on a global load; the factor rows
+//     (1/pivot, u1, u2, rhs -- 64 B per row) leave by plain stores to a per-CTA workspace slot and come back through
+//     the same tiles for the back-substitution.
+// Per row the chain is  |p| compare -> 1/p -> multiplier -> new diagonal  (~110 cycles); n = 4097: ~0.16 ms per system
+// (the one-thread-per-system kernel of round 1 took 5 ms), any n (tiles stream: n = 1e6 takes ~40 ms).
+// What matters beyond speed is that numpy.linalg.LinAlgError is raised for genuinely singular systems only, as the
+// reference does (nb:204): a zero pivot after the interchange gives Inf -> NaN, reported in status.
 namespace fh {
-__global__ void pivoted_gtsv_kernel(const cplx *__restrict__ dl, const cplx *__restrict__ d, const cplx *__restrict__ du,
-                                    const cplx *__restrict__ b, cplx *__restrict__ u, int64_t n, int64_t batch,
-                                    cplx *__restrict__ work, int32_t *__restrict__ status) {
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= batch) return;
-    const cplx *L = dl + s * n, *D0 = d + s * n, *U0 = du + s * n, *B = b + s * n;
-    cplx *x = u + s * n;                 // right-hand side, then the solution
-    cplx *dd = work + (3 * s) * n;       // diagonal
-    cplx *u1 = dd + n, *u2 = u1 + n;     // first and second super-diagonal of the factor
-    for (int64_t i = 0; i < n; ++i) dd[i] = D0[i], u1[i] = i < n - 1 ? U0[i] : czero(), u2[i] = czero(), x[i] = B[i];
-    bool singular = false;
-    for (int64_t i = 0; i + 1 < n; ++i) {
-        const cplx sub = L[i + 1];
-        if (abs1c(dd[i]) >= abs1c(sub)) {  // no interchange
-            if (abs1c(dd[i]) == 0.0) { singular = true; break; }
-            const cplx m = sub * crecip(dd[i]);
-            dd[i + 1] = nmsub(dd[i + 1], m, u1[i]);
-            x[i + 1] = nmsub(x[i + 1], m, x[i]);
-        } else {                           // swap rows i and i+1
-            const cplx m = dd[i] * crecip(sub);
-            const cplx di1 = dd[i + 1], ui = u1[i], xi = x[i];
-            dd[i] = sub;
-            u1[i] = di1;
-            dd[i + 1] = nmsub(ui, m, di1);
-            if (i + 2 < n) {
-                u2[i] = u1[i + 1];
-                u1[i + 1] = -(m * u1[i + 1]);
+
+constexpr int kPivThreads = 256;
+constexpr int kPivTile = 128;  // rows per side and tile
+constexpr int kPivSlotsMax = 256;
+
+struct PivSmem {
+    cplx tile[2][2][kPivTile][4];  // [side][buffer][row][4 numbers]  (forward: lo, di, hi, rhs; backward: the factor row)
+    cplx mid[2][3];                // the two modified rows that meet in the middle: (diag, off-diagonal, rhs)
+    cplx xmid[2];                  // x_m, x_{m+1}
+    double red[4][kPivThreads / 32];
+    int flag;
+};
+
+// normwise backward error ingredients of one system, by the whole CTA (same arithmetic as residual_kernel)
+__device__ __forceinline__ void cta_residual(const cplx *dl, const cplx *d, const cplx *du, const cplx *b, const cplx *u,
+                                             int64_t n, double (*red)[kPivThreads / 32], double out[4]) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    double r2 = 0.0, u2 = 0.0, b2 = 0.0, amax = 0.0;
+    for (int64_t j = t; j < n; j += kPivThreads) {
+        const cplx uj = u[j], bj = ldg_stream(b + j), dj = ldg_stream(d + j);
+        cplx r = nmsub(bj, dj, uj);
+        double rowsum = hypot(dj.re, dj.im);
+        if (j > 0) {
+            const cplx lj = ldg_stream(dl + j);
+            r = nmsub(r, lj, u[j - 1]);
+            rowsum += hypot(lj.re, lj.im);
+        }
+        if (j < n - 1) {
+            const cplx hj = ldg_stream(du + j);
+            r = nmsub(r, hj, u[j + 1]);
+            rowsum += hypot(hj.re, hj.im);
+        }
+        r2 += r.re * r.re + r.im * r.im;
+        u2 += uj.re * uj.re + uj.im * uj.im;
+        b2 += bj.re * bj.re + bj.im * bj.im;
+        amax = fmax(amax, rowsum);
+    }
+    r2 = warp_sum(r2), u2 = warp_sum(u2), b2 = warp_sum(b2), amax = warp_max(amax);
+    __syncthreads();  // (red[] may still be read from a previous call)
+    if (lane == 0) red[0][warp] = r2, red[1][warp] = u2, red[2][warp] = b2, red[3][warp] = amax;
+    __syncthreads();
+    constexpr int nw = kPivThreads / 32;
+    double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+#pragma unroll
+    for (int w = 0; w < nw; ++w) v0 += red[0][w], v1 += red[1][w], v2 += red[2][w], v3 = fmax(v3, red[3][w]);
+    out[0] = v0, out[1] = v1, out[2] = v2, out[3] = v3;  // identical on every thread
+}
+
+// One system, one CTA.  L, D, U, B: the system's bands and right-hand side (global); x: the solution (global, may not
+// alias B); fac: workspace slot of n * 4 complex numbers.  Returns true (on every thread) if the system is singular to
+// working precision (a non-finite value in the solution).
+__device__ bool cta_pivoted_solve(const cplx *L, const cplx *D, const cplx *U, const cplx *B, cplx *x, int64_t n,
+                                  cplx *fac, PivSmem &sm) {
+    const int t = threadIdx.x;
+    if (n == 1) {
+        if (t == 0) {
+            const cplx v = B[0] * crecip(D[0]);
+            x[0] = v;
+            sm.flag = cfinite(v) ? 0 : 1;
+        }
+        __syncthreads();
+        const bool bad1 = sm.flag != 0;
+        __syncthreads();
+        return bad1;
+    }
+    // rows consumed by the two sweeps: top 0 .. m (m + 1 rows), bottom n-1 .. m+1 (mp + 1 rows); they eliminate
+    // x_0 .. x_{m-1} and x_{n-1} .. x_{m+2}
+    const int64_t m = (n - 2) / 2, mp = n - 2 - m;
+    const int64_t cnt[2] = {m + 1, mp + 1};
+    const int64_t tiles = ((cnt[0] > cnt[1] ? cnt[0] : cnt[1]) + kPivTile - 1) / kPivTile;
+    // side s, local row j <-> global row (s == 0 ? j : n - 1 - j); local "lo" couples to local row j - 1
+    auto load_tile = [&](int64_t it, int buf) {
+        for (int e = t; e < 2 * kPivTile; e += kPivThreads) {
+            const int s = e / kPivTile, r = e - s * kPivTile;
+            const int64_t j = it * kPivTile + r;
+            if (j < cnt[s]) {
+                const int64_t g = s == 0 ? j : n - 1 - j;
+                cp_async16(&sm.tile[s][buf][r][0], (s == 0 ? L : U) + g);
+                cp_async16(&sm.tile[s][buf][r][1], D + g);
+                cp_async16(&sm.tile[s][buf][r][2], (s == 0 ? U : L) + g);
+                cp_async16(&sm.tile[s][buf][r][3], B + g);
             }
-            x[i] = x[i + 1];
-            x[i + 1] = nmsub(xi, m, x[i + 1]);
+        }
+        cp_async_commit();
+    };
+    const bool sweeper = (t & 31) == 0 && t < 64;
+    const int side = t >> 5;  // (meaningful for the sweepers)
+    cplx dd = czero(), u1 = czero(), rr = czero();  // the sweeper's current row: dd x_j + u1 x_{j+1} = rr
+    load_tile(0, 0);
+    for (int64_t it = 0; it < tiles; ++it) {
+        const int buf = (int)(it & 1);
+        cp_async_wait_all();
+        __syncthreads();  // tile `it` has landed; everybody is done with the other buffer
+        if (it + 1 < tiles) load_tile(it + 1, buf ^ 1);
+        if (sweeper) {
+            const int64_t j0 = it * kPivTile;
+            int64_t j1 = j0 + kPivTile;
+            if (j1 > cnt[side]) j1 = cnt[side];
+            const cplx(*rows)[4] = sm.tile[side][buf];
+            cplx nlo = rows[0][0], ndi = rows[0][1], nhi = rows[0][2], nrh = rows[0][3];
+            for (int64_t j = j0; j < j1; ++j) {
+                const cplx lo = nlo, di = ndi, hi = nhi, rh = nrh;
+                if (j + 1 < j1) {  // the next row's reads are issued ahead of this row's dependent chain
+                    const int r = (int)(j + 1 - j0);
+                    nlo = rows[r][0], ndi = rows[r][1], nhi = rows[r][2], nrh = rows[r][3];
+                }
+                if (j == 0) {  // the first row of the sweep: nothing above it
+                    dd = di, u1 = hi, rr = rh;
+                    continue;
+                }
+                // eliminate x_{j-1} between the current row (dd, u1, 0 | rr) and the next one (lo, di, hi | rh):
+                // the row with the larger leading entry (LAPACK's cabs1) is the pivot row
+                const bool swap = abs1c(dd) < abs1c(lo);
+                const cplx p0 = swap ? lo : dd, p1 = swap ? di : u1, p2 = swap ? hi : czero(), pr = swap ? rh : rr;
+                const cplx o0 = swap ? dd : lo, o1 = swap ? u1 : di, o2 = swap ? czero() : hi, orr = swap ? rr : rh;
+                const cplx inv = frecip(p0);
+                const cplx mlt = o0 * inv;
+                cplx *f = fac + 4 * (side == 0 ? j - 1 : n - j);  // factor row of the eliminated unknown
+                f[0] = inv, f[1] = p1, f[2] = p2, f[3] = pr;
+                dd = nmsub(o1, mlt, p1);
+                u1 = nmsub(o2, mlt, p2);
+                rr = nmsub(orr, mlt, pr);
+            }
         }
     }
-    if (!singular && abs1c(dd[n - 1]) == 0.0) singular = true;
-    if (!singular) {
-        x[n - 1] = x[n - 1] * crecip(dd[n - 1]);
-        if (n > 1) x[n - 2] = nmsub(x[n - 2], u1[n - 2], x[n - 1]) * crecip(dd[n - 2]);
-        for (int64_t i = n - 3; i >= 0; --i)
-            x[i] = nmsub(nmsub(x[i], u1[i], x[i + 1]), u2[i], x[i + 2]) * crecip(dd[i]);
-        for (int64_t i = 0; i < n && !singular; ++i) singular = !cfinite(x[i]);
+    if (sweeper) sm.mid[side][0] = dd, sm.mid[side][1] = u1, sm.mid[side][2] = rr;
+    __syncthreads();
+    if (t == 0) {
+        // top:    a00 x_m + a01 x_{m+1} = r0      bottom (reversed): a11 x_{m+1} + a10 x_m = r1
+        cplx a00 = sm.mid[0][0], a01 = sm.mid[0][1], r0 = sm.mid[0][2];
+        cplx a11 = sm.mid[1][0], a10 = sm.mid[1][1], r1 = sm.mid[1][2];
+        cplx xm, xm1;
+        if (abs1c(a00) >= abs1c(a10)) {
+            const cplx inv = crecip(a00), w = a10 * inv;
+            xm1 = nmsub(r1, w, r0) * crecip(nmsub(a11, w, a01));
+            xm = nmsub(r0, a01, xm1) * inv;
+        } else {
+            const cplx inv = crecip(a10), w = a00 * inv;
+            xm1 = nmsub(r0, w, r1) * crecip(nmsub(a01, w, a11));
+            xm = nmsub(r1, a11, xm1) * inv;
+        }
+        sm.xmid[0] = xm, sm.xmid[1] = xm1;
+        x[m] = xm, x[m + 1] = xm1;
+        sm.flag = (cfinite(xm) && cfinite(xm1)) ? 0 : 1;
     }
-    if (status != nullptr) status[s] = singular ? 1 : 0;
+    __syncthreads();  // (also: the factor rows written by the sweepers are visible to the whole CTA)
+    // ---- back-substitution, outwards from the middle: local rows cnt - 2 .. 0 of each side ----
+    auto load_fac = [&](int64_t it, int buf) {
+        for (int e = t; e < 2 * kPivTile * 4; e += kPivThreads) {
+            const int s = e / (4 * kPivTile), q = e - s * 4 * kPivTile, r = q >> 2, c = q & 3;
+            const int64_t j = it * kPivTile + r;
+            if (j + 1 < cnt[s]) cp_async16(&sm.tile[s][buf][r][c], fac + 4 * (s == 0 ? j : n - 1 - j) + c);
+        }
+        cp_async_commit();
+    };
+    const int64_t ftiles = ((cnt[0] > cnt[1] ? cnt[0] : cnt[1]) - 1 + kPivTile - 1) / kPivTile;
+    cplx xa = czero(), xb = czero();  // the two unknowns beyond the current one (local j + 1, j + 2)
+    if (sweeper) xa = sm.xmid[side], xb = sm.xmid[side ^ 1];
+    bool bad = false;
+    if (ftiles > 0) load_fac(ftiles - 1, (int)((ftiles - 1) & 1));
+    for (int64_t it = ftiles - 1; it >= 0; --it) {
+        const int buf = (int)(it & 1);
+        cp_async_wait_all();
+        __syncthreads();
+        if (it > 0) load_fac(it - 1, buf ^ 1);
+        if (sweeper) {
+            const int64_t j0 = it * kPivTile;
+            int64_t j1 = j0 + kPivTile;
+            if (j1 > cnt[side] - 1) j1 = cnt[side] - 1;
+            const cplx(*rows)[4] = sm.tile[side][buf];
+            cplx ninv = czero(), nf1 = czero(), nf2 = czero(), nfr = czero();
+            if (j1 > j0) ninv = rows[j1 - 1 - j0][0], nf1 = rows[j1 - 1 - j0][1], nf2 = rows[j1 - 1 - j0][2], nfr = rows[j1 - 1 - j0][3];
+            for (int64_t j = j1 - 1; j >= j0; --j) {
+                const cplx inv = ninv, f1 = nf1, f2 = nf2, fr = nfr;
+                if (j > j0) {
+                    const int r = (int)(j - 1 - j0);
+                    ninv = rows[r][0], nf1 = rows[r][1], nf2 = rows[r][2], nfr = rows[r][3];
+                }
+                const cplx v = nmsub(nmsub(fr, f2, xb), f1, xa) * inv;
+                bad |= !cfinite(v);
+                x[side == 0 ? j : n - 1 - j] = v;
+                xb = xa, xa = v;
+            }
+        }
+    }
+    if (sweeper && bad) atomicOr(&sm.flag, 1);
+    __syncthreads();
+    const bool singular = sm.flag != 0;
+    __syncthreads();
+    return singular;
+}
+
+// Direct entry: every system of the batch (grid-stride over the workspace slots).
+__global__ void __launch_bounds__(kPivThreads)
+pivoted_gtsv_kernel(const cplx *__restrict__ dl, const cplx *__restrict__ d, const cplx *__restrict__ du,
+                    const cplx *__restrict__ b, cplx *__restrict__ u, int64_t n, int64_t batch, cplx *__restrict__ work,
+                    int32_t *__restrict__ status) {
+    __shared__ PivSmem sm;
+    cplx *fac = work + (size_t)blockIdx.x * 4 * (size_t)n;
+    for (int64_t s = blockIdx.x; s < batch; s += gridDim.x) {
+        const bool singular = cta_pivoted_solve(dl + s * n, d + s * n, du + s * n, b + s * n, u + s * n, n, fac, sm);
+        if (threadIdx.x == 0 && status != nullptr) status[s] = singular ? 1 : 0;
+    }
+}
+
+// Repair of the systems whose status carries the breakdown bit (bit 0), decided and carried out on the device:
+//   header[0] = number of such systems (from compact_flagged_kernel), list = their indices
+//   per system: normwise backward error of the solution that is there (refinement may already have repaired it);
+//               finite and <= accept_tol -> kept, bit 0 cleared;   otherwise -> re-solved with partial pivoting,
+//               status = 1 only if that solution is not finite either (singular to working precision)
+//   header[2] += kept, header[3] += re-solved, header[4] += singular
+__global__ void __launch_bounds__(kPivThreads)
+repair_flagged_kernel(const cplx *__restrict__ dl, const cplx *__restrict__ d, const cplx *__restrict__ du,
+                      const cplx *__restrict__ b, cplx *__restrict__ u, int64_t n, const int32_t *__restrict__ list,
+                      int32_t *__restrict__ header, double accept_tol, cplx *__restrict__ work,
+                      int32_t *__restrict__ status) {
+    __shared__ PivSmem sm;
+    cplx *fac = work + (size_t)blockIdx.x * 4 * (size_t)n;
+    const int count = header[0];
+    for (int i = blockIdx.x; i < count; i += gridDim.x) {
+        const int64_t s = list[i], o = s * n;
+        double m4[4];
+        cta_residual(dl + o, d + o, du + o, b + o, u + o, n, sm.red, m4);
+        const double be = sqrt(m4[0]) / (m4[3] * sqrt(m4[1]) + sqrt(m4[2]));
+        if (be <= accept_tol) {  // (false for NaN)
+            if (threadIdx.x == 0) {
+                status[s] &= ~1;
+                atomicAdd(&header[2], 1);
+            }
+            continue;
+        }
+        const bool singular = cta_pivoted_solve(dl + o, d + o, du + o, b + o, u + o, n, fac, sm);
+        if (threadIdx.x == 0) {
+            status[s] = singular ? 1 : 0;
+            atomicAdd(&header[3], 1);
+            if (singular) atomicAdd(&header[4], 1);
+        }
+    }
+}
+
+static int64_t pivoted_slots(int64_t n, int64_t batch) {
+    int64_t slots = batch < kPivSlotsMax ? batch : kPivSlotsMax;
+    const int64_t by_mem = (int64_t)((2ull << 30) / (sizeof(cplx) * 4 * (size_t)n));  // <= 2 GB of factor rows
+    if (slots > by_mem) slots = by_mem;
+    return slots < 1 ? 1 : slots;
 }
 }  // namespace fh
 
 extern "C" size_t fh_tridiag_solve_pivoted_workspace_bytes(int64_t n, int64_t batch) {
-    return sizeof(fh::cplx) * 3 * (size_t)n * (size_t)batch;
+    if (n <= 0 || batch <= 0) return 0;
+    return sizeof(fh::cplx) * 4 * (size_t)n * (size_t)fh::pivoted_slots(n, batch);
 }
 
 extern "C" int fh_tridiag_solve_pivoted_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c128 *du, const fh_c128 *b,
@@ -336,11 +552,70 @@ extern "C" int fh_tridiag_solve_pivoted_c128(const fh_c128 *dl, const fh_c128 *d
     FH_REQUIRE(n >= 0 && batch >= 0, "n and batch must be >= 0");
     if (n == 0 || batch == 0) return FH_OK;
     FH_REQUIRE(dl && d && du && b && u && workspace, "NULL device pointer");
-    FH_REQUIRE(workspace_bytes >= fh_tridiag_solve_pivoted_workspace_bytes(n, batch), "workspace too small");
-    pivoted_gtsv_kernel<<<(unsigned)((batch + 31) / 32), 32, 0, static_cast<cudaStream_t>(stream)>>>(
+    FH_REQUIRE(u != b, "the solution must not alias the right-hand side");
+    int64_t slots = (int64_t)(workspace_bytes / (sizeof(cplx) * 4 * (size_t)n));
+    FH_REQUIRE(slots >= 1, "workspace too small (see fh_tridiag_solve_pivoted_workspace_bytes)");
+    if (slots > batch) slots = batch;
+    if (slots > kPivSlotsMax) slots = kPivSlotsMax;
+    pivoted_gtsv_kernel<<<(unsigned)slots, kPivThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const cplx *>(dl), reinterpret_cast<const cplx *>(d), reinterpret_cast<const cplx *>(du),
         reinterpret_cast<const cplx *>(b), reinterpret_cast<cplx *>(u), n, batch, reinterpret_cast<cplx *>(workspace),
         status);
     FH_LAUNCH_CHECK("pivoted_gtsv_kernel");
+    return FH_OK;
+}
+
+namespace fh {
+struct RepairPlan {
+    int64_t slots;
+    size_t off_header, off_list, off_work, total;
+};
+static RepairPlan repair_plan(int64_t n, int64_t batch, int64_t slots) {
+    RepairPlan p;
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    p.slots = slots;
+    p.off_header = 0;
+    p.off_list = up(8 * sizeof(int32_t));
+    p.off_work = p.off_list + up(sizeof(int32_t) * (size_t)batch);
+    p.total = p.off_work + sizeof(cplx) * 4 * (size_t)n * (size_t)slots;
+    return p;
+}
+}  // namespace fh
+
+// Workspace for repairing with up to `max_concurrent` systems in flight (every one of them is repaired either way).
+extern "C" size_t fh_tridiag_repair_flagged_workspace_bytes(int64_t n, int64_t batch, int64_t max_concurrent) {
+    if (n <= 0 || batch <= 0) return 0;
+    if (max_concurrent < 1) max_concurrent = 1;
+    const int64_t cap = fh::pivoted_slots(n, batch);
+    return fh::repair_plan(n, batch, max_concurrent < cap ? max_concurrent : cap).total;
+}
+
+extern "C" int fh_tridiag_repair_flagged_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c128 *du, const fh_c128 *b,
+                                              fh_c128 *u, int64_t n, int64_t batch, int32_t *status, double accept_tol,
+                                              void *workspace, size_t workspace_bytes, fh_stream_t stream) {
+    using namespace fh;
+    FH_REQUIRE(n >= 0 && batch >= 0, "n and batch must be >= 0");
+    if (n == 0 || batch == 0) return FH_OK;
+    FH_REQUIRE(dl && d && du && b && u && status && workspace, "NULL device pointer");
+    FH_REQUIRE(batch < (1ll << 31), "batch too large");
+    const RepairPlan fixed = repair_plan(n, batch, 0);
+    FH_REQUIRE(workspace_bytes > fixed.total, "workspace too small (see fh_tridiag_repair_flagged_workspace_bytes)");
+    int64_t slots = (int64_t)((workspace_bytes - fixed.total) / (sizeof(cplx) * 4 * (size_t)n));
+    FH_REQUIRE(slots >= 1, "workspace too small (see fh_tridiag_repair_flagged_workspace_bytes)");
+    if (slots > kPivSlotsMax) slots = kPivSlotsMax;
+    if (slots > batch) slots = batch;
+    const RepairPlan p = repair_plan(n, batch, slots);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    char *ws = static_cast<char *>(workspace);
+    int32_t *header = reinterpret_cast<int32_t *>(ws + p.off_header);
+    int32_t *list = reinterpret_cast<int32_t *>(ws + p.off_list);
+    FH_CUDA(cudaMemsetAsync(header, 0, 8 * sizeof(int32_t), st));
+    compact_flagged_kernel<<<1, kCompactThreads, 0, st>>>(status, batch, 1, (int32_t)batch, list, header);
+    FH_LAUNCH_CHECK("compact_flagged_kernel");
+    repair_flagged_kernel<<<(unsigned)slots, kPivThreads, 0, st>>>(
+        reinterpret_cast<const cplx *>(dl), reinterpret_cast<const cplx *>(d), reinterpret_cast<const cplx *>(du),
+        reinterpret_cast<const cplx *>(b), reinterpret_cast<cplx *>(u), n, list, header, accept_tol,
+        reinterpret_cast<cplx *>(ws + p.off_work), status);
+    FH_LAUNCH_CHECK("repair_flagged_kernel");
     return FH_OK;
 }

@@ -224,7 +224,16 @@ def assembly(N: int, k, h: float, elements=None, theta=0.0, *, bc_left="neumann"
     return (A, b[0].cpu().numpy()) if scalar else (A, b)
 
 
-_refine_ws = {}
+_refine_ws = {}   # (n, batch, device) -> (capacity in systems, buffer); a handful of shapes are kept
+_WS_KEEP = 4
+
+
+def _remember(cache, key, value):
+    cache.pop(key, None)
+    while len(cache) >= _WS_KEEP:
+        cache.pop(next(iter(cache)))
+    cache[key] = value
+    return value
 
 
 def _refine_workspace(n, batch, device, min_systems=0):
@@ -236,25 +245,26 @@ def _refine_workspace(n, batch, device, min_systems=0):
     ent = _refine_ws.get(key)
     cap = min(batch, max(256, batch // 16, int(min_systems)))
     if ent is None or ent[0] < cap:
-        _refine_ws.clear()
         nbytes = lib.fh_tridiag_refine_flagged_workspace_bytes(n, batch, cap)
-        ent = _refine_ws[key] = (cap, torch.empty(nbytes, dtype=torch.uint8, device=device))
+        ent = _remember(_refine_ws, key, (cap, torch.empty(nbytes, dtype=torch.uint8, device=device)))
     return ent[1]
 
 
-def refine_flagged(dl, d, du, b, u, status, sync=True):
+def refine_flagged(dl, d, du, b, u, status, sync=True, ws=None):
     """One step of iterative refinement for exactly the systems whose elimination met a small pivot
     (``status & STATUS_SMALL_PIVOT``): r = b - A u, solve A e = r, u += e -- all on the device, matrices read in
     place through an index list that never visits the host (``fh_tridiag_refine_flagged_c128``).  The solver is
     unpivoted, so a pivot that cancels to 1e-5 of its scale costs five digits of backward error (seen for ~1 in 10^4
     wavenumbers of a fine sweep); one refinement step restores it.  Returns the number of refined systems; reading it
-    is the only host synchronisation (``sync=False`` skips it and returns None: at most batch/16 systems are then
-    refined)."""
+    is the only host synchronisation (``sync=False`` skips it and returns None: at most as many systems as the
+    workspace holds -- batch/16 by default -- are then refined; ``ws``: a caller-owned workspace)."""
     lib = _lib.require_cuda()
     batch, n = d.shape
     if n > lib.fh_tridiag_batched_max_n():
         return 0  # the large-system solver does not set the flag
-    ws = _refine_workspace(n, batch, d.device)
+    own = ws is None
+    if own:
+        ws = _refine_workspace(n, batch, d.device)
     total = 0
     while True:
         check(lib.fh_tridiag_refine_flagged_c128(ptr(dl), ptr(d), ptr(du), ptr(b), ptr(u), n, batch, ptr(status),
@@ -267,56 +277,61 @@ def refine_flagged(dl, d, du, b, u, status, sync=True):
             return total
         # more flagged systems than the workspace holds: finish them now, and size the workspace for the next batch
         # of this shape (so that a later sync=False call covers it in one go)
-        ws = _refine_workspace(n, batch, d.device, min_systems=flagged + flagged // 4)
+        if own:
+            ws = _refine_workspace(n, batch, d.device, min_systems=flagged + flagged // 4)
 
 
-ACCEPT_BACKWARD_ERROR = 2e-15  # what counts as "at LAPACK quality" below (median of the fast path: 2e-16; zgtsv: 2e-17)
+# What counts as repaired: three digits inside the 1e-10 contract (nb:204 / BASELINE north_star).  The unpivoted fast
+# path sits at 2e-16 (median) and LAPACK's zgtsv at 2e-17, but a refined solution at a resonance of the partition can
+# land at a few 1e-15 (k = 806.8412 in the 8-rank sweep: 2.4e-15) -- re-solving that with the serial pivoted kernel
+# buys nothing the contract asks for.
+ACCEPT_BACKWARD_ERROR = 1e-13
+
+_repair_ws = {}
 
 
-def _accept_verified(idx, backward, status, tol=ACCEPT_BACKWARD_ERROR):
-    """Of the flagged systems ``idx`` (int64 tensor), keep the flag only where the measured backward error (numpy array,
-    one entry per flagged system) is not finite or not below ``tol``; the others have their status cleared.  Returns the
-    systems that still need the pivoted re-solve."""
-    good = torch.from_numpy(np.isfinite(backward) & (backward < tol)).to(idx.device)
-    if bool(good.any()):
-        status.index_fill_(0, idx[good], 0)
-    return idx[~good]
+def _repair_workspace(n, batch, device, concurrent=16):
+    """Workspace of fh_tridiag_repair_flagged_c128, kept between calls (64 B per row for each of ``concurrent`` re-solves
+    in flight + 4 B per system of the batch)."""
+    lib = _lib.load()
+    key = (n, batch, device)
+    ent = _repair_ws.get(key)
+    if ent is None:
+        nbytes = lib.fh_tridiag_repair_flagged_workspace_bytes(n, batch, concurrent)
+        ent = _remember(_repair_ws, key, torch.empty(nbytes, dtype=torch.uint8, device=device))
+    return ent
+
+
+def repair_flagged(dl, d, du, b, u, status, sync=True, accept_tol=ACCEPT_BACKWARD_ERROR, ws=None):
+    """Deal with the systems on which the unpivoted kernels reported a breakdown (``status & STATUS_NONFINITE``): a
+    non-finite value -- a vanishing leading minor is harmless to LAPACK's zgesv, which the reference uses (nb:204), so
+    it must be harmless here -- or a probe defect beyond what one refinement step is trusted to repair.  Entirely on the
+    device (``fh_tridiag_repair_flagged_c128``: compact the flags, verify, re-solve), stream-ordered, no host round
+    trip: a flagged system whose present solution (run :func:`refine_flagged` first) is finite with a normwise backward
+    error <= ``accept_tol`` is kept; any other is re-solved with partial pivoting by a one-CTA-per-system kernel
+    (~0.2 ms for 4,097 rows).  Afterwards the flag stays set only for systems that are singular to working precision.
+
+    ``sync=True`` reads the counters back and returns ``{"flagged", "kept", "resolved", "singular"}``; ``sync=False``
+    returns None (the counters stay in the first 32 bytes of the workspace: :func:`repair_counts`)."""
+    lib = _lib.require_cuda()
+    batch, n = d.shape
+    if ws is None:
+        ws = _repair_workspace(n, batch, d.device)
+    check(lib.fh_tridiag_repair_flagged_c128(ptr(dl), ptr(d), ptr(du), ptr(b), ptr(u), n, batch, ptr(status),
+                                             float(accept_tol), ptr(ws), ws.numel(), stream_ptr()),
+          "fh_tridiag_repair_flagged_c128")
+    return repair_counts(ws) if sync else None
+
+
+def repair_counts(ws):
+    """Counters left in a repair workspace by the last :func:`repair_flagged` call (synchronises)."""
+    h = ws[:32].view(torch.int32).tolist()
+    return {"flagged": h[0], "kept": h[2], "resolved": h[3], "singular": h[4]}
 
 
 def resolve_nonfinite(dl, d, du, b, u, status):
-    """Re-solve, with partial pivoting, the systems on which the unpivoted kernels reported a breakdown
-    (``status & STATUS_NONFINITE``): a vanishing leading minor is harmless to LAPACK's zgesv, which the reference
-    uses, so it must be harmless here.  Afterwards the flag stays set only for systems that are singular to working
-    precision.  Returns the number of re-solved systems.
-
-    The flag is also raised for a FINITE solution whose probe defect was beyond what one refinement step is trusted to
-    repair.  If :func:`refine_flagged` has already run (such a system carries the small-pivot bit as well) and its
-    solution verifiably is at LAPACK quality -- device-side backward error below ``ACCEPT_BACKWARD_ERROR`` --, it is
-    kept and the flag cleared: the pivoted kernel works with one thread per system (about 5 ms for one 4,097-row
-    system, measured), which is fine for a rare fallback but not worth paying for a solution that is already good."""
-    lib = _lib.require_cuda()
-    idx = torch.nonzero((status & STATUS_NONFINITE) != 0).flatten()
-    if int(idx.numel()) == 0:
-        return 0
-    try:
-        be = tridiagonal_residual(*(t.index_select(0, idx) for t in (dl, d, du, b, u)))["backward"]
-        idx = _accept_verified(idx, be, status)
-    except Exception:  # the check is an optimisation: whatever goes wrong, every flagged system is re-solved
-        pass
-    m = int(idx.numel())
-    if m == 0:
-        return 0
-    n = d.shape[1]
-    sub = [t.index_select(0, idx).contiguous() for t in (dl, d, du, b)]
-    x = torch.empty_like(sub[3])
-    st = torch.zeros(m, dtype=torch.int32, device=d.device)
-    ws_bytes = lib.fh_tridiag_solve_pivoted_workspace_bytes(n, m)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=d.device)
-    check(lib.fh_tridiag_solve_pivoted_c128(*(ptr(t) for t in sub), ptr(x), n, m, ptr(st), ptr(ws), ws_bytes,
-                                            stream_ptr()), "fh_tridiag_solve_pivoted_c128")
-    u.index_copy_(0, idx, x)
-    status.index_copy_(0, idx, st)
-    return m
+    """:func:`repair_flagged`, returning the number of systems that went through the pivoted re-solve."""
+    return repair_flagged(dl, d, du, b, u, status)["resolved"]
 
 
 def solve_tridiagonal(dl, d, du, b, out=None, refine=True):
@@ -338,8 +353,10 @@ def solve_tridiagonal(dl, d, du, b, out=None, refine=True):
     check(lib.fh_tridiag_solve_batched_c128(ptr(dl), ptr(d), ptr(du), ptr(b), ptr(u), n, batch, ptr(status),
                                             ptr(ws), ws_bytes, stream_ptr()), "fh_tridiag_solve_batched_c128")
     if refine:
-        resolve_nonfinite(dl, d, du, b, u, status)
+        # both steps are stream-ordered device work: the refinement first (it repairs most severe defects too), then
+        # the verify-or-pivot pass over whatever still carries the breakdown bit
         refine_flagged(dl, d, du, b, u, status)
+        repair_flagged(dl, d, du, b, u, status, sync=False)
     return u, status
 
 
@@ -361,23 +378,48 @@ def tridiagonal_residual(dl, d, du, b, u):
                 "b2": o[:, 2], "anorm": an}
 
 
+PIPELINES = ("staged", "one_pass", "fused")
+
+
+def _pick_pipeline(pipeline, fused, N, nodal_h):
+    """``pipeline=None`` -> "fused" if the legacy ``fused=True`` switch is set, else the default: the one-pass kernel
+    (A written once, solved from registers: same bits as the staged pair, 80 instead of 144 B/DOF of traffic) wherever
+    it applies -- uniform meshes of 3 .. fh_tridiag_batched_max_n() nodes --, the staged pair elsewhere."""
+    if pipeline is None:
+        pipeline = "fused" if fused else "auto"
+    if pipeline == "auto":
+        ok = (not nodal_h) and int(N) >= 2 and int(N) + 1 <= _lib.load().fh_tridiag_batched_max_n()
+        pipeline = "one_pass" if ok else "staged"
+    if pipeline not in PIPELINES:
+        raise ValueError(f"pipeline must be one of {PIPELINES} (or None / 'auto'), got {pipeline!r}")
+    return pipeline
+
+
 def solve_helmholtz_sweep(N, ks, L=1.0, theta=0.0, *, bc_left="neumann", bc_right="sommerfeld",
-                          g_left=1.0, g_right=0.0, fused=False, nodal_h=False, out=None,
+                          g_left=1.0, g_right=0.0, fused=False, pipeline=None, nodal_h=False, out=None,
                           check_singular=True, return_status=False):
     """Assemble and solve the 1D problem for every wavenumber in ``ks`` (the shape of the reference's
     sweep loop nb:300-317 / nb:469-471, batched).  Returns ``(nodes, U)`` with ``U`` a CUDA tensor
     complex128[n_k, N+1].
 
-    ``fused=False`` (default): staged pipeline, ``assembly`` writes the bands, the batched solver
-    reads them back -- the reference's structure.  ``fused=True``: one kernel generates the rows in
-    registers and only writes ``U``."""
+    ``pipeline``: "staged" -- ``assembly`` writes the bands, the batched solver reads them back (the reference's
+    structure, two kernels); "one_pass" -- one kernel writes the same bands and solves from its registers (bit-identical
+    results; the default where it applies); "fused" (or ``fused=True``) -- the rows are generated in registers and only
+    ``U`` is written.  In every variant flagged systems are refined / repaired to ``np.linalg.solve`` quality."""
     lib = _lib.require_cuda()
     h, nodes = L / N, np.linspace(0, L, N + 1)  # create_mesh without the (unused, 16 B/element) connectivity
     ks_h, k2s_h, _ = _host_k_and_k2(ks)
     n_k, n = len(ks_h), int(N) + 1
     dev = _lib.device()
+    pipeline = _pick_pipeline(pipeline, fused, N, nodal_h)
+    fused = pipeline == "fused"
     nodes_d = _lib.as_device(nodes, torch.float64) if nodal_h else None
-    if not fused:
+    if pipeline == "one_pass" and (nodal_h or N < 2 or n > lib.fh_tridiag_batched_max_n()):
+        pipeline = "staged"
+    if pipeline == "one_pass":
+        _, U, status = assemble_and_solve(N, (ks_h, k2s_h), L, theta, bc_left=bc_left, bc_right=bc_right, g_left=g_left,
+                                          g_right=g_right, out=out)
+    elif not fused:
         dl, d, du, b = assemble_bands(N, (ks_h, k2s_h), h, theta, bc_left=bc_left, bc_right=bc_right, g_left=g_left, g_right=g_right,
                                       nodes=nodes if nodal_h else None)
         U, status = solve_tridiagonal(dl, d, du, b, out=out)
@@ -401,7 +443,7 @@ def solve_helmholtz_sweep(N, ks, L=1.0, theta=0.0, *, bc_left="neumann", bc_righ
         idx = torch.nonzero(status != 0).flatten()
         if idx.numel() > 0:
             # the fused kernel stores no bands: assemble them for the few flagged wavenumbers and solve those again
-            # through the staged path (pivoted re-solve of breakdowns, refinement of small-pivot systems)
+            # through the staged path (refinement of small-pivot systems, pivoted re-solve of breakdowns)
             sel = idx.cpu().numpy()
             bands = assemble_bands(N, (ks_h[sel], k2s_h[sel]), h, theta, bc_left=bc_left, bc_right=bc_right,
                                    g_left=g_left, g_right=g_right, nodes=nodes if nodal_h else None)
@@ -421,7 +463,7 @@ def assemble_and_solve(N, ks, L=1.0, theta=0.0, *, bc_left="neumann", bc_right="
     ``((dl, d, du, b), U, status)`` -- CUDA tensors complex128[n_k, N+1].  Uniform meshes up to the batched solver's
     size; longer or non-uniform meshes take the two-kernel path."""
     lib = _lib.require_cuda()
-    ks_h, k2s_h, _ = _host_k_and_k2(ks)
+    ks_h, k2s_h = ks if isinstance(ks, tuple) else _host_k_and_k2(ks)[:2]  # tuple = (ks, k2s) already split
     n_k, n = len(ks_h), int(N) + 1
     dev = _lib.device()
     if n > lib.fh_tridiag_batched_max_n() or N < 2:
@@ -440,8 +482,8 @@ def assemble_and_solve(N, ks, L=1.0, theta=0.0, *, bc_left="neumann", bc_right="
           "fh_helmholtz1d_sweep_assemble_solve_c128")
     bands = (B[0], B[1], B[2], B[3])
     if refine:
-        resolve_nonfinite(*bands, U, status)
         refine_flagged(*bands, U, status)
+        repair_flagged(*bands, U, status, sync=False)
     return bands, U, status
 
 
@@ -542,47 +584,84 @@ def analytical_solution(x, k):
 class HostSweepPlan:
     """Reusable buffers for :func:`solve_helmholtz_sweep_host`: a pinned host array for the result, and two
     sets of device buffers so that chunk i+1 is assembled+solved while chunk i is copied back.  (Pinning
-    gigabytes of host memory costs about a second, so a caller that sweeps repeatedly keeps the plan.)"""
+    gigabytes of host memory costs about a second, so a caller that sweeps repeatedly keeps the plan.)
 
-    def __init__(self, N, n_k, chunk=None, numa_local=True):
-        _lib.require_cuda()
+    ``reduce="l2"``: the sweep returns, per wavenumber, the 16-byte sum inside ``compute_L2_error`` (nb:259-281) instead
+    of the solution -- what the reference's own sweep driver ``convergence_test`` (nb:284-362) consumes; no solution ever
+    crosses PCIe and the plan holds no n_k x (N+1) host buffer.  ``pipeline``: see :func:`solve_helmholtz_sweep`."""
+
+    def __init__(self, N, n_k, chunk=None, numa_local=True, reduce=None, pipeline=None, fused=False):
+        lib = _lib.require_cuda()
+        if reduce not in (None, "l2"):
+            raise ValueError("reduce must be None or 'l2'")
         # pinned buffers on the GPU's own NUMA node (matters with one process per GPU on a two-socket host)
         self.cpu_cores = _lib.bind_host_thread_near_device() if numa_local else None
-        self.N, self.n, self.n_k = int(N), int(N) + 1, int(n_k)
+        self.N, self.n, self.n_k, self.reduce = int(N), int(N) + 1, int(n_k), reduce
+        self.pipeline = _pick_pipeline(pipeline, fused, N, False)
         if chunk is None:  # ~256 MB of solution per chunk keeps both the copy engine and the SMs busy
             chunk = max(1, min(self.n_k, (256 << 20) // (16 * self.n)))
         self.chunk = int(chunk)
         dev = _lib.device()
-        self.U_host = torch.empty((self.n_k, self.n), dtype=torch.complex128).pin_memory()
         self.k_host = torch.empty((2, self.n_k), dtype=torch.float64).pin_memory()
         self.k_dev = torch.empty((2, self.n_k), dtype=torch.float64, device=dev)
-        self.bands = [torch.empty((4, self.chunk, self.n), dtype=torch.complex128, device=dev) for _ in range(2)]
-        self.U_dev = [torch.empty((self.chunk, self.n), dtype=torch.complex128, device=dev) for _ in range(2)]
+        slots = 2
+        self.bands = ([torch.empty((4, self.chunk, self.n), dtype=torch.complex128, device=dev) for _ in range(slots)]
+                      if self.pipeline != "fused" else None)
+        self.U_dev = [torch.empty((self.chunk, self.n), dtype=torch.complex128, device=dev) for _ in range(slots)]
         self.status = torch.zeros(self.n_k, dtype=torch.int32, device=dev)
+        self.status_host = torch.empty(self.n_k, dtype=torch.int32).pin_memory()
         self.copy_stream = torch.cuda.Stream()
         self.h2d_bytes = self.k_host.numel() * 8
-        self.d2h_bytes = self.U_host.numel() * 16 + self.n_k * 4
+        if reduce is None:
+            self.U_host = torch.empty((self.n_k, self.n), dtype=torch.complex128).pin_memory()
+            self.d2h_bytes = self.U_host.numel() * 16 + self.n_k * 4
+        else:
+            self.U_host = None
+            self.nodes_dev = None  # set per call (depends on L)
+            self.sums_dev = torch.empty(self.n_k, dtype=torch.complex128, device=dev)
+            self.sums_host = torch.empty(self.n_k, dtype=torch.complex128).pin_memory()
+            self.d2h_bytes = self.n_k * 16 + self.n_k * 4
+        if self.pipeline != "fused" and self.n <= lib.fh_tridiag_batched_max_n():
+            cap = max(256, self.chunk // 4)  # systems one stream-ordered refinement call can take
+            nb = lib.fh_tridiag_refine_flagged_workspace_bytes(self.n, self.chunk, cap)
+            self.refine_ws = [torch.empty(nb, dtype=torch.uint8, device=dev) for _ in range(slots)]
+            nb = lib.fh_tridiag_repair_flagged_workspace_bytes(self.n, self.chunk, 8)
+            self.repair_ws = [torch.empty(nb, dtype=torch.uint8, device=dev) for _ in range(slots)]
+        else:
+            self.refine_ws = self.repair_ws = None
 
 
-def solve_helmholtz_sweep_host(N, ks, L=1.0, theta=0.0, *, plan=None, fused=False, check_singular=True,
-                               **bc):
+def solve_helmholtz_sweep_host(N, ks, L=1.0, theta=0.0, *, plan=None, fused=False, pipeline=None, reduce=None,
+                               check_singular=True, **bc):
     """Host-to-host wavenumber sweep: ``ks`` (numpy / list) in, ``(nodes, U)`` out with ``U`` a numpy
     complex128[n_k, N+1] array (a view of the plan's pinned buffer).  Per call: one pinned H2D copy of
     (k, k**2), chunked assemble+solve on the compute stream, and D2H copies of the finished chunks on a
-    second stream, overlapped with the next chunk's kernels."""
+    second stream, overlapped with the next chunk's kernels.  Flagged systems are refined and breakdowns repaired on
+    the device inside the pipeline (no host round trip); the status array is read once at the end.
+
+    ``reduce="l2"``: returns ``(nodes, sums)`` instead, ``sums`` = numpy complex128[n_k], the sum inside
+    ``compute_L2_error`` (nb:259-281; ``np.sqrt`` of it is the reference's return value) of every solution against
+    ``analytical_solution`` -- the only thing the reference's ``convergence_test`` (nb:284-362) does with ``u``.  The
+    solutions stay on the device; 20 bytes per wavenumber cross PCIe."""
     lib = _lib.require_cuda()
     h, nodes = L / N, np.linspace(0, L, N + 1)
     ks_h, k2s_h, _ = _host_k_and_k2(ks)
     n_k = len(ks_h)
     if plan is None:
-        plan = HostSweepPlan(N, n_k)
+        plan = HostSweepPlan(N, n_k, reduce=reduce, pipeline=pipeline, fused=fused)
     assert plan.N == int(N) and plan.n_k == n_k, "plan was built for another sweep shape"
-    prob = _problem(N, h, theta, bc.get("bc_left", "neumann"), bc.get("bc_right", "sommerfeld"),
-                    bc.get("g_left", 1.0), bc.get("g_right", 0.0), None)
+    reduce, pipeline = plan.reduce, plan.pipeline
+    bcs = dict(bc_left=bc.get("bc_left", "neumann"), bc_right=bc.get("bc_right", "sommerfeld"),
+               g_left=bc.get("g_left", 1.0), g_right=bc.get("g_right", 0.0))
+    prob = _problem(N, h, theta, bcs["bc_left"], bcs["bc_right"], bcs["g_left"], bcs["g_right"], None)
     main = torch.cuda.current_stream()
     plan.k_host[0].copy_(torch.from_numpy(ks_h))
     plan.k_host[1].copy_(torch.from_numpy(k2s_h))
     plan.k_dev.copy_(plan.k_host, non_blocking=True)
+    if reduce == "l2":
+        plan.nodes_dev = torch.from_numpy(nodes).to(plan.k_dev.device)
+        gp = np.ascontiguousarray(gauss_point, dtype=np.float64)
+        gw = np.ascontiguousarray(gauss_weight, dtype=np.float64)
     done = [None, None]
     for c, lo in enumerate(range(0, n_k, plan.chunk)):
         hi = min(n_k, lo + plan.chunk)
@@ -591,19 +670,32 @@ def solve_helmholtz_sweep_host(N, ks, L=1.0, theta=0.0, *, plan=None, fused=Fals
             main.wait_event(done[slot])  # the copy engine has drained this slot's previous chunk
         ks_d, k2s_d = plan.k_dev[0, lo:hi], plan.k_dev[1, lo:hi]
         U, st = plan.U_dev[slot][:m], plan.status[lo:hi]
-        if fused:
+        if pipeline == "fused":
             check(lib.fh_helmholtz1d_sweep_fused_c128(C.byref(prob), ptr(ks_d), ptr(k2s_d), m, ptr(U), ptr(st),
                                                       None, 0, stream_ptr()), "fh_helmholtz1d_sweep_fused_c128")
         else:
-            B = plan.bands[slot]
-            dl, d, du, b = (B[i, :m] for i in range(4))
-            check(lib.fh_assemble_1d_c128(C.byref(prob), ptr(ks_d), ptr(k2s_d), m, ptr(dl), ptr(d), ptr(du),
-                                          ptr(b), stream_ptr()), "fh_assemble_1d_c128")
-            check(lib.fh_tridiag_solve_batched_c128(ptr(dl), ptr(d), ptr(du), ptr(b), ptr(U), plan.n, m, ptr(st),
-                                                    None, 0, stream_ptr()), "fh_tridiag_solve_batched_c128")
-            # stream-ordered (no host round trip inside the pipeline); whatever one call cannot take is finished below
-            _refine_workspace(plan.n, m, d.device, min_systems=m // 4)
-            refine_flagged(dl, d, du, b, U, st, sync=False)
+            # (a chunk smaller than the plan's takes the head of the slot's buffers: same pointers every call)
+            B = plan.bands[slot].view(-1)[:4 * m * plan.n].view(4, m, plan.n)
+            dl, d, du, b = (B[i] for i in range(4))
+            if pipeline == "one_pass":
+                check(lib.fh_helmholtz1d_sweep_assemble_solve_c128(C.byref(prob), ptr(ks_d), ptr(k2s_d), m, ptr(dl),
+                                                                   ptr(d), ptr(du), ptr(b), ptr(U), ptr(st), None, 0,
+                                                                   stream_ptr()),
+                      "fh_helmholtz1d_sweep_assemble_solve_c128")
+            else:
+                check(lib.fh_assemble_1d_c128(C.byref(prob), ptr(ks_d), ptr(k2s_d), m, ptr(dl), ptr(d), ptr(du),
+                                              ptr(b), stream_ptr()), "fh_assemble_1d_c128")
+                check(lib.fh_tridiag_solve_batched_c128(ptr(dl), ptr(d), ptr(du), ptr(b), ptr(U), plan.n, m, ptr(st),
+                                                        None, 0, stream_ptr()), "fh_tridiag_solve_batched_c128")
+            if plan.refine_ws is not None:
+                # stream-ordered, no host round trip; whatever one call cannot take is finished below
+                refine_flagged(dl, d, du, b, U, st, sync=False, ws=plan.refine_ws[slot])
+                repair_flagged(dl, d, du, b, U, st, sync=False, ws=plan.repair_ws[slot])
+        if reduce == "l2":
+            check(lib.fh_l2_error_1d_c128(ptr(plan.nodes_dev), ptr(U), ptr(ks_d), int(N), m,
+                                          gp.ctypes.data_as(C.c_void_p), gw.ctypes.data_as(C.c_void_p), len(gp),
+                                          ptr(plan.sums_dev[lo:hi]), stream_ptr()), "fh_l2_error_1d_c128")
+            continue
         ready = torch.cuda.Event()
         ready.record(main)
         with torch.cuda.stream(plan.copy_stream):
@@ -611,25 +703,30 @@ def solve_helmholtz_sweep_host(N, ks, L=1.0, theta=0.0, *, plan=None, fused=Fals
             plan.U_host[lo:hi].copy_(U, non_blocking=True)
             done[slot] = torch.cuda.Event()
             done[slot].record(plan.copy_stream)
+    if reduce == "l2":
+        plan.sums_host.copy_(plan.sums_dev, non_blocking=True)
     main.wait_stream(plan.copy_stream)
-    status_host = plan.status.cpu()  # synchronises: everything above has finished
+    plan.status_host.copy_(plan.status, non_blocking=True)
+    main.synchronize()  # everything above has finished
+    status_host = plan.status_host
     left = torch.nonzero(status_host != 0).flatten()
     if left.numel() > 0:
-        # breakdowns of the unpivoted kernels, flagged systems of the fused variant (which keeps no bands), or more
-        # flagged systems in a chunk than its refinement workspace holds: solve those wavenumbers again through the
-        # staged path (pivoted re-solve + refinement) and patch their rows of the result
+        # flagged systems of the fused variant (which keeps no bands), more flagged systems in a chunk than its
+        # refinement workspace holds, or systems singular to working precision: solve those wavenumbers again through
+        # the staged path (refinement + pivoted repair) and patch their part of the result
         sel = left.numpy()
-        bands = assemble_bands(N, (ks_h[sel], k2s_h[sel]), h, theta, bc_left=bc.get("bc_left", "neumann"),
-                               bc_right=bc.get("bc_right", "sommerfeld"), g_left=bc.get("g_left", 1.0),
-                               g_right=bc.get("g_right", 0.0))
+        bands = assemble_bands(N, (ks_h[sel], k2s_h[sel]), h, theta, **bcs)
         u_fix, st_fix = solve_tridiagonal(*bands)
-        plan.U_host[left] = u_fix.cpu()
+        if reduce == "l2":
+            plan.sums_host[left] = torch.from_numpy(l2_error_sums(ks_h[sel], N, nodes, u_fix))
+        else:
+            plan.U_host[left] = u_fix.cpu()
         status_host[left] = st_fix.cpu()
         plan.status.copy_(status_host)
     if check_singular and bool(torch.any((status_host & STATUS_NONFINITE) != 0)):
         bad = torch.nonzero(status_host & STATUS_NONFINITE).flatten()[:8].tolist()
         raise np.linalg.LinAlgError(f"Singular matrix (zero pivot / non-finite solution) in systems {bad}")
-    return nodes, plan.U_host.numpy()
+    return nodes, (plan.sums_host.numpy() if reduce == "l2" else plan.U_host.numpy())
 
 
 def l2_error_sums(k, N, nodes, u_num, gauss_points=gauss_point, gauss_weights=gauss_weight):

@@ -92,7 +92,7 @@ FH_API int fh_assemble_1d_c128(const fh_problem1d *prob_host, const double *ks, 
  * per-thread interface rows in shared memory; a 2-CTA cluster solves one system when n > 2056.
  * status[batch] (device int32, may be NULL): bit 0 (FH_STATUS_NONFINITE) set if the unpivoted elimination broke
  * down -- the solution holds a non-finite value (zero pivot / singular system) or the a-posteriori probe found a
- * relative defect above 1e-8: re-solve that system with fh_tridiag_solve_pivoted_c128; bit 1
+ * relative defect above 1e-8: see fh_tridiag_repair_flagged_c128 / fh_tridiag_solve_pivoted_c128; bit 1
  * (FH_STATUS_SMALL_PIVOT) set if the probe -- every thread re-evaluates the original equation of its interface row
  * with the computed solution -- found a relative defect above 5e-14 (backward error may exceed ~1e-13: refine that
  * system, see fh_tridiag_refine_flagged_c128).  n <= fh_tridiag_batched_max_n() takes the cluster kernel, larger n
@@ -191,12 +191,28 @@ FH_API int fh_tridiag_residual_c128(const fh_c128 *dl, const fh_c128 *d, const f
                              const fh_c128 *u, int64_t n, int64_t batch, double *out4,
                              fh_stream_t stream);
 
-/* Pivoted fallback (LAPACK zgtsv's algorithm, one thread per system): for the few systems on which the unpivoted
- * solvers report a non-finite value.  status[s] = 1 only if the system is singular to working precision. */
+/* Pivoted fallback (LAPACK zgtsv's algorithm: Gaussian elimination with partial pivoting between adjacent rows, which
+ * is what np.linalg.solve, nb:204, reaches through zgesv on a tridiagonal A): for the few systems on which the unpivoted
+ * solvers break down.  One CTA per system; the serial recurrence runs from both ends of the system at once (two
+ * sweeping lanes that meet in a pivoted 2 x 2 system), the rows stream through shared memory one tile ahead.  Any n.
+ * u must not alias b.  status[s] = 1 only if the system is singular to working precision, else 0 (may be NULL).
+ * workspace: 64 B per row for every system in flight (the query sizes it for min(batch, 256) of them). */
 FH_API size_t fh_tridiag_solve_pivoted_workspace_bytes(int64_t n, int64_t batch);
 FH_API int fh_tridiag_solve_pivoted_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c128 *du, const fh_c128 *b,
                                   fh_c128 *u, int64_t n, int64_t batch, int32_t *status, void *workspace,
                                   size_t workspace_bytes, fh_stream_t stream);
+
+/* Repair of breakdowns, decided and carried out on the device (no host round trip): every system whose status carries
+ * FH_STATUS_NONFINITE (1) is looked at once more -- if the solution that is there (e.g. after
+ * fh_tridiag_refine_flagged_c128) is finite and its normwise backward error ||b - A u|| / (||A||_inf ||u|| + ||b||) is
+ * <= accept_tol, it is kept and the bit cleared; otherwise the system is re-solved with partial pivoting
+ * (fh_tridiag_solve_pivoted_c128's kernel) and status[s] becomes 0, or 1 if it is singular to working precision.
+ * On return (stream-ordered) the first five int32 of the workspace hold {flagged, -, kept, re-solved, singular}.
+ * max_concurrent: how many re-solves may be in flight (64 B per row each); every flagged system is handled either way. */
+FH_API size_t fh_tridiag_repair_flagged_workspace_bytes(int64_t n, int64_t batch, int64_t max_concurrent);
+FH_API int fh_tridiag_repair_flagged_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c128 *du, const fh_c128 *b,
+                                   fh_c128 *u, int64_t n, int64_t batch, int32_t *status, double accept_tol,
+                                   void *workspace, size_t workspace_bytes, fh_stream_t stream);
 
 /* r = b - A u for every system (complex128[batch][n]): the right-hand side of one refinement step. */
 FH_API int fh_tridiag_residual_vector_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c128 *du, const fh_c128 *b,

@@ -112,18 +112,3 @@ def test_2d_host_objects_match_reference(golden2d):
     assert list(g["solver_names"]) == solvers
     with pytest.raises(AssertionError):
         get_solver("nope", eqn)
-
-
-def test_accepting_verified_solutions_is_pure_bookkeeping():
-    """fem1d._accept_verified (the pre-check of resolve_nonfinite): flags are cleared exactly where the measured backward
-    error is finite and under the bar; everything else is handed to the pivoted re-solve."""
-    import numpy as np
-    import torch
-
-    from fem_helmholtz_eqn_b200 import fem1d
-    status = torch.tensor([0, 3, 0, 1, 3, 2], dtype=torch.int32)
-    idx = torch.nonzero((status & fem1d.STATUS_NONFINITE) != 0).flatten()
-    left = fem1d._accept_verified(idx, np.array([1e-16, np.nan, 3e-9]), status)
-    assert left.tolist() == [3, 4] and status.tolist() == [0, 0, 0, 1, 3, 2]
-    left = fem1d._accept_verified(idx, np.array([np.inf, 1e-3, fem1d.ACCEPT_BACKWARD_ERROR]), status)
-    assert left.tolist() == [1, 3, 4] and status.tolist() == [0, 0, 0, 1, 3, 2]

@@ -309,9 +309,10 @@ def test_zero_pivot_is_resolved_by_the_pivoted_fallback():
 
 
 def test_breakdown_flag_on_a_verified_solution_is_cleared_without_the_pivoted_resolve():
-    """resolve_nonfinite: a system that carries the breakdown bit but whose (refined) solution verifiably is at LAPACK
-    quality is kept; a real breakdown in the same batch still goes through the pivoted kernel."""
-    N, ks = 512, [3.0, 40.0, 77.0]
+    """repair_flagged (device-driven): a system that carries the breakdown bit but whose (refined) solution verifiably is
+    within the acceptance bar is kept untouched; a real breakdown in the same batch goes through the pivoted kernel; a
+    finite but wrong solution does too."""
+    N, ks = 512, [3.0, 40.0, 77.0, 21.5]
     dl, d, du, b = fh.assemble_bands(N, ks, 1.0 / N)
     u, status = fh.solve_tridiagonal(dl, d, du, b)
     assert int(status.abs().sum()) == 0
@@ -319,11 +320,83 @@ def test_breakdown_flag_on_a_verified_solution_is_cleared_without_the_pivoted_re
     status[1] = 3              # as if the probe had found a severe defect and the refinement step had run since
     u[2] = float("nan")        # a real breakdown
     status[2] = 1
-    m = fh.fem1d.resolve_nonfinite(dl, d, du, b, u, status)
-    assert m in (1, 2) and int(status.abs().sum()) == 0
-    if m == 1:                 # (the usual case: the backward error of system 1 is ~2e-16, under the acceptance bar)
-        assert torch.equal(u[1], ref[1])
-    assert rel_err(_np(u[1]), _np(ref[1])) < 1e-10 and rel_err(_np(u[2]), _np(ref[2])) < 1e-10
+    u[3, 100] += 1e-6          # finite, but five digits short of the bar
+    status[3] = 1
+    counts = fh.fem1d.repair_flagged(dl, d, du, b, u, status)
+    assert counts == {"flagged": 3, "kept": 1, "resolved": 2, "singular": 0}, counts
+    assert int(status.abs().sum()) == 0
+    assert torch.equal(u[0], ref[0]) and torch.equal(u[1], ref[1])
+    assert rel_err(_np(u[2]), _np(ref[2])) < 1e-10 and rel_err(_np(u[3]), _np(ref[3])) < 1e-10
+    assert fh.tridiagonal_residual(dl, d, du, b, u)["backward"].max() < 1e-15
+
+
+def _call_pivoted(dl, d, du, b):
+    import ctypes as C  # noqa: F401
+    from fem_helmholtz_eqn_b200._lib import as_device, check, ptr, stream_ptr
+    lib = fh._lib.require_cuda()
+    dev = [as_device(np.atleast_2d(x), torch.complex128) for x in (dl, d, du, b)]
+    batch, n = dev[1].shape
+    x = torch.empty_like(dev[3])
+    st = torch.full((batch,), 7, dtype=torch.int32, device="cuda")
+    ws_bytes = lib.fh_tridiag_solve_pivoted_workspace_bytes(n, batch)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    check(lib.fh_tridiag_solve_pivoted_c128(*(ptr(t) for t in dev), ptr(x), n, batch, ptr(st), ptr(ws), ws_bytes,
+                                            stream_ptr()), "fh_tridiag_solve_pivoted_c128")
+    return _np(x), _np(st)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 9, 127, 128, 129, 130, 255, 256, 257, 258, 259, 513, 4097, 4112, 5001, 100_003])
+def test_pivoted_kernel_matches_lapack_on_systems_that_need_pivoting(n):
+    """fh_tridiag_solve_pivoted_c128 (one CTA per system, elimination from both ends, tiles of 128 rows per side): sizes
+    around the tile boundaries, exact zeros on the diagonal (every third entry), batch of 3 (grid-stride over slots)."""
+    rng = np.random.default_rng(n)
+    batch = 3 if n < 10_000 else 1
+    dl, d, du, b = (rng.normal(size=(batch, n)) + 1j * rng.normal(size=(batch, n)) for _ in range(4))
+    if n > 3:
+        d[:, ::3] = 0
+    x, st = _call_pivoted(dl, d, du, b)
+    assert st.tolist() == [0] * batch
+    for i in range(batch):
+        ref = banded1d.solve_bands(dl[i], d[i], du[i], b[i])
+        assert rel_err(x[i], ref) < 1e-9, (n, i, rel_err(x[i], ref))
+        # (random hollow matrices are not well conditioned: the backward error is the sharp gate)
+        assert banded1d.residual_metrics(dl[i], d[i], du[i], b[i], x[i])[0] < 5e-15, n
+
+
+def test_pivoted_kernel_reports_singular_systems_only():
+    n = 9
+    one, zero = np.ones(n, complex), np.zeros(n, complex)
+    rng = np.random.default_rng(1)
+    ok = [rng.normal(size=n) + 1j * rng.normal(size=n) for _ in range(4)]
+    dl, d, du, b = (np.stack([s, g]) for s, g in zip((one, zero, one, one), ok))  # system 0: odd hollow matrix
+    x, st = _call_pivoted(dl, d, du, b)
+    assert st.tolist() == [1, 0]
+    assert rel_err(x[1], banded1d.solve_bands(*ok)) < 1e-10
+
+
+def test_eight_rank_sweep_shards_near_the_partition_resonance():
+    """in the 8-rank sweep (8 x 65,536 wavenumbers over [1, 1000]) rank 3 owns k = 806.8412377190356,
+    a resonance of the batched kernel's partition (raw backward error 8e-8 -> severe flag).  Every shard's wavenumbers
+    around it go through the real kernels here: after refinement + device-side repair nothing may be above 1e-13, no
+    system may be left flagged, and the pivoted re-solve must not be needed (one refinement step reaches ~2e-15)."""
+    N, world, n_k = 4096, 8, 65536
+    ks_all = np.linspace(1.0, 1000.0, n_k * world)
+    worst, resolved, severe = 0.0, 0, 0
+    for r in range(world):
+        ks = ks_all[r::world]
+        ks = ks[np.abs(ks - 806.8412377190356) < 0.75]
+        assert len(ks) > 90
+        dl, d, du, b = fh.assemble_bands(N, ks, 1.0 / N)
+        u, status = fh.solve_tridiagonal(dl, d, du, b, refine=False)
+        severe += int(((status & 1) != 0).sum())
+        fh.fem1d.refine_flagged(dl, d, du, b, u, status)
+        counts = fh.fem1d.repair_flagged(dl, d, du, b, u, status)
+        resolved += counts["resolved"]
+        assert int(status.abs().sum()) == 0, (r, _np(status).nonzero())
+        worst = max(worst, float(fh.tridiagonal_residual(dl, d, du, b, u)["backward"].max()))
+    assert severe >= 1          # the resonance is in there
+    assert worst < 1e-13, worst
+    assert resolved == 0, resolved
 
 
 @pytest.mark.parametrize("fused", [False, True])
