@@ -208,13 +208,21 @@ def workload_config(n_gpus):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-def other_configs(world, rank, dev, dist):
+BYTES_LARGE_SOLVE = 162   # stored bands, one long system: reduce 64 read; back-substitution 64 read + 16 written; +18 levels
+BYTES_LARGE_FUSED = 16    # generated rows (periodic recursion): the solution is written, nothing is read at level 0
+
+
+def other_configs(world, rank, dev, dist, peak):
     """The BASELINE configs that are not the headline workload, timed after it (they are parity tests in tests/; this
-    only records how long they take on this box): configs 2 / 5 (N = 1e6, one GPU) through fem1d.LargeMeshPlan, and
-    config 4 (N = 2^27, k = 1000) through distributed.PartitionedPlan -- the whole mesh on one GPU, or one slab per
-    rank with a 128-byte NCCL all-gather.  CUDA events around solve(k), max over ranks, median of 10."""
+    records how long they take on this box, as a fraction of the HBM roofline, with the backward error of what was timed):
+    config 1 (1,000 nodes, host-to-host latency), configs 2 / 5 (N = 1e6, one GPU) through fem1d.LargeMeshPlan, and
+    config 4 (N = 2^27, k = 1000) through distributed.PartitionedPlan -- one slab per rank, 128-byte NCCL all-gather --,
+    rows generated and with A materialised.  With more than one rank also the STRONG-scaling wavenumber sweep (65,536
+    wavenumbers over all ranks) and the final all-gather of its solutions.  CUDA events, max over ranks, median of 10."""
+    import numpy as np
     import torch
 
+    import fem_helmholtz_eqn_b200 as fh
     from fem_helmholtz_eqn_b200 import distributed as D
     from fem_helmholtz_eqn_b200 import fem1d
 
@@ -241,40 +249,105 @@ def other_configs(world, rank, dev, dist):
             ts.append(float(t.item()))
         return statistics.median(ts)
 
+    def rate(dof, ms, bytes_per_dof, gpus=1):
+        gbs = bytes_per_dof * dof / (ms * 1e-3) / 1e9 / gpus
+        return {"ms": ms, "dof_per_s": dof / (ms * 1e-3), "bytes_per_dof": bytes_per_dof, "gbs_per_gpu": gbs,
+                "frac_of_hbm_peak": gbs / peak}
+
     res = {}
     if world == 1:
+        # ---- config 1: the reference's CPU-runnable case, host numbers in, host solution out --------------------
+        bc1 = dict(bc_left="dirichlet", bc_right="dirichlet", g_left=1.0, g_right=0.0)
+        lat = {}
+        for name, kw in (("dirichlet_rows", bc1), ("notebook_neumann_sommerfeld", {})):
+            fh.solve_helmholtz_fem(999, 10.0, **kw)
+            ts = []
+            for _ in range(20):
+                t0 = time.perf_counter()
+                nodes, u = fh.solve_helmholtz_fem(999, 10.0, **kw)
+                ts.append(time.perf_counter() - t0)
+            A, b = fh.assembly(999, 10.0, 1.0 / 999, **kw)
+            be = float(A.residual(torch.from_numpy(u).reshape(1, -1))["backward"][0])
+            lat[name] = {"host_to_host_ms": 1e3 * statistics.median(ts), "backward_error": be}
+        res["config1_N999_k10"] = dict(lat, api="solve_helmholtz_fem(999, 10.0): mesh, assembly, solve, D2H of u",
+                                       note="152 KB of traffic: launch- and PCIe-latency bound, no roofline fraction; "
+                                            "the reference takes 117 ms (8 cores, SURVEY.md section 6)")
+        # ---- configs 2 / 5: one mesh of 1e6 elements ------------------------------------------------------------
         N = 1_000_000
         for name, k in (("config2_N1e6_k10", 10.0), ("config5_N1e6_k1000_robin", 1000.0)):
             staged, fused = fem1d.LargeMeshPlan(N), fem1d.LargeMeshPlan(N, fused=True)
-            ms_s, ms_f = timed(lambda: staged.solve(k), cold=True), timed(lambda: fused.solve(k), cold=True)
-            dev_mod = float((fused.solve(k).abs() - 1.0).abs().max().item())  # exact discrete solution: |u_j| = 1
-            res[name] = {"staged_assemble_plus_solve_ms": ms_s, "staged_dof_per_s": (N + 1) / (ms_s * 1e-3),
-                         "fused_ms": ms_f, "fused_dof_per_s": (N + 1) / (ms_f * 1e-3),
-                         "max_dev_from_unit_modulus": dev_mod, "l2": "flushed between repetitions",
-                         "api": "fem1d.LargeMeshPlan(N).solve(k): one CUDA graph replay per wavenumber"}
+            entry = {"rows": N + 1, "api": "fem1d.LargeMeshPlan(N).solve(k): one CUDA graph replay per wavenumber"}
+            for label, plan, bpd in (("staged", staged, BYTES_ASSEMBLY + BYTES_LARGE_SOLVE), ("fused", fused, BYTES_LARGE_FUSED)):
+                cold, warm = timed(lambda: plan.solve(k), cold=True), timed(lambda: plan.solve(k))
+                plan.solve(k)
+                entry[label] = {"cold_l2": rate(N + 1, cold, bpd), "warm_l2": rate(N + 1, warm, bpd),
+                                "backward_error": plan.backward_error(), "status": int(plan.status.item())}
+            entry["max_dev_from_unit_modulus"] = float((fused.solve(k).abs() - 1.0).abs().max().item())
+            entry["note"] = ("152-226 MB of traffic = 23-35 us at the HBM peak and less than the 126 MB L2 once warm: "
+                             "bound by its dependent launches, the fractions say how far")
+            res[name] = entry
             del staged, fused
+    # ---- config 4: N = 2^27, one slab per rank ----------------------------------------------------------------------
     N4, k4 = 2**27, 1000.0
-    entry = {"ranks": world, "rows": N4 + 1, "api": "distributed.PartitionedPlan(N).solve(k), rows generated",
-             "timing": "CUDA events around solve(k), max over ranks, median of 10"}
-    plan = D.PartitionedPlan(N4, use_graph=False)
-    ms = timed(lambda: plan.solve(k4))
-    dev_mod = (plan.solve(k4)[2].abs() - 1.0).abs().max().reshape(1).to(torch.float64)
-    if dist is not None:
-        dist.all_reduce(dev_mod, op=dist.ReduceOp.MAX)
-    entry.update({"call_by_call_ms": ms, "call_by_call_dof_per_s": (N4 + 1) / (ms * 1e-3),
-                  "max_dev_from_unit_modulus": float(dev_mod.item()), "singular": plan.singular()})
-    del plan
-    if world == 1:  # one CUDA graph per solve (with more ranks the graph holds NCCL kernels: measured with
-        # tools/plan_probe.py -- 2 / 4 GPUs: 0.32 / 0.22 ms --, kept out of the bench run)
-        plan = D.PartitionedPlan(N4, use_graph=True)
+    entry = {"ranks": world, "rows": N4 + 1, "api": "distributed.PartitionedPlan(N).solve(k)",
+             "timing": "CUDA events around solve(k), max over ranks, median of 10; inputs larger than L2",
+             "parity": "normwise backward error of the whole solution, measured on the device (rows re-generated; "
+                       "all-reduced over the ranks); bar 1e-10"}
+    for label, staged, bpd in (("generated_rows", False, BYTES_LARGE_FUSED), ("assembled_A", True, BYTES_ASSEMBLY + BYTES_LARGE_SOLVE)):
+        sub = {}
+        plan = D.PartitionedPlan(N4, use_graph=False, staged=staged)
+        ms = timed(lambda: plan.solve(k4))
+        plan.solve(k4)
+        sub["call_by_call"] = rate(N4 + 1, ms, bpd, world)
+        sub["backward_error"] = plan.backward_error()
+        sub["status_flags"] = plan.flags()
+        if not staged:
+            dev_mod = (plan.u.abs() - 1.0).abs().max().reshape(1).to(torch.float64)
+            if dist is not None:
+                dist.all_reduce(dev_mod, op=dist.ReduceOp.MAX)
+            sub["max_dev_from_unit_modulus"] = float(dev_mod.item())
+        del plan
+        torch.cuda.empty_cache()
+        # the whole sequence (NCCL all-gather included) as one CUDA graph per rank
+        plan = D.PartitionedPlan(N4, use_graph=True, staged=staged)
         try:
-            if plan.graph is not None:
+            has = torch.tensor([1 if plan.graph is not None else 0], dtype=torch.int32, device=dev)
+            if dist is not None:
+                dist.all_reduce(has, op=dist.ReduceOp.MIN)
+            if int(has.item()) == 1:
                 ms = timed(lambda: plan.solve(k4))
-                entry.update({"graph_ms": ms, "graph_dof_per_s": (N4 + 1) / (ms * 1e-3),
-                              "graph_write_gbs_per_gpu": 16 * (N4 + 1) / (ms * 1e-3) / 1e9})
+                plan.solve(k4)
+                sub["graph"] = rate(N4 + 1, ms, bpd, world)
+                sub["graph_backward_error"] = plan.backward_error()
         finally:
             plan.close()
+            del plan
+            torch.cuda.empty_cache()
+        entry[label] = sub
     res["config4_N2^27_k1000"] = entry
+    # ---- strong-scaling sweep + the final gather ------------------------------------------
+    if world > 1:
+        n, n_k = N_ELEM + 1, N_K_PER_GPU // world
+        ks = np.linspace(K_MIN, K_MAX, N_K_PER_GPU)[rank::world]
+        out = torch.empty((n_k, n), dtype=torch.complex128, device=dev)
+
+        def sweep():
+            fem1d.solve_helmholtz_sweep(N_ELEM, ks, out=out, check_singular=False)
+
+        ms = timed(sweep, reps=5)
+        full = torch.empty((world * n_k, n, 2), dtype=torch.float64, device=dev)
+        src = torch.view_as_real(out)
+        ms_g = timed(lambda: dist.all_gather_into_tensor(full, src), reps=5)
+        total_bytes = world * n_k * n * 16
+        res["sweep_strong_scaling"] = {
+            "n_k_total": N_K_PER_GPU, "n_k_per_rank": n_k, "ranks": world,
+            "api": "fem1d.solve_helmholtz_sweep on ks[rank::world] (default pipeline: one pass, A kept), host call included",
+            "ms": ms, "dof_per_s": N_K_PER_GPU * n / (ms * 1e-3),
+            "gather": {"api": "dist.all_gather_into_tensor of the solution shards (every rank ends with all 4.3 GB)",
+                       "ms": ms_g, "bytes_total": total_bytes,
+                       "algbw_gbs": total_bytes / (ms_g * 1e-3) / 1e9,
+                       "per_gpu_receive_gbs": total_bytes * (world - 1) / world / (ms_g * 1e-3) / 1e9}}
+        del full, out
     return res
 
 

@@ -46,6 +46,13 @@ _SIGNATURES = {
     "fh_element_matrices_1d": (C.c_int, [C.c_double, C.c_double, C.c_double, _P, _P, _P]),
     "fh_boundary_matrices_1d": (C.c_int, [C.c_double, C.c_double, _P, _P, _P]),
     "fh_assemble_1d_c128": (C.c_int, [C.POINTER(Problem1d), _P, _P, C.c_int64, _P, _P, _P, _P, _P]),
+    "fh_assemble_1d_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int64]),
+    "fh_assemble_1d_ws_c128": (C.c_int, [C.POINTER(Problem1d), _P, _P, C.c_int64, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "fh_assemble_1d_slab_c128": (C.c_int, [C.POINTER(Problem1d), C.c_double, C.c_double, _P, C.c_int64, C.c_int64, _P, _P,
+                                           _P, _P, _P]),
+    "fh_helmholtz1d_residual_workspace_bytes": (C.c_size_t, []),
+    "fh_helmholtz1d_residual_c128": (C.c_int, [C.POINTER(Problem1d), C.c_double, C.c_double, _P, C.c_int64, C.c_int64, _P,
+                                               _P, _P, _P, _P, C.c_size_t, _P]),
     "fh_tridiag_batched_max_n": (C.c_int64, []),
     "fh_tridiag_solve_batched_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "fh_tridiag_solve_batched_c128": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, _P,

@@ -133,6 +133,31 @@ assemble1d_table_kernel(Problem1d p, const double *__restrict__ geom, const doub
     }
 }
 
+// One wavenumber, a contiguous range of mesh rows [row_begin, row_begin + n_rows): the slab of one rank of the partitioned
+// solve (BASELINE config 4 with A materialised), or a window of a long mesh.  Same structured fill; (k, k**2) may live in
+// device memory (kk != NULL) so that a captured graph can be replayed for another wavenumber.
+__global__ void __launch_bounds__(kAsmThreads)
+assemble1d_slab_kernel(Problem1d p, double k, double k2, const double *__restrict__ kk, int64_t row_begin,
+                       int64_t n_rows, int64_t per_block, cplx *__restrict__ dl, cplx *__restrict__ d,
+                       cplx *__restrict__ du, cplx *__restrict__ b) {
+    const int64_t o_begin = static_cast<int64_t>(blockIdx.x) * per_block;
+    const int64_t o_end = min(n_rows, o_begin + per_block);
+    if (o_begin >= o_end) return;
+    if (kk != nullptr) k = __ldg(kk), k2 = __ldg(kk + 1);
+    const bool scalar = p.h_mode == FH_H_SCALAR && p.n_elem >= 2;
+    cplx il = czero(), id = czero(), iu = czero(), ib = czero();
+    if (scalar) row_values(p, row_geom(p, 1), 1, k, k2, il, id, iu, ib);
+    for (int64_t o = o_begin + threadIdx.x; o < o_end; o += kAsmThreads) {
+        const int64_t j = row_begin + o;
+        cplx vl = il, vd = id, vu = iu, vb = ib;
+        if (!scalar || j == 0 || j == p.n_elem) row_values(p, row_geom(p, j), j, k, k2, vl, vd, vu, vb);
+        stg_stream(dl + o, vl);
+        stg_stream(d + o, vd);
+        stg_stream(du + o, vu);
+        stg_stream(b + o, vb);
+    }
+}
+
 __global__ void shape1d_kernel(double xi, double *phi, double *dphi) {
     double a[2], c[2];
     shape1d(xi, a, c);
@@ -183,8 +208,9 @@ int fh_boundary_matrices_1d(double k, double cos_theta, fh_c128 *Ne2, fh_c128 *S
     return FH_OK;
 }
 
-int fh_assemble_1d_c128(const fh_problem1d *prob_host, const double *ks, const double *k2s, int64_t n_k,
-                        fh_c128 *dl, fh_c128 *d, fh_c128 *du, fh_c128 *b, fh_stream_t stream) {
+static int assemble_impl(const fh_problem1d *prob_host, const double *ks, const double *k2s, int64_t n_k, fh_c128 *dl,
+                         fh_c128 *d, fh_c128 *du, fh_c128 *b, void *workspace, size_t workspace_bytes,
+                         fh_stream_t stream) {
     fh::Problem1d p;
     int rc = fh::problem_from_host(prob_host, p);
     if (rc != FH_OK) return rc;
@@ -207,38 +233,25 @@ int fh_assemble_1d_c128(const fh_problem1d *prob_host, const double *ks, const d
     }
     const int64_t row_blocks = (n + fh::kAsmThreads - 1) / fh::kAsmThreads;
     FH_REQUIRE(row_blocks < (1ll << 31), "mesh too large for one launch");
-    if (n_k >= 8) {  // many wavenumbers: geometry table (stream-ordered scratch, 48 B per row) + structured fill
-        {   // keep freed scratch in the device's default pool (released at synchronisation points otherwise: every call
-            // would go back to the driver for 200 KB)
-            static int configured_device = -1;
-            int dev = 0;
-            cudaMemPool_t pool;
-            if (cudaGetDevice(&dev) == cudaSuccess && dev != configured_device &&
-                cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-                unsigned long long keep = 64ull << 20;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-                configured_device = dev;
-            }
-        }
-        double *geom = nullptr;
-        if (cudaMallocAsync(reinterpret_cast<void **>(&geom), sizeof(double) * 6 * (size_t)n, st) == cudaSuccess) {
-            fh::row_geometry_kernel<<<(unsigned)row_blocks, fh::kAsmThreads, 0, st>>>(p, geom);
-            const int64_t total = n_k * n;
-            int64_t slabs = 8ll * fh::sm_count();
-            int64_t per = (total + slabs - 1) / slabs;
-            per = ((per + fh::kAsmThreads - 1) / fh::kAsmThreads) * fh::kAsmThreads;
-            slabs = (total + per - 1) / per;
-            fh::assemble1d_table_kernel<<<(unsigned)slabs, fh::kAsmThreads, 0, st>>>(
-                p, geom, ks, k2s, n_k, per, reinterpret_cast<fh::cplx *>(dl), reinterpret_cast<fh::cplx *>(d),
-                reinterpret_cast<fh::cplx *>(du), reinterpret_cast<fh::cplx *>(b));
-            FH_CUDA(cudaFreeAsync(geom, st));
-            FH_LAUNCH_CHECK("assemble1d_table_kernel");
-            return FH_OK;
-        }
-        (void)cudaGetLastError();  // no stream-ordered allocator: fall through to the row-tiled kernel
+    if (workspace != nullptr && workspace_bytes >= sizeof(double) * 6 * (size_t)n) {
+        // caller-supplied scratch: geometry table (48 B per row, evaluated once) + structured fill
+        double *geom = static_cast<double *>(workspace);
+        fh::row_geometry_kernel<<<(unsigned)row_blocks, fh::kAsmThreads, 0, st>>>(p, geom);
+        FH_LAUNCH_CHECK("row_geometry_kernel");
+        const int64_t total = n_k * n;
+        int64_t slabs = 8ll * fh::sm_count();
+        int64_t per = (total + slabs - 1) / slabs;
+        per = ((per + fh::kAsmThreads - 1) / fh::kAsmThreads) * fh::kAsmThreads;
+        slabs = (total + per - 1) / per;
+        fh::assemble1d_table_kernel<<<(unsigned)slabs, fh::kAsmThreads, 0, st>>>(
+            p, geom, ks, k2s, n_k, per, reinterpret_cast<fh::cplx *>(dl), reinterpret_cast<fh::cplx *>(d),
+            reinterpret_cast<fh::cplx *>(du), reinterpret_cast<fh::cplx *>(b));
+        FH_LAUNCH_CHECK("assemble1d_table_kernel");
+        return FH_OK;
     }
-    // Split the k range so that the grid covers every SM several times even for short meshes,
-    // while each thread still amortises its geometry over a slab of wavenumbers.
+    // No scratch: the row-tiled kernel (every thread owns a mesh row and evaluates its geometry itself).  Split the k
+    // range so that the grid covers every SM several times even for short meshes, while each thread still amortises
+    // its geometry over a slab of wavenumbers.
     const int64_t want_blocks = 8ll * fh::sm_count();
     int64_t k_splits = (want_blocks + row_blocks - 1) / row_blocks;
     if (k_splits < 1) k_splits = 1;
@@ -251,6 +264,44 @@ int fh_assemble_1d_c128(const fh_problem1d *prob_host, const double *ks, const d
         p, ks, k2s, n_k, k_per_block, reinterpret_cast<fh::cplx *>(dl), reinterpret_cast<fh::cplx *>(d),
         reinterpret_cast<fh::cplx *>(du), reinterpret_cast<fh::cplx *>(b));
     FH_LAUNCH_CHECK("assemble1d_kernel");
+    return FH_OK;
+}
+
+int fh_assemble_1d_c128(const fh_problem1d *prob_host, const double *ks, const double *k2s, int64_t n_k,
+                        fh_c128 *dl, fh_c128 *d, fh_c128 *du, fh_c128 *b, fh_stream_t stream) {
+    return assemble_impl(prob_host, ks, k2s, n_k, dl, d, du, b, nullptr, 0, stream);
+}
+
+size_t fh_assemble_1d_workspace_bytes(int64_t n_elem, int h_mode, int64_t n_k) {
+    // worth it from a handful of wavenumbers on: the table costs one pass over the mesh
+    return (h_mode == FH_H_NODAL && n_k >= 8 && n_elem >= 1) ? sizeof(double) * 6 * (size_t)(n_elem + 1) : 0;
+}
+
+int fh_assemble_1d_ws_c128(const fh_problem1d *prob_host, const double *ks, const double *k2s, int64_t n_k,
+                           fh_c128 *dl, fh_c128 *d, fh_c128 *du, fh_c128 *b, void *workspace, size_t workspace_bytes,
+                           fh_stream_t stream) {
+    return assemble_impl(prob_host, ks, k2s, n_k, dl, d, du, b, workspace, workspace_bytes, stream);
+}
+
+int fh_assemble_1d_slab_c128(const fh_problem1d *prob_host, double k, double k2, const double *k_k2_dev,
+                             int64_t row_begin, int64_t n_rows, fh_c128 *dl, fh_c128 *d, fh_c128 *du, fh_c128 *b,
+                             fh_stream_t stream) {
+    fh::Problem1d p;
+    int rc = fh::problem_from_host(prob_host, p);
+    if (rc != FH_OK) return rc;
+    FH_REQUIRE(row_begin >= 0 && n_rows >= 0 && row_begin + n_rows <= p.n_elem + 1,
+               "row range [%lld, %lld) outside the mesh of %lld nodes", (long long)row_begin,
+               (long long)(row_begin + n_rows), (long long)(p.n_elem + 1));
+    if (n_rows == 0) return FH_OK;
+    FH_REQUIRE(dl && d && du && b, "NULL device pointer");
+    int64_t slabs = 8ll * fh::sm_count();
+    int64_t per = (n_rows + slabs - 1) / slabs;
+    per = ((per + fh::kAsmThreads - 1) / fh::kAsmThreads) * fh::kAsmThreads;
+    slabs = (n_rows + per - 1) / per;
+    fh::assemble1d_slab_kernel<<<(unsigned)slabs, fh::kAsmThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        p, k, k2, k_k2_dev, row_begin, n_rows, per, reinterpret_cast<fh::cplx *>(dl), reinterpret_cast<fh::cplx *>(d),
+        reinterpret_cast<fh::cplx *>(du), reinterpret_cast<fh::cplx *>(b));
+    FH_LAUNCH_CHECK("assemble1d_slab_kernel");
     return FH_OK;
 }
 

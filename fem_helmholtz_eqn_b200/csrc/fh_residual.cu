@@ -1,7 +1,7 @@
 // Residual / parity metrics of a batch of tridiagonal systems, on device (gate G3):
 // out[s] = { ||b - A u||_2^2, ||u||_2^2, ||b||_2^2, ||A||_inf }.  One CTA per system (grid-stride),
 // coalesced streaming reads (96 B per row), fixed-shape tree reductions => deterministic results.
-#include "fh_common.cuh"
+#include "fh_helm1d.cuh"
 
 namespace fh {
 
@@ -109,6 +109,108 @@ extern "C" int fh_tridiag_residual_c128(const fh_c128 *dl, const fh_c128 *d, con
         reinterpret_cast<const cplx *>(dl), reinterpret_cast<const cplx *>(d), reinterpret_cast<const cplx *>(du),
         reinterpret_cast<const cplx *>(b), reinterpret_cast<const cplx *>(u), n, batch, out4);
     FH_LAUNCH_CHECK("residual_kernel");
+    return FH_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The same metrics for GENERATED rows (the fused / partitioned solvers never store A): rows [row_begin, row_begin + n_rows)
+// of the Helmholtz system of wavenumber k are re-generated from (h, k) -- bit-identical to fh_assemble_1d_c128 -- and
+// applied to the slab of the solution; 16 B per row of HBM traffic (u is read once; the neighbours come from L1/L2).
+// The two unknowns next to the slab (previous rank's last, next rank's first) are passed as pointers.  Every CTA leaves
+// its partial sums in the workspace, the last CTA to finish folds them in a fixed order (deterministic) into
+// out4 = { sum |b - A u|^2, sum |u|^2, sum |b|^2, max row sum of |A| } of this slab: partial sums of a rank; the caller
+// adds (max for the fourth) over the ranks.
+namespace fh {
+constexpr int kGenResCtasMax = 2048;
+struct GenResWs {
+    double part[kGenResCtasMax][4];
+    unsigned int done;
+};
+
+__global__ void __launch_bounds__(kResThreads)
+residual_generated_kernel(Problem1d p, double k, double k2, const double *__restrict__ kk, int64_t row_begin,
+                          int64_t n_rows, const cplx *__restrict__ u, const cplx *__restrict__ u_left,
+                          const cplx *__restrict__ u_right, GenResWs *__restrict__ ws, double *__restrict__ out4) {
+    __shared__ double red[4][kResThreads / 32];
+    __shared__ bool last;
+    if (kk != nullptr) k = __ldg(kk), k2 = __ldg(kk + 1);
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const bool scalar = p.h_mode == FH_H_SCALAR && p.n_elem >= 2;
+    cplx il = czero(), id = czero(), iu = czero(), ib = czero();
+    if (scalar) row_values(p, row_geom(p, 1), 1, k, k2, il, id, iu, ib);
+    const double irow = hypot(il.re, il.im) + hypot(id.re, id.im) + hypot(iu.re, iu.im);
+    double r2 = 0.0, u2 = 0.0, b2 = 0.0, amax = 0.0;
+    for (int64_t o = (int64_t)blockIdx.x * kResThreads + t; o < n_rows; o += (int64_t)gridDim.x * kResThreads) {
+        const int64_t j = row_begin + o;
+        cplx lo = il, di = id, hi = iu, rh = ib;
+        double rowsum = irow;
+        if (!scalar || j == 0 || j == p.n_elem) {
+            row_values(p, row_geom(p, j), j, k, k2, lo, di, hi, rh);
+            rowsum = hypot(di.re, di.im) + (j > 0 ? hypot(lo.re, lo.im) : 0.0) + (j < p.n_elem ? hypot(hi.re, hi.im) : 0.0);
+        }
+        const cplx uj = u[o];
+        cplx r = nmsub(rh, di, uj);
+        if (j > 0) r = nmsub(r, lo, o > 0 ? u[o - 1] : (u_left != nullptr ? *u_left : czero()));
+        if (j < p.n_elem) r = nmsub(r, hi, o + 1 < n_rows ? u[o + 1] : (u_right != nullptr ? *u_right : czero()));
+        r2 += r.re * r.re + r.im * r.im;
+        u2 += uj.re * uj.re + uj.im * uj.im;
+        b2 += rh.re * rh.re + rh.im * rh.im;
+        amax = fmax(amax, rowsum);
+    }
+    r2 = warp_sum(r2), u2 = warp_sum(u2), b2 = warp_sum(b2), amax = warp_max(amax);
+    if (lane == 0) red[0][warp] = r2, red[1][warp] = u2, red[2][warp] = b2, red[3][warp] = amax;
+    __syncthreads();
+    if (t == 0) {
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+        for (int w = 0; w < kResThreads / 32; ++w) v0 += red[0][w], v1 += red[1][w], v2 += red[2][w], v3 = fmax(v3, red[3][w]);
+        double *mine = ws->part[blockIdx.x];
+        mine[0] = v0, mine[1] = v1, mine[2] = v2, mine[3] = v3;
+        __threadfence();
+        last = atomicAdd(&ws->done, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && t == 0) {  // (<= 2048 partial sums: a fixed-order serial fold keeps the result reproducible)
+        __threadfence();
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+        for (unsigned c = 0; c < gridDim.x; ++c) {
+            const volatile double *q = ws->part[c];
+            v0 += q[0], v1 += q[1], v2 += q[2], v3 = fmax(v3, q[3]);
+        }
+        out4[0] = v0, out4[1] = v1, out4[2] = v2, out4[3] = v3;
+        ws->done = 0;  // ready for the next launch (graph replays)
+    }
+}
+}  // namespace fh
+
+extern "C" size_t fh_helmholtz1d_residual_workspace_bytes(void) { return sizeof(fh::GenResWs); }
+
+extern "C" int fh_helmholtz1d_residual_c128(const fh_problem1d *prob_host, double k, double k2, const double *k_k2_dev,
+                                            int64_t row_begin, int64_t n_rows, const fh_c128 *u, const fh_c128 *u_left,
+                                            const fh_c128 *u_right, double *out4, void *workspace,
+                                            size_t workspace_bytes, fh_stream_t stream) {
+    using namespace fh;
+    Problem1d p;
+    int rc = problem_from_host(prob_host, p);
+    if (rc != FH_OK) return rc;
+    FH_REQUIRE(row_begin >= 0 && n_rows >= 1 && row_begin + n_rows <= p.n_elem + 1,
+               "row range [%lld, %lld) outside the mesh of %lld nodes", (long long)row_begin,
+               (long long)(row_begin + n_rows), (long long)(p.n_elem + 1));
+    FH_REQUIRE(u && out4 && workspace, "NULL device pointer");
+    FH_REQUIRE(workspace_bytes >= sizeof(GenResWs), "workspace too small (fh_helmholtz1d_residual_workspace_bytes)");
+    FH_REQUIRE(row_begin == 0 || u_left != nullptr, "u_left is needed unless the slab starts at mesh row 0");
+    FH_REQUIRE(row_begin + n_rows == p.n_elem + 1 || u_right != nullptr, "u_right is needed unless the slab ends the mesh");
+    int64_t grid = 8ll * sm_count();
+    const int64_t need = (n_rows + kResThreads - 1) / kResThreads;
+    if (grid > need) grid = need;
+    if (grid > kGenResCtasMax) grid = kGenResCtasMax;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GenResWs *ws = static_cast<GenResWs *>(workspace);
+    // (the counter is zero after every completed launch; the first use of a fresh workspace needs it cleared)
+    FH_CUDA(cudaMemsetAsync(&ws->done, 0, sizeof(unsigned int), st));
+    residual_generated_kernel<<<(unsigned)grid, kResThreads, 0, st>>>(
+        p, k, k2, k_k2_dev, row_begin, n_rows, reinterpret_cast<const cplx *>(u), reinterpret_cast<const cplx *>(u_left),
+        reinterpret_cast<const cplx *>(u_right), ws, out4);
+    FH_LAUNCH_CHECK("residual_generated_kernel");
     return FH_OK;
 }
 

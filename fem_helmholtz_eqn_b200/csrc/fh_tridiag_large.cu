@@ -34,6 +34,32 @@ constexpr int kMaxLevels = 16;
 
 __device__ __forceinline__ int lswz(int r) { return r ^ ((r >> 4) & 7); }
 
+// A-posteriori accuracy probe, the large-system counterpart of the batched kernel's (fh_tridiag_dev.cuh): the chunked
+// elimination is unpivoted; what it can lose shows up as a defect of a chunk's two INTERFACE equations (first and last
+// row of the chunk, which became rows of the next level) when they are re-evaluated with the computed solution --
+// interior rows are satisfied by construction of the back-substitution.  A defect of a level-l row is a residual of the
+// ORIGINAL system at that row (the reduced row is the original one minus multiples of interior rows, which hold), so it
+// is measured in units of the original system: |r| <= tau (||A||_inf max|x_neighbourhood| + |d|) on every probed row
+// bounds the normwise backward error by ~2 tau.  (Measured against the reduced row's own entries -- which shrink by 16x
+// per level on a fine mesh -- the same defects look up to 1e6 times larger than they are: tools/probe_large_stats.py.)
+// ||A||_inf: the level-0 reduction records the largest row sum it sees; generated rows take the interior row's.
+// Status bits as fh_tridiag_solve_batched_c128: bit 1 (2) defect > kLargeProbeTol -> refine; bit 0 (1) as well above
+// kLargeSevereTol or if not finite.
+constexpr double kLargeProbeTol = 5e-14, kLargeSevereTol = 1e-8;
+__device__ __forceinline__ double labs1(cplx z) { return fabs(z.re) + fabs(z.im); }
+#ifdef FH_PROBE_STAT  // development: the largest relative defect any probe has seen (tools/probe_large_stats.py)
+__device__ unsigned long long g_probe_max = 0ull;
+#endif
+__device__ __forceinline__ int probe_row(cplx a, cplx b, cplx c, cplx d, cplx xm, cplx x0, cplx xp, double anorm) {
+    const cplx r = nmsub(nmsub(nmsub(d, a, xm), b, x0), c, xp);
+    const double scale = anorm * fmax(fmax(labs1(xm), labs1(x0)), labs1(xp)) + labs1(d);
+    const double v = labs1(r);
+#ifdef FH_PROBE_STAT
+    if (scale > 0.0 && v == v) atomicMax(&g_probe_max, (unsigned long long)__double_as_longlong(v / scale));
+#endif
+    return v > kLargeSevereTol * scale ? 3 : (v > kLargeProbeTol * scale ? 2 : 0);  // (NaN: reported by the finite test)
+}
+
 struct LargeSmem {  // +8: a trailing 1-row tile is merged into its predecessor (1025 rows)
     cplx a[kLTile + 8], b[kLTile + 8], c[kLTile + 8], d[kLTile + 8];
 };
@@ -64,6 +90,8 @@ struct GlobalBands {  // rows of a level stored in global memory
     const cplx *dl, *d, *du, *b;
     int64_t n;
     int open_first, open_last;  // keep the coupling of the first / last row (slab of a larger system)
+    __device__ __forceinline__ bool open_first_row() const { return open_first != 0; }
+    __device__ __forceinline__ bool open_last_row() const { return open_last != 0; }
     __device__ __forceinline__ void fill(LargeSmem &sm, int64_t row0, int rows) const {
         for (int j = threadIdx.x; j < rows; j += kLT) {
             const int s = lswz(j);
@@ -88,6 +116,8 @@ struct HelmRows {  // level-0 rows generated from the Helmholtz problem: local r
     double k, k2;
     const double *kk = nullptr;  // device-resident (k, k**2): the periodic recursion only (see UniformRows)
     int64_t g_off, n;
+    __device__ __forceinline__ bool open_first_row() const { return g_off > 0; }
+    __device__ __forceinline__ bool open_last_row() const { return g_off + n - 1 < p.n_elem; }
     __device__ __forceinline__ void fill(LargeSmem &sm, int64_t row0, int rows) const {
         // scalar-h (the reference's mode): every interior row is the same -- evaluate it once per thread
         const bool scalar = p.h_mode == FH_H_SCALAR && p.n_elem >= 2;
@@ -108,7 +138,7 @@ struct HelmRows {  // level-0 rows generated from the Helmholtz problem: local r
 template <class Source>
 __global__ void __launch_bounds__(kLT, 3)
 large_reduce_kernel(Source src, cplx *__restrict__ ra, cplx *__restrict__ rb, cplx *__restrict__ rc,
-                    cplx *__restrict__ rd) {
+                    cplx *__restrict__ rd, unsigned long long *__restrict__ anorm_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LargeSmem &sm = *reinterpret_cast<LargeSmem *>(smem_raw);
     const int64_t n_tiles = tile_count(src.n);
@@ -119,6 +149,16 @@ large_reduce_kernel(Source src, cplx *__restrict__ ra, cplx *__restrict__ rb, cp
         const int t = threadIdx.x, r0 = t * kLM;
         const int nch = chunk_count(rows);
         const int len = t < nch ? (t == nch - 1 ? rows - r0 : kLM) : 0;  // 2..17 (1 only if n == 1)
+        if (anorm_out != nullptr) {  // level 0: ||A||_inf of the system, the unit of the back-substitution's probe
+            double rs = 0.0;
+            for (int i = 0; i < len; ++i) {
+                const int s = lswz(r0 + i);
+                rs = fmax(rs, labs1(sm.a[s]) + labs1(sm.b[s]) + labs1(sm.c[s]));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) rs = fmax(rs, __shfl_xor_sync(0xffffffffu, rs, o));
+            if ((t & 31) == 0) atomicMax(anorm_out, (unsigned long long)__double_as_longlong(rs));  // (>= 0: bit order)
+        }
         if (len >= 1) {
             cplx a1, b1, c1, d1, a2, b2, c2, d2;  // interface rows in the chunk's first / last unknown
             if (len == 1) {
@@ -161,9 +201,11 @@ large_reduce_kernel(Source src, cplx *__restrict__ ra, cplx *__restrict__ rb, cp
 // ---------------------------------------------------------------------------------------------- back-substitution
 template <class Source>
 __global__ void __launch_bounds__(kLT, 3)
-large_backsub_kernel(Source src, const cplx *__restrict__ xr, cplx *__restrict__ x, int32_t *__restrict__ status) {
+large_backsub_kernel(Source src, const cplx *__restrict__ xr, cplx *__restrict__ x, int32_t *__restrict__ status,
+                     const double *__restrict__ anorm_ptr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LargeSmem &sm = *reinterpret_cast<LargeSmem *>(smem_raw);
+    const double anorm = *anorm_ptr;
     const int64_t n_tiles = tile_count(src.n);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t row0 = tile * kLTile;
@@ -173,10 +215,15 @@ large_backsub_kernel(Source src, const cplx *__restrict__ xr, cplx *__restrict__
         const int nch = chunk_count(rows);
         const int len = t < nch ? (t == nch - 1 ? rows - r0 : kLM) : 0;
         bool bad = false;
+        int flag = 0;
         if (len >= 1) {
             const int64_t o = 2 * (tile * kLT + t);
             const cplx x0 = xr[o], xl = len > 1 ? xr[o + 1] : x0;
             bad = !cfinite(x0) || !cfinite(xl);
+            // the two interface equations of the chunk, kept for the probe (their right-hand sides are overwritten below)
+            const int sF = lswz(r0), sL = lswz(r0 + len - 1);
+            const cplx fa = sm.a[sF], fb = sm.b[sF], fc = sm.c[sF], fd = sm.d[sF];
+            const cplx la = sm.a[sL], lb = sm.b[sL], lc = sm.c[sL], ld = sm.d[sL];
             // interior rows 1 .. len-2: Thomas with the two known neighbours; c', d' overwrite the tile
             cplx cp = czero(), dp = x0;  // "row 0" acts as x_0 = x0
             for (int i = 1; i <= len - 2; ++i) {
@@ -196,10 +243,21 @@ large_backsub_kernel(Source src, const cplx *__restrict__ xr, cplx *__restrict__
                 sm.d[s] = xn;
             }
             sm.d[lswz(r0)] = x0;
+            if (len >= 2) {
+                const int64_t n_red = reduced_rows(src.n);
+                const cplx x1 = len > 2 ? sm.d[lswz(r0 + 1)] : xl, xm2 = len > 2 ? sm.d[lswz(r0 + len - 2)] : x0;
+                // the neighbours' unknowns: the previous chunk's last / the next chunk's first (a slab's outermost
+                // rows couple to another rank's unknown, which is not here: those two equations are skipped)
+                if (o > 0) flag |= probe_row(fa, fb, fc, fd, xr[o - 1], x0, x1, anorm);
+                else if (!src.open_first_row()) flag |= probe_row(czero(), fb, fc, fd, czero(), x0, x1, anorm);
+                if (o + 2 < n_red) flag |= probe_row(la, lb, lc, ld, xm2, xl, xr[o + 2], anorm);
+                else if (!src.open_last_row()) flag |= probe_row(la, lb, czero(), ld, xm2, xl, czero(), anorm);
+            }
         }
         const int any_bad = __syncthreads_or(bad ? 1 : 0);
         for (int j = threadIdx.x; j < rows; j += kLT) stg_stream(x + row0 + j, sm.d[lswz(j)]);
         if (any_bad && status != nullptr && threadIdx.x == 0) atomicOr(status, 1);
+        if (flag != 0 && status != nullptr) atomicOr(status, flag);  // (rare)
         __syncthreads();
     }
 }
@@ -447,11 +505,31 @@ __device__ void deep_reduce_levels(const UniformRows &u, const DeepPlan &dp, Dee
 // = 16 chunks per pass, 8 passes in flight (the end-value loads overlap): one "round" writes 128 chunks = 32 KB of
 // contiguous solution.  A thread keeps the same row-in-chunk i throughout.
 // (xr is NOT __restrict__ / read-only-cached: inside the single-CTA kernel it was written a level earlier)
-__device__ __forceinline__ bool deep_backsub_plain(const DeepConsts &C, int64_t c_begin, int64_t c_end,
-                                                   const cplx *xr, cplx *x) {
+// Probe of a plain chunk's two interface equations (rows 16 c and 16 c + 15 of the level: the constants E and O), by the
+// two threads that hold x(16 c + 1) and x(16 c + 14); the neighbouring chunks' unknowns are entries 2 c - 1 and 2 c + 2
+// of the level below (n_next entries), passed in by the caller.
+__device__ __forceinline__ int deep_probe_plain(const DeepConsts &C, double anorm, int i, cplx xi, cplx x_first,
+                                                cplx x_last, bool has_prev, cplx x_prev, bool has_next, cplx x_next) {
+    if (i == 1 && has_prev) {
+        const cplx *e = C.eo[0];
+        return probe_row(e[0], e[1], e[2], e[3], x_prev, x_first, xi, anorm);
+    }
+    if (i == kLM - 2 && has_next) {
+        const cplx *e = C.eo[1];
+        return probe_row(e[0], e[1], e[2], e[3], xi, x_last, x_next, anorm);
+    }
+    return 0;
+}
+// ||A||_inf of a generated system: the interior row's sum (the mesh-end rows hold half its diagonal)
+__device__ __forceinline__ double deep_anorm(const DeepConsts *cs) {
+    const cplx *e = cs[0].eo[0];
+    return labs1(e[0]) + labs1(e[1]) + labs1(e[2]);
+}
+__device__ __forceinline__ int deep_backsub_plain(const DeepConsts &C, double anorm, int64_t c_begin, int64_t c_end,
+                                                  const cplx *xr, int64_t n_next, cplx *x) {
     const int i = threadIdx.x & (kLM - 1);
     const cplx al = C.tab[0][i], be = C.tab[1][i], ga = C.tab[2][i];
-    bool bad = false;
+    int flag = 0;
     constexpr int kStep = kDeepThreads / kLM, kFly = 8;
     for (int64_t c0 = c_begin + (threadIdx.x >> 4); c0 < c_end; c0 += kFly * kStep) {
         cplx x0[kFly], xl[kFly];
@@ -465,21 +543,27 @@ __device__ __forceinline__ bool deep_backsub_plain(const DeepConsts &C, int64_t 
             const int64_t c = c0 + q * kStep;
             if (c < c_end) {
                 const cplx xi = cmadd(cmadd(ga, al, x0[q]), be, xl[q]);
-                bad |= !cfinite(xi);
+                flag |= cfinite(xi) ? 0 : 1;
                 stg_stream(x + c * kLM + i, xi);
+                if (i == 1 || i == kLM - 2) {
+                    const bool hp = c > 0, hn = 2 * c + 2 < n_next;
+                    flag |= deep_probe_plain(C, anorm, i, xi, x0[q], xl[q], hp, hp && i == 1 ? xr[2 * c - 1] : czero(),
+                                             hn, hn && i != 1 ? xr[2 * c + 2] : czero());
+                }
             }
         }
     }
-    return bad;
+    return flag;
 }
 // special chunk number s of level l (rows staged by deep_stage): Thomas sweep between the two known end values, one
 // thread; c', d' overwrite the staged rows
-__device__ __forceinline__ bool deep_backsub_special(const DeepLevel &L, DeepStage &sg, int s, const cplx *xr, cplx *x) {
+__device__ __forceinline__ int deep_backsub_special(const DeepLevel &L, double anorm, DeepStage &sg, int s,
+                                                    const cplx *xr, int64_t n_next, cplx *x) {
     const int64_t c = deep_special_chunk(L, s), r0 = c * kLM;
     const int len = sg.len[s];
     DeepRows &R = sg.rows[s];
     const cplx x0 = xr[2 * c], xl = xr[2 * c + 1];
-    bool bad = !cfinite(x0) || !cfinite(xl);
+    int flag = (cfinite(x0) && cfinite(xl)) ? 0 : 1;
     cplx cpv = czero(), dpv = x0;  // "row 0" acts as x_0 = x0
     for (int i = 1; i <= len - 2; ++i) {
         const cplx a = R[i][0];
@@ -488,15 +572,27 @@ __device__ __forceinline__ bool deep_backsub_special(const DeepLevel &L, DeepSta
         cpv = R[i][2] * inv;
         R[i][2] = cpv, R[i][3] = dpv;
     }
-    cplx xn = xl;
+    cplx xn = xl, x1 = xl, xm2 = x0;  // x(r0 + 1), x(r0 + len - 2)
     x[r0 + len - 1] = xl;
     for (int i = len - 2; i >= 1; --i) {
         xn = nmsub(R[i][3], R[i][2], xn);
-        bad |= !cfinite(xn);
+        flag |= cfinite(xn) ? 0 : 1;
         x[r0 + i] = xn;
+        if (i == len - 2) xm2 = xn;
+        x1 = xn;
     }
     x[r0] = x0;
-    return bad;
+    if (len >= 2) {  // probe: the chunk's two interface equations (rows 0 and len - 1 are untouched by the sweep)
+        // rows without a neighbour inside this slab: a mesh end has an exact zero there, a slab end couples to another
+        // rank's unknown (then the equation is skipped: its coefficient is non-zero)
+        const bool hp = c > 0, hn = 2 * c + 2 < n_next;
+        if (hp || (R[0][0].re == 0.0 && R[0][0].im == 0.0))
+            flag |= probe_row(R[0][0], R[0][1], R[0][2], R[0][3], hp ? xr[2 * c - 1] : czero(), x0, x1, anorm);
+        const cplx *q = R[len - 1];
+        if (hn || (q[2].re == 0.0 && q[2].im == 0.0))
+            flag |= probe_row(q[0], q[1], q[2], q[3], xm2, xl, hn ? xr[2 * c + 2] : czero(), anorm);
+    }
+    return flag;
 }
 __device__ __forceinline__ const cplx *deep_xr(const DeepPlan &dp, int l) { return dp.ptr[l + 1].x; }
 __device__ __forceinline__ cplx *deep_x(const DeepPlan &dp, int l, cplx *u_out) { return l == 0 ? u_out : dp.ptr[l].x; }
@@ -508,25 +604,29 @@ struct DeepStageSet {
 };
 __device__ void deep_backsub_small_levels(const UniformRows &u, const DeepPlan &dp, const DeepConsts *cs, DeepStageSet &set,
                                           cplx *u_out, int32_t *status) {
-    bool bad = false;
+    int flag = 0;
     int j = 0;
     for (int l = dp.levels - 1; l >= 0 && dp.lv[l].n <= kDeepSmall; --l, ++j)
         deep_stage(u, dp, cs, nullptr, l, false, set.lv[j], 32 * j);
     __syncthreads();
+    const double anorm = deep_anorm(cs);
     j = 0;
     for (int l = dp.levels - 1; l >= 0 && dp.lv[l].n <= kDeepSmall; --l, ++j) {
         const DeepLevel &L = dp.lv[l];
         const cplx *xr = deep_xr(dp, l);
         cplx *x = deep_x(dp, l, u_out);
+        const int64_t n_next = dp.lv[l + 1].n;
         // the special chunks go to lane 0 of the last warps, ahead of their share of the streaming part (the sweep is
         // the critical path of the level)
         const int w = (kDeepThreads >> 5) - 1 - (int)(threadIdx.x >> 5);
-        if (w < deep_special_count(L) && (threadIdx.x & 31) == 0) bad |= deep_backsub_special(L, set.lv[j], w, xr, x);
+        if (w < deep_special_count(L) && (threadIdx.x & 31) == 0)
+            flag |= deep_backsub_special(L, anorm, set.lv[j], w, xr, n_next, x);
         __syncwarp();
-        bad |= deep_backsub_plain(cs[l], L.clo, L.chi, xr, x);
+        flag |= deep_backsub_plain(cs[l], anorm, L.clo, L.chi, xr, n_next, x);
         __syncthreads();
     }
-    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0 && status != nullptr) atomicOr(status, 1);
+    flag = (int)__reduce_or_sync(0xffffffffu, (unsigned)flag);
+    if (flag != 0 && (threadIdx.x & 31) == 0 && status != nullptr) atomicOr(status, flag);
 }
 
 // multi-GPU piece 1: reduce the slab to its two interface rows (iface8 = a[2] b[2] c[2] d[2])
@@ -583,9 +683,9 @@ constexpr int kDeepStages = 4;
 struct DeepRing {
     cplx buf[kDeepStages][2 * 128];
 };
-__device__ __forceinline__ bool deep_backsub_plain_staged(const DeepConsts &C, int64_t c_begin, int64_t c_end,
-                                                          const cplx *__restrict__ xr, cplx *__restrict__ x,
-                                                          DeepRing &ring) {
+__device__ __forceinline__ int deep_backsub_plain_staged(const DeepConsts &C, double anorm, int64_t c_begin,
+                                                         int64_t c_end, const cplx *__restrict__ xr, int64_t n_next,
+                                                         cplx *__restrict__ x, DeepRing &ring) {
     const int t = threadIdx.x, i = t & (kLM - 1), cl = t >> 4;
     const cplx al = C.tab[0][i], be = C.tab[1][i], ga = C.tab[2][i];
     const int64_t rounds = (c_end - c_begin + 127) / 128;
@@ -595,7 +695,7 @@ __device__ __forceinline__ bool deep_backsub_plain_staged(const DeepConsts &C, i
         cp_async_commit();
     };
     for (int r = 0; r < kDeepStages - 1; ++r) fetch(r);
-    bool bad = false;
+    int flag = 0;
     for (int64_t r = 0; r < rounds; ++r) {
         asm volatile("cp.async.wait_group %0;" ::"n"(kDeepStages - 2) : "memory");  // this thread's share of round r
         __syncthreads();  // everybody's share has landed, and everybody is done with round r - 1 ...
@@ -606,13 +706,22 @@ __device__ __forceinline__ bool deep_backsub_plain_staged(const DeepConsts &C, i
         for (int q = 0; q < 8; ++q) {
             const int64_t c = c0 + 16 * q;
             if (c < c_end) {
-                const cplx xi = cmadd(cmadd(ga, al, b[2 * (cl + 16 * q)]), be, b[2 * (cl + 16 * q) + 1]);
-                bad |= !cfinite(xi);
+                const int lc = cl + 16 * q;  // chunk within the round
+                const cplx xf = b[2 * lc], xl = b[2 * lc + 1];
+                const cplx xi = cmadd(cmadd(ga, al, xf), be, xl);
+                flag |= cfinite(xi) ? 0 : 1;
                 stg_stream(x + c * kLM + i, xi);
+                if (i == 1 || i == kLM - 2) {  // two lanes per chunk: the accuracy probe (neighbours mostly in the ring)
+                    const bool hp = c > 0, hn = 2 * c + 2 < n_next;
+                    cplx xn = czero();
+                    if (i == 1 && hp) xn = lc > 0 ? b[2 * lc - 1] : xr[2 * c - 1];
+                    if (i != 1 && hn) xn = (lc < 127 && c + 1 < c_end) ? b[2 * lc + 2] : xr[2 * c + 2];
+                    flag |= deep_probe_plain(C, anorm, i, xi, xf, xl, hp, xn, hn, xn);
+                }
             }
         }
     }
-    return bad;
+    return flag;
 }
 
 // one large level: CTA 0 takes the special chunks, every other CTA streams `per` contiguous rounds of plain chunks
@@ -625,18 +734,22 @@ deep_backsub_level_kernel(UniformRows u, const __grid_constant__ DeepPlan dp, co
     const DeepLevel &L = dp.lv[l];
     const cplx *xr = deep_xr(dp, l);
     cplx *x = deep_x(dp, l, u_out);
-    bool bad = false;
+    const int64_t n_next = dp.lv[l + 1].n;
+    const double anorm = deep_anorm(cs);
+    int flag = 0;
     if (blockIdx.x == 0) {
         deep_stage(u, dp, cs, nullptr, l, false, sg);
         __syncthreads();
-        if ((int)threadIdx.x < deep_special_count(L)) bad = deep_backsub_special(L, sg, threadIdx.x, xr, x);
+        if ((int)threadIdx.x < deep_special_count(L))
+            flag = deep_backsub_special(L, anorm, sg, threadIdx.x, xr, n_next, x);
     } else {
         const int64_t b = blockIdx.x - 1;
         int64_t c_end = L.clo + (b + 1) * per * 128;
         if (c_end > L.chi) c_end = L.chi;
-        bad = deep_backsub_plain_staged(cs[l], L.clo + b * per * 128, c_end, xr, x, ring);
+        flag = deep_backsub_plain_staged(cs[l], anorm, L.clo + b * per * 128, c_end, xr, n_next, x, ring);
     }
-    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0 && status != nullptr) atomicOr(status, 1);
+    flag = (int)__reduce_or_sync(0xffffffffu, (unsigned)flag);
+    if (flag != 0 && (threadIdx.x & 31) == 0 && status != nullptr) atomicOr(status, flag);
 }
 
 // Tiny dense solve of the gathered interface system (2P rows, P = number of ranks): one thread,
@@ -692,6 +805,7 @@ struct LevelPlan {
     int levels;                     // number of reduced levels (level 0 is the caller's system)
     int64_t n[kMaxLevels + 1];      // rows per level
     size_t off[kMaxLevels + 1];     // byte offset of level l >= 1 inside the workspace (5 arrays of n[l])
+    size_t off_anorm;               // one double: ||A||_inf of level 0, recorded by its reduction (the probe's unit)
     size_t total;
 };
 
@@ -706,6 +820,8 @@ static LevelPlan plan_levels(int64_t n0, int64_t stop_at) {
         pl.total += 5 * sizeof(cplx) * (size_t)nn;
         pl.total = (pl.total + 255) & ~(size_t)255;
     }
+    pl.off_anorm = pl.total;
+    pl.total += 256;
     return pl;
 }
 
@@ -721,19 +837,24 @@ static unsigned grid_for(int64_t n) {
     return (unsigned)(tiles < cap ? (tiles < 1 ? 1 : tiles) : cap);
 }
 
+static unsigned long long *anorm_slot(void *ws, const LevelPlan &pl) {
+    return reinterpret_cast<unsigned long long *>(static_cast<char *>(ws) + pl.off_anorm);
+}
 template <class Source>
-static int launch_reduce(const Source &src, const LevelPtrs &out, cudaStream_t st) {
+static int launch_reduce(const Source &src, const LevelPtrs &out, unsigned long long *anorm_out, cudaStream_t st) {
     auto kern = large_reduce_kernel<Source>;
     FH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LargeSmem)));
-    kern<<<grid_for(src.n), kLT, sizeof(LargeSmem), st>>>(src, out.a, out.b, out.c, out.d);
+    if (anorm_out != nullptr) FH_CUDA(cudaMemsetAsync(anorm_out, 0, sizeof(unsigned long long), st));
+    kern<<<grid_for(src.n), kLT, sizeof(LargeSmem), st>>>(src, out.a, out.b, out.c, out.d, anorm_out);
     FH_LAUNCH_CHECK("large_reduce_kernel");
     return FH_OK;
 }
 template <class Source>
-static int launch_backsub(const Source &src, const cplx *xr, cplx *x, int32_t *status, cudaStream_t st) {
+static int launch_backsub(const Source &src, const cplx *xr, cplx *x, int32_t *status, const double *anorm,
+                          cudaStream_t st) {
     auto kern = large_backsub_kernel<Source>;
     FH_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LargeSmem)));
-    kern<<<grid_for(src.n), kLT, sizeof(LargeSmem), st>>>(src, xr, x, status);
+    kern<<<grid_for(src.n), kLT, sizeof(LargeSmem), st>>>(src, xr, x, status, anorm);
     FH_LAUNCH_CHECK("large_backsub_kernel");
     return FH_OK;
 }
@@ -816,8 +937,8 @@ static int reduce_all(const Source0 &src0, const LevelPlan &pl, void *ws, int op
                       cudaStream_t st) {
     for (int l = 0; l < pl.levels; ++l) {
         const LevelPtrs out = level_ptrs(ws, pl, l + 1);
-        int rc = l == 0 ? launch_reduce(src0, out, st)
-                        : launch_reduce(bands_of(level_ptrs(ws, pl, l), pl.n[l], open_first, open_last), out, st);
+        int rc = l == 0 ? launch_reduce(src0, out, anorm_slot(ws, pl), st)
+                        : launch_reduce(bands_of(level_ptrs(ws, pl, l), pl.n[l], open_first, open_last), out, nullptr, st);
         if (rc != FH_OK) return rc;
     }
     return FH_OK;
@@ -828,9 +949,10 @@ static int backsub_all(const Source0 &src0, const LevelPlan &pl, void *ws, int o
                        cplx *u, int32_t *status, cudaStream_t st) {
     for (int l = pl.levels - 1; l >= 0; --l) {
         const cplx *xr = level_ptrs(ws, pl, l + 1).x;
-        int rc = l == 0 ? launch_backsub(src0, xr, u, status, st)
+        const double *anorm = reinterpret_cast<const double *>(anorm_slot(ws, pl));
+        int rc = l == 0 ? launch_backsub(src0, xr, u, status, anorm, st)
                         : launch_backsub(bands_of(level_ptrs(ws, pl, l), pl.n[l], open_first, open_last), xr,
-                                         level_ptrs(ws, pl, l).x, status, st);
+                                         level_ptrs(ws, pl, l).x, status, anorm, st);
         if (rc != FH_OK) return rc;
     }
     return FH_OK;
@@ -848,8 +970,9 @@ static int solve_large_any(const Source0 &src0, cplx *u, int64_t n, int32_t *sta
     int rc = reduce_all(src0, pl, ws, 0, 0, st);
     if (rc != FH_OK) return rc;
     const LevelPtrs top = level_ptrs(ws, pl, pl.levels);
-    int32_t *coarse_status = nullptr;  // the batched kernel zeroes status[] itself; keep the OR semantics
-    rc = batched_solve_bands(top.a, top.b, top.c, top.d, top.x, pl.n[pl.levels], 1, coarse_status, st);
+    // (the batched kernel zeroes status[0] itself -- nothing has been flagged yet: the reductions do not write it -- and
+    // ORs in its own probe / breakdown bits; the back-substitution levels OR theirs on top)
+    rc = batched_solve_bands(top.a, top.b, top.c, top.d, top.x, pl.n[pl.levels], 1, status, st);
     if (rc != FH_OK) return rc;
     return backsub_all(src0, pl, ws, 0, 0, u, status, st);
 }
@@ -886,6 +1009,17 @@ static int kdev_unsupported() {
 }  // namespace fh
 
 extern "C" {
+
+#ifdef FH_PROBE_STAT
+__attribute__((visibility("default"))) double fh_debug_probe_max(int reset) {
+    unsigned long long v = 0ull, z = 0ull;
+    cudaMemcpyFromSymbol(&v, fh::g_probe_max, sizeof(v));
+    if (reset) cudaMemcpyToSymbol(fh::g_probe_max, &z, sizeof(z));
+    double d;
+    memcpy(&d, &v, sizeof(d));
+    return d;
+}
+#endif
 
 size_t fh_tridiag_solve_large_workspace_bytes(int64_t n) { return fh::solve_large_workspace_bytes(n); }
 

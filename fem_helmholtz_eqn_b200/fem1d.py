@@ -204,8 +204,11 @@ def assemble_bands(N, k, h, theta=0.0, *, bc_left="neumann", bc_right="sommerfel
         out = torch.empty((4, n_k, n), dtype=torch.complex128, device=dev)
     assert out.shape == (4, n_k, n) and out.dtype == torch.complex128 and out.is_contiguous()
     prob = _problem(N, h, theta, bc_left, bc_right, g_left, g_right, nodes_d)
-    check(lib.fh_assemble_1d_c128(C.byref(prob), ptr(ks_d), ptr(k2s_d), n_k, ptr(out[0]), ptr(out[1]),
-                                  ptr(out[2]), ptr(out[3]), stream_ptr()), "fh_assemble_1d_c128")
+    # non-uniform mesh, many wavenumbers: the row geometry is tabulated once in caller-owned scratch (48 B per row)
+    ws_bytes = lib.fh_assemble_1d_workspace_bytes(int(N), prob.h_mode, n_k)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
+    check(lib.fh_assemble_1d_ws_c128(C.byref(prob), ptr(ks_d), ptr(k2s_d), n_k, ptr(out[0]), ptr(out[1]),
+                                     ptr(out[2]), ptr(out[3]), ptr(ws), ws_bytes, stream_ptr()), "fh_assemble_1d_ws_c128")
     return out[0], out[1], out[2], out[3]
 
 
@@ -261,7 +264,7 @@ def refine_flagged(dl, d, du, b, u, status, sync=True, ws=None):
     lib = _lib.require_cuda()
     batch, n = d.shape
     if n > lib.fh_tridiag_batched_max_n():
-        return 0  # the large-system solver does not set the flag
+        return _refine_large(dl, d, du, b, u, status)
     own = ws is None
     if own:
         ws = _refine_workspace(n, batch, d.device)
@@ -279,6 +282,32 @@ def refine_flagged(dl, d, du, b, u, status, sync=True, ws=None):
         # of this shape (so that a later sync=False call covers it in one go)
         if own:
             ws = _refine_workspace(n, batch, d.device, min_systems=flagged + flagged // 4)
+
+
+def _refine_large(dl, d, du, b, u, status):
+    """:func:`refine_flagged` for systems too long for the batched kernel (n > 4112: the recursive-partition solver,
+    whose back-substitution carries the same interface-row probe).  These come one or a few at a time, so the loop is
+    driven from the host: r = b - A u, A e = r by the same solver, u += e.  The small-pivot bit is cleared; a breakdown
+    of the correction solve (non-finite, or again a severe defect) sets the breakdown bit, which sends the system to
+    :func:`repair_flagged` (verify, else pivoted re-solve)."""
+    lib = _lib.require_cuda()
+    batch, n = d.shape
+    st_host = status.cpu()
+    idx = [i for i in range(batch) if int(st_host[i]) & STATUS_SMALL_PIVOT]
+    if not idx:
+        return 0
+    ws_bytes = lib.fh_tridiag_solve_large_workspace_bytes(n)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=d.device)
+    r, e = torch.empty(n, dtype=torch.complex128, device=d.device), torch.empty(n, dtype=torch.complex128, device=d.device)
+    st_e = torch.zeros(1, dtype=torch.int32, device=d.device)
+    for i in idx:
+        check(lib.fh_tridiag_residual_vector_c128(ptr(dl[i]), ptr(d[i]), ptr(du[i]), ptr(b[i]), ptr(u[i]), n, 1, ptr(r),
+                                                  stream_ptr()), "fh_tridiag_residual_vector_c128")
+        check(lib.fh_tridiag_solve_large_c128(ptr(dl[i]), ptr(d[i]), ptr(du[i]), ptr(r), ptr(e), n, ptr(st_e), ptr(ws),
+                                              ws_bytes, stream_ptr()), "fh_tridiag_solve_large_c128")
+        u[i] += e
+        status[i:i + 1] = (status[i:i + 1] & ~STATUS_SMALL_PIVOT) | (st_e & STATUS_NONFINITE)
+    return len(idx)
 
 
 # What counts as repaired: three digits inside the 1e-10 contract (nb:204 / BASELINE north_star).  The unpivoted fast
@@ -439,11 +468,12 @@ def solve_helmholtz_sweep(N, ks, L=1.0, theta=0.0, *, bc_left="neumann", bc_righ
                 check(lib.fh_helmholtz1d_solve_large_fused_c128(
                     C.byref(prob), float(ks_h[i]), float(k2s_h[i]), ptr(U[i]), ptr(status[i:i + 1]), ptr(ws),
                     ws_bytes, stream_ptr()), "fh_helmholtz1d_solve_large_fused_c128")
-    if fused and n <= lib.fh_tridiag_batched_max_n():
+    if fused:
         idx = torch.nonzero(status != 0).flatten()
         if idx.numel() > 0:
-            # the fused kernel stores no bands: assemble them for the few flagged wavenumbers and solve those again
-            # through the staged path (refinement of small-pivot systems, pivoted re-solve of breakdowns)
+            # the fused kernels store no bands: assemble them for the few flagged wavenumbers (small-pivot probe or
+            # breakdown; short and long meshes alike) and solve those again through the staged path (refinement,
+            # verification, pivoted re-solve)
             sel = idx.cpu().numpy()
             bands = assemble_bands(N, (ks_h[sel], k2s_h[sel]), h, theta, bc_left=bc_left, bc_right=bc_right,
                                    g_left=g_left, g_right=g_right, nodes=nodes if nodal_h else None)
@@ -487,6 +517,31 @@ def assemble_and_solve(N, ks, L=1.0, theta=0.0, *, bc_left="neumann", bc_right="
     return bands, U, status
 
 
+class _WavenumberFeed:
+    """Hands (k, k**2) to device memory without blocking the host: a small ring of pinned host slots, each copied with
+    ``non_blocking=True`` and guarded by an event, so back-to-back ``solve(k)`` calls queue behind each other on the
+    stream instead of waiting for the previous replay (a pageable ``copy_`` is a cudaMemcpyAsync + stream
+    synchronise).  nb:185: ``k**2`` is evaluated on the host."""
+
+    def __init__(self, k_dev, depth=8):
+        self.k_dev = k_dev
+        self.slots = torch.empty((depth, 2), dtype=torch.float64).pin_memory()
+        self.events = [None] * depth
+        self.i = 0
+
+    def push(self, k):
+        i = self.i
+        self.i = (i + 1) % len(self.events)
+        if self.events[i] is not None:
+            self.events[i].synchronize()  # (only when the ring has wrapped onto a copy that is still queued)
+        self.slots[i, 0] = float(k)
+        self.slots[i, 1] = float(k**2)
+        self.k_dev.copy_(self.slots[i], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.events[i] = ev
+
+
 class LargeMeshPlan:
     """One long mesh, many solves (BASELINE configs 2 and 5: N = 10^6, a new wavenumber per call).  At that size the
     work is 0.15 GB -- tens of microseconds of HBM time -- and the path is bound by its nine dependent kernel launches
@@ -511,7 +566,9 @@ class LargeMeshPlan:
                     else lib.fh_tridiag_solve_batched_workspace_bytes(self.n, 1))
         self.ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
         self._prob = _problem(N, L / N, theta, bc_left, bc_right, g_left, g_right, None)
+        self._kw = dict(theta=theta, bc_left=bc_left, bc_right=bc_right, g_left=g_left, g_right=g_right)
         self.graph = None
+        self._feed = _WavenumberFeed(self.k_dev)
         self._set_k(1.0)
         self._launch()                      # warm-up: module load, function attributes, driver entry points
         torch.cuda.synchronize()
@@ -526,10 +583,7 @@ class LargeMeshPlan:
                 self._launch()
 
     def _set_k(self, k):
-        # nb:185: k**2 evaluated on the host.  A plain (pageable) 16-byte copy: it is staged by the driver before the
-        # call returns, so a second solve() may overwrite the host values while the first replay is still queued
-        # (a pinned buffer copied with non_blocking=True could not be reused that way).
-        self.k_dev.copy_(torch.tensor([float(k), float(k**2)], dtype=torch.float64))
+        self._feed.push(k)
 
     def _launch(self):
         lib, B = _lib.load(), self.bands
@@ -555,12 +609,29 @@ class LargeMeshPlan:
             self._launch()
         return self.U[0]
 
+    def backward_error(self):
+        """Normwise backward error ||b - A u|| / (||A||_inf ||u|| + ||b||) of the last solve, measured on the device:
+        the rows are re-generated (bit-identical to the assembled bands), 16 B per node read.  Synchronises."""
+        lib = _lib.load()
+        if getattr(self, "_res", None) is None:
+            dev = self.U.device
+            self._res = (torch.empty(lib.fh_helmholtz1d_residual_workspace_bytes(), dtype=torch.uint8, device=dev),
+                         torch.empty(4, dtype=torch.float64, device=dev))
+        ws, out = self._res
+        check(lib.fh_helmholtz1d_residual_c128(C.byref(self._prob), 0.0, 0.0, ptr(self.k_dev), 0, self.n, ptr(self.U),
+                                               None, None, ptr(out), ptr(ws), ws.numel(), stream_ptr()),
+              "fh_helmholtz1d_residual_c128")
+        r2, u2, b2, an = out.tolist()
+        return float(np.sqrt(r2) / (an * np.sqrt(u2) + np.sqrt(b2)))
+
     def solution(self, k):
         """``solve_helmholtz_fem(N, k)`` for this mesh: ``(nodes, u)`` as numpy arrays."""
         u = self.solve(k)
         out = u.cpu().numpy()
-        if int(self.status.item()) & STATUS_NONFINITE:      # rare: take the general path (pivoted re-solve)
-            return solve_helmholtz_fem(self.N, k, L=self.L)
+        if int(self.status.item()) != 0:
+            # rare: the probe of the unpivoted solve found a defect, or it broke down -- take the general staged path
+            # (refinement, verification against the 1e-13 bar, pivoted re-solve; LinAlgError only if singular)
+            return solve_helmholtz_fem(self.N, k, L=self.L, **self._kw)
         return np.linspace(0, self.L, self.N + 1), out
 
 

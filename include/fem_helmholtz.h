@@ -16,7 +16,8 @@
  *   - Return value: 0 = ok, < 0 = invalid argument (FH_E_*), > 0 = a cudaError_t.
  *     fh_last_error() returns a thread-local description of the last failure.
  *   - No exceptions cross the boundary; the library keeps no global mutable state besides the
- *     thread-local error string and one-time per-device kernel attribute setup.
+ *     thread-local error string and one-time per-device kernel attribute setup, and it never allocates
+ *     device memory (not even stream-ordered scratch).
  *   - Batched 1D arrays are batch-major: entry (system s, row j) lives at [s * n + j].
  *     Tridiagonal bands use n entries per system: dl[s][0] and du[s][n-1] are ignored.
  */
@@ -80,12 +81,23 @@ FH_API int fh_boundary_matrices_1d(double k, double cos_theta, fh_c128 *Ne2, fh_
 /* ---- assembly (replaces nb:134-187 `assembly`): A = -K + k^2 M + S as tridiagonal bands ---------
  * ks / k2s: device fp64[n_k]; k2s[i] must be the caller's k**2 (nb:185 evaluates it on the host).
  * dl, d, du, b: device complex128[n_k][N+1].  Values are bit-identical to the reference's dense A.
- * The one call that takes scratch space on its own: on a non-uniform mesh (FH_H_NODAL) with n_k >= 8 the k-independent
- * geometry of the rows (48 B per mesh row) is tabulated in stream-ordered memory (cudaMallocAsync / cudaFreeAsync on
- * `stream`, released inside the call; the device's default pool is told to keep 64 MB across synchronisations). */
+ * fh_assemble_1d_c128 allocates nothing and needs no scratch.  On a non-uniform mesh (FH_H_NODAL) with many wavenumbers
+ * fh_assemble_1d_ws_c128 is faster (0.97 instead of 0.63 of the HBM write peak): the k-independent geometry of the rows
+ * (48 B per mesh row) is tabulated once in a caller-supplied workspace of fh_assemble_1d_workspace_bytes() bytes (0 =
+ * no use for one: both calls then do the same). */
 FH_API int fh_assemble_1d_c128(const fh_problem1d *prob_host, const double *ks, const double *k2s,
                         int64_t n_k, fh_c128 *dl, fh_c128 *d, fh_c128 *du, fh_c128 *b,
                         fh_stream_t stream);
+FH_API size_t fh_assemble_1d_workspace_bytes(int64_t n_elem, int h_mode, int64_t n_k);
+FH_API int fh_assemble_1d_ws_c128(const fh_problem1d *prob_host, const double *ks, const double *k2s,
+                           int64_t n_k, fh_c128 *dl, fh_c128 *d, fh_c128 *du, fh_c128 *b, void *workspace,
+                           size_t workspace_bytes, fh_stream_t stream);
+/* One wavenumber, the mesh rows [row_begin, row_begin + n_rows) only: dl, d, du, b = device complex128[n_rows] (the slab
+ * of one rank of the partitioned solve with A materialised, BASELINE config 4; same values as the full assembly).
+ * k_k2_dev != NULL: (k, k**2) are read from device memory when the kernel runs (CUDA-graph replays), k / k2 are ignored. */
+FH_API int fh_assemble_1d_slab_c128(const fh_problem1d *prob_host, double k, double k2, const double *k_k2_dev,
+                             int64_t row_begin, int64_t n_rows, fh_c128 *dl, fh_c128 *d, fh_c128 *du, fh_c128 *b,
+                             fh_stream_t stream);
 
 /* ---- batched tridiagonal solve (replaces nb:204 `np.linalg.solve(A, b)` for tridiagonal A) ------
  * Thread-chunk partition (8 rows per thread in registers) + parallel cyclic reduction of the
@@ -190,6 +202,19 @@ FH_API int fh_helmholtz1d_spike_backsub_kdev_c128(const fh_problem1d *prob_host,
 FH_API int fh_tridiag_residual_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c128 *du, const fh_c128 *b,
                              const fh_c128 *u, int64_t n, int64_t batch, double *out4,
                              fh_stream_t stream);
+
+/* The same four numbers for GENERATED rows (the fused / partitioned solvers never store A): rows [row_begin, row_begin +
+ * n_rows) of the system of wavenumber k are re-generated (bit-identical to fh_assemble_1d_c128) and applied to the slab
+ * u = device complex128[n_rows] of the solution; u_left / u_right point at the unknowns next to the slab (NULL at a mesh
+ * end).  out4 (device fp64[4]) = { sum |b - A u|^2, sum |u|^2, sum |b|^2, max row sum |A| } over the slab: add (max for
+ * the fourth) over the ranks, then ||r|| / (||A||_inf ||u|| + ||b||) is the normwise backward error of the whole solve --
+ * the gate for meshes no dense reference can run (BASELINE configs 2 and 4; nb:204 is the solve it checks).
+ * k_k2_dev != NULL: (k, k**2) are read from device memory (graph replays).  16 B per row of HBM traffic. */
+FH_API size_t fh_helmholtz1d_residual_workspace_bytes(void);
+FH_API int fh_helmholtz1d_residual_c128(const fh_problem1d *prob_host, double k, double k2, const double *k_k2_dev,
+                                 int64_t row_begin, int64_t n_rows, const fh_c128 *u, const fh_c128 *u_left,
+                                 const fh_c128 *u_right, double *out4, void *workspace, size_t workspace_bytes,
+                                 fh_stream_t stream);
 
 /* Pivoted fallback (LAPACK zgtsv's algorithm: Gaussian elimination with partial pivoting between adjacent rows, which
  * is what np.linalg.solve, nb:204, reaches through zgesv on a tridiagonal A): for the few systems on which the unpivoted

@@ -71,6 +71,40 @@ def _worker(rank, world, port, results):
         dist.destroy_process_group()
 
 
+def _worker_bad_rank(rank, world, port, results):
+    """A breakdown on ONE rank: every rank must raise (nobody may be left waiting in the gather)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    for p in (os.path.dirname(here), here):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        N, k = 5000, 37.5
+        ops = NumpySlabOps(N, k)
+        ops.bad = rank == 1
+        try:
+            fh_dist.solve_partitioned(N, k, ops=ops, gather=True)
+            results[rank] = "returned"
+        except np.linalg.LinAlgError:
+            results[rank] = "raised"
+
+        def sweep(N_, ks_, L_=1.0, theta_=0.0, **kw):
+            nodes, U = _numpy_sweep(N_, ks_, L_, theta_)
+            st = torch.zeros(len(ks_), dtype=torch.int32)
+            if rank == 0:
+                st[1] = 1
+            return nodes, U, st
+        try:
+            fh_dist.sweep_sharded(64, np.linspace(1.0, 50.0, 7), solver=sweep, gather=True)
+            results[rank] += "+returned"
+        except np.linalg.LinAlgError:
+            results[rank] += "+raised"
+    finally:
+        dist.destroy_process_group()
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -110,6 +144,14 @@ def test_world_size_2_partitioned_solve_and_sharded_sweep():
         assert results[r]["cyc"] == (r, world)
         assert np.array_equal(results[r]["U_cyc"], Uref.numpy()[r::world])
         assert np.array_equal(results[r]["U_cyc_all"], Uref.numpy())
+
+
+def test_world_size_2_rank_local_breakdown_raises_on_every_rank():
+    world = 2
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker_bad_rank, args=(world, _free_port(), results), nprocs=world, join=True)
+    assert dict(results) == {0: "raised+raised", 1: "raised+raised"}
 
 
 def test_single_process_path_needs_no_process_group():

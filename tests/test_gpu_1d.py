@@ -317,7 +317,7 @@ def test_breakdown_flag_on_a_verified_solution_is_cleared_without_the_pivoted_re
     u, status = fh.solve_tridiagonal(dl, d, du, b)
     assert int(status.abs().sum()) == 0
     ref = u.clone()
-    status[1] = 3              # as if the probe had found a severe defect and the refinement step had run since
+    status[1] = 1              # as if the probe had found a severe defect (3) and the refinement step had run since (-> 1)
     u[2] = float("nan")        # a real breakdown
     status[2] = 1
     u[3, 100] += 1e-6          # finite, but five digits short of the bar
