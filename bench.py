@@ -487,6 +487,7 @@ def run_gpu(args):
 
     # end-to-end through the public host-to-host API
     e2e = None
+    e2e_s = ceil_s = l2_s = 0.0
     if not args.no_e2e:
         del bands
         torch.cuda.empty_cache()
@@ -499,23 +500,53 @@ def run_gpu(args):
             _, U_host = fem1d.solve_helmholtz_sweep_host(N_ELEM, ks_h, plan=plan)
         torch.cuda.synchronize()
         e2e_s = (time.perf_counter() - t0) / e2e_steps
-        e2e = {"seconds": e2e_s, "h2d": plan.h2d_bytes, "d2h": plan.d2h_bytes, "steps": e2e_steps}
+        sample = [0, n_k // 3, n_k - 1]
+        sums_from_u = fem1d.l2_error_sums(ks_h[sample], N_ELEM, np.linspace(0, 1.0, n), U_host[sample])
+        # the box's ceiling for that path: the same bytes, device -> the same pinned buffer, nothing else -- every rank
+        # at once (one process per GPU; on this pool the host is a VM with one NUMA node: all ranks share its DMA path)
+        def d2h_only():
+            for c, lo in enumerate(range(0, n_k, plan.chunk)):
+                hi = min(n_k, lo + plan.chunk)
+                plan.U_host[lo:hi].copy_(plan.U_dev[c & 1][:hi - lo], non_blocking=True)
+            torch.cuda.synchronize()
+        d2h_only()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            d2h_only()
+        ceil_s = (time.perf_counter() - t0) / e2e_steps
+        e2e = {"h2d": plan.h2d_bytes, "d2h": plan.d2h_bytes, "steps": e2e_steps, "pipeline": plan.pipeline}
+        del plan, U_host
+        torch.cuda.empty_cache()
+        # the reduced variant: what the reference's own sweep driver (convergence_test, nb:284-362) takes from every
+        # solution is its L2 error sum -- 16 bytes per wavenumber cross PCIe instead of 64 KB
+        plan = fem1d.HostSweepPlan(N_ELEM, n_k, reduce="l2")
+        fem1d.solve_helmholtz_sweep_host(N_ELEM, ks_h, plan=plan)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            _, sums = fem1d.solve_helmholtz_sweep_host(N_ELEM, ks_h, plan=plan)
+        torch.cuda.synchronize()
+        l2_s = (time.perf_counter() - t0) / e2e_steps
+        e2e.update({"l2_h2d": plan.h2d_bytes, "l2_d2h": plan.d2h_bytes,
+                    "l2_matches_full": bool(np.allclose(sums[sample], sums_from_u, rtol=1e-12, atol=0.0))})
+        del plan
 
     # max over ranks
-    vals = torch.tensor([total_ms, e2e["seconds"] if e2e else 0.0, fused_ms,
+    vals = torch.tensor([total_ms, e2e_s, fused_ms,
                          statistics.mean(sol_ms), statistics.mean(asm_ms), float(done), backward_max, one_pass_ms,
-                         one_pass_berr, float(repaired["flagged"]), float(repaired["kept"]), float(repaired["resolved"])],
-                        dtype=torch.float64, device=dev)
+                         one_pass_berr, float(repaired["flagged"]), float(repaired["kept"]), float(repaired["resolved"]),
+                         ceil_s, l2_s], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
     (total_ms, e2e_s, fused_ms, sol_mean, asm_mean, refined_max, backward_max, one_pass_ms,
-     one_pass_berr, brk_flagged, brk_kept, brk_resolved) = vals.tolist()
+     one_pass_berr, brk_flagged, brk_kept, brk_resolved, ceil_s, l2_s) = vals.tolist()
 
     configs = None
     if not args.no_configs:  # every rank takes part (config 4 holds a collective)
         del U
         torch.cuda.empty_cache()
-        configs = other_configs(world, rank, dev, dist)
+        configs = other_configs(world, rank, dev, dist, measured_peak_gbs()[0])
 
     if rank == 0:
         dof_rank = n_k * n
@@ -539,6 +570,9 @@ def run_gpu(args):
                          "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured"
                          else "fallback 6.65 TB/s (B200_PROFILING.md)",
                          "algorithmic_bytes_per_launch": BYTES_SOLVE * dof_rank, "traffic": traffic,
+                         "traffic_source": "profiles/ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of "
+                                           "this kernel from a committed `ncu --set full` capture of this command -- a "
+                                           "constant of that capture, not measured in this run",
                          "launch_ms": sol_mean},
             "stages": {"assembly_ms": asm_mean, "solve_ms": sol_mean, "refine_ms": statistics.mean(ref_ms),
                        "solve_ms_per_step": [round(v, 3) for v in sol_ms],
@@ -565,9 +599,23 @@ def run_gpu(args):
         if configs is not None:
             out["other_configs"] = configs
         if e2e:
+            d2h_all = e2e["d2h"] * world
             out["e2e"] = {"value": dof_all / e2e_s, "unit": "DOF/s", "h2d_bytes_per_step": e2e["h2d"],
                           "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": 1e3 * e2e_s, "steps": e2e["steps"],
-                          "api": "fem1d.solve_helmholtz_sweep_host (pinned H2D of k, k^2; D2H of every solution)"}
+                          "api": "fem1d.solve_helmholtz_sweep_host (pinned H2D of k, k^2; D2H of every solution), "
+                                 f"pipeline {e2e['pipeline']}",
+                          "d2h_gbs_all_gpus": d2h_all / e2e_s / 1e9,
+                          "ceiling_gbs": d2h_all / ceil_s / 1e9,
+                          "ceiling_ms_per_step": 1e3 * ceil_s,
+                          "frac_of_ceiling": ceil_s / e2e_s,
+                          "ceiling": "the same solution bytes, device -> the same pinned host buffers, nothing else, all "
+                                     "ranks at once (max over ranks): what this box's PCIe / host-memory path delivers",
+                          "reduced_l2": {"value": dof_all / l2_s, "unit": "DOF/s", "ms_per_step": 1e3 * l2_s,
+                                         "h2d_bytes_per_step": e2e["l2_h2d"], "d2h_bytes_per_step": e2e["l2_d2h"],
+                                         "matches_full_solution_path": e2e["l2_matches_full"],
+                                         "api": "fem1d.solve_helmholtz_sweep_host(reduce='l2'): per wavenumber the "
+                                                "16-byte sum of compute_L2_error (nb:259-281) comes back, which is all "
+                                                "the reference's convergence_test (nb:284-362) takes from a solution"}}
         if world == 1 and not args.no_cpu:
             ks_cpu = ks_h[[0, n_k // 2, n_k - 1]]
             cpu_reference_step(ks_cpu[:1])  # warm the BLAS threads
@@ -575,7 +623,7 @@ def run_gpu(args):
             out["cpu_baseline"] = {
                 "value": len(ks_cpu) * n / t, "unit": "DOF/s", "cores": cpu_threads(), "kind": cpu_reference_kind(),
                 "sample": f"{len(ks_cpu)} of the {n_k} wavenumbers (k = first, middle, last) at N={N_ELEM}: the "
-                          f"reference's dense assembly + np.linalg.solve (oracle/ref1d.py), {t:.1f} s",
+                          f"reference's dense assembly + np.linalg.solve ({'the notebook code itself' if literal_reference() else 'oracle/ref1d.py'}), {t:.1f} s",
                 "banded_zgtsv_dof_per_s_1thread": cpu_banded_rate()}
         print(json.dumps(out))
     if dist is not None:

@@ -219,6 +219,9 @@ large_backsub_kernel(Source src, const cplx *__restrict__ xr, cplx *__restrict__
         if (len >= 1) {
             const int64_t o = 2 * (tile * kLT + t);
             const cplx x0 = xr[o], xl = len > 1 ? xr[o + 1] : x0;
+            // (the neighbours' unknowns, for the probe: requested together with the chunk's own, used at the end)
+            const int64_t n_red = reduced_rows(src.n);
+            const cplx xprev = o > 0 ? xr[o - 1] : czero(), xnext = o + 2 < n_red ? xr[o + 2] : czero();
             bad = !cfinite(x0) || !cfinite(xl);
             // the two interface equations of the chunk, kept for the probe (their right-hand sides are overwritten below)
             const int sF = lswz(r0), sL = lswz(r0 + len - 1);
@@ -244,13 +247,12 @@ large_backsub_kernel(Source src, const cplx *__restrict__ xr, cplx *__restrict__
             }
             sm.d[lswz(r0)] = x0;
             if (len >= 2) {
-                const int64_t n_red = reduced_rows(src.n);
                 const cplx x1 = len > 2 ? sm.d[lswz(r0 + 1)] : xl, xm2 = len > 2 ? sm.d[lswz(r0 + len - 2)] : x0;
                 // the neighbours' unknowns: the previous chunk's last / the next chunk's first (a slab's outermost
                 // rows couple to another rank's unknown, which is not here: those two equations are skipped)
-                if (o > 0) flag |= probe_row(fa, fb, fc, fd, xr[o - 1], x0, x1, anorm);
+                if (o > 0) flag |= probe_row(fa, fb, fc, fd, xprev, x0, x1, anorm);
                 else if (!src.open_first_row()) flag |= probe_row(czero(), fb, fc, fd, czero(), x0, x1, anorm);
-                if (o + 2 < n_red) flag |= probe_row(la, lb, lc, ld, xm2, xl, xr[o + 2], anorm);
+                if (o + 2 < n_red) flag |= probe_row(la, lb, lc, ld, xm2, xl, xnext, anorm);
                 else if (!src.open_last_row()) flag |= probe_row(la, lb, czero(), ld, xm2, xl, czero(), anorm);
             }
         }
@@ -525,8 +527,8 @@ __device__ __forceinline__ double deep_anorm(const DeepConsts *cs) {
     const cplx *e = cs[0].eo[0];
     return labs1(e[0]) + labs1(e[1]) + labs1(e[2]);
 }
-__device__ __forceinline__ int deep_backsub_plain(const DeepConsts &C, double anorm, int64_t c_begin, int64_t c_end,
-                                                  const cplx *xr, int64_t n_next, cplx *x) {
+__device__ __forceinline__ int deep_backsub_plain(const DeepConsts &C, int64_t c_begin, int64_t c_end, const cplx *xr,
+                                                  cplx *x) {
     const int i = threadIdx.x & (kLM - 1);
     const cplx al = C.tab[0][i], be = C.tab[1][i], ga = C.tab[2][i];
     int flag = 0;
@@ -545,13 +547,33 @@ __device__ __forceinline__ int deep_backsub_plain(const DeepConsts &C, double an
                 const cplx xi = cmadd(cmadd(ga, al, x0[q]), be, xl[q]);
                 flag |= cfinite(xi) ? 0 : 1;
                 stg_stream(x + c * kLM + i, xi);
-                if (i == 1 || i == kLM - 2) {
-                    const bool hp = c > 0, hn = 2 * c + 2 < n_next;
-                    flag |= deep_probe_plain(C, anorm, i, xi, x0[q], xl[q], hp, hp && i == 1 ? xr[2 * c - 1] : czero(),
-                                             hn, hn && i != 1 ? xr[2 * c + 2] : czero());
-                }
             }
         }
+    }
+    return flag;
+}
+// The probe of the plain chunks.  They all go through the same three tables and the same two constant rows; what
+// differs from chunk to chunk is only the pair of end values.  A loss of accuracy in the tables or constants of a level
+// -- the failure mode of the unpivoted symbolic sweep -- therefore shows in every chunk, and a SAMPLE of them, spread
+// evenly over the level, is probed: one chunk per thread of one CTA (<= 256 chunks), both interface equations, the two
+// unknowns next to the end values re-evaluated from the tables.  (Probing every chunk inside the streaming loop made the
+// store stream instruction-bound: 2^27 rows took 1.2 ms instead of 0.5 ms.)
+__device__ __forceinline__ int deep_probe_samples(const DeepConsts &C, double anorm, const DeepLevel &L, const cplx *xr,
+                                                  int64_t n_next, int tid, int n_threads) {  // sample `tid` of `n_threads`
+    const int64_t count = L.chi - L.clo;
+    if (count <= 0 || tid < 0) return 0;
+    const int64_t stride = count > (int64_t)n_threads ? count / (int64_t)n_threads : 1;
+    const int64_t c = L.clo + (int64_t)tid * stride;
+    if (c >= L.chi) return 0;
+    const cplx xf = xr[2 * c], xl = xr[2 * c + 1];
+    int flag = 0;
+    if (c > 0) {
+        const cplx x1 = cmadd(cmadd(C.tab[2][1], C.tab[0][1], xf), C.tab[1][1], xl);
+        flag |= deep_probe_plain(C, anorm, 1, x1, xf, xl, true, xr[2 * c - 1], false, czero());
+    }
+    if (2 * c + 2 < n_next) {
+        const cplx x14 = cmadd(cmadd(C.tab[2][kLM - 2], C.tab[0][kLM - 2], xf), C.tab[1][kLM - 2], xl);
+        flag |= deep_probe_plain(C, anorm, kLM - 2, x14, xf, xl, false, czero(), true, xr[2 * c + 2]);
     }
     return flag;
 }
@@ -622,8 +644,15 @@ __device__ void deep_backsub_small_levels(const UniformRows &u, const DeepPlan &
         if (w < deep_special_count(L) && (threadIdx.x & 31) == 0)
             flag |= deep_backsub_special(L, anorm, set.lv[j], w, xr, n_next, x);
         __syncwarp();
-        flag |= deep_backsub_plain(cs[l], anorm, L.clo, L.chi, xr, n_next, x);
+        flag |= deep_backsub_plain(cs[l], L.clo, L.chi, xr, x);
         __syncthreads();
+    }
+    // the probes of all these levels at once, off the critical path of the level-by-level chain: warp w samples 32
+    // chunks of the w-th small level (every level's solution is still in the workspace)
+    {
+        const int l = dp.levels - 1 - (int)(threadIdx.x >> 5);
+        if (l >= 0 && dp.lv[l].n <= kDeepSmall)
+            flag |= deep_probe_samples(cs[l], anorm, dp.lv[l], deep_xr(dp, l), dp.lv[l + 1].n, (int)(threadIdx.x & 31), 32);
     }
     flag = (int)__reduce_or_sync(0xffffffffu, (unsigned)flag);
     if (flag != 0 && (threadIdx.x & 31) == 0 && status != nullptr) atomicOr(status, flag);
@@ -683,9 +712,9 @@ constexpr int kDeepStages = 4;
 struct DeepRing {
     cplx buf[kDeepStages][2 * 128];
 };
-__device__ __forceinline__ int deep_backsub_plain_staged(const DeepConsts &C, double anorm, int64_t c_begin,
-                                                         int64_t c_end, const cplx *__restrict__ xr, int64_t n_next,
-                                                         cplx *__restrict__ x, DeepRing &ring) {
+__device__ __forceinline__ int deep_backsub_plain_staged(const DeepConsts &C, int64_t c_begin, int64_t c_end,
+                                                         const cplx *__restrict__ xr, cplx *__restrict__ x,
+                                                         DeepRing &ring) {
     const int t = threadIdx.x, i = t & (kLM - 1), cl = t >> 4;
     const cplx al = C.tab[0][i], be = C.tab[1][i], ga = C.tab[2][i];
     const int64_t rounds = (c_end - c_begin + 127) / 128;
@@ -695,7 +724,7 @@ __device__ __forceinline__ int deep_backsub_plain_staged(const DeepConsts &C, do
         cp_async_commit();
     };
     for (int r = 0; r < kDeepStages - 1; ++r) fetch(r);
-    int flag = 0;
+    bool bad = false;
     for (int64_t r = 0; r < rounds; ++r) {
         asm volatile("cp.async.wait_group %0;" ::"n"(kDeepStages - 2) : "memory");  // this thread's share of round r
         __syncthreads();  // everybody's share has landed, and everybody is done with round r - 1 ...
@@ -706,22 +735,13 @@ __device__ __forceinline__ int deep_backsub_plain_staged(const DeepConsts &C, do
         for (int q = 0; q < 8; ++q) {
             const int64_t c = c0 + 16 * q;
             if (c < c_end) {
-                const int lc = cl + 16 * q;  // chunk within the round
-                const cplx xf = b[2 * lc], xl = b[2 * lc + 1];
-                const cplx xi = cmadd(cmadd(ga, al, xf), be, xl);
-                flag |= cfinite(xi) ? 0 : 1;
+                const cplx xi = cmadd(cmadd(ga, al, b[2 * (cl + 16 * q)]), be, b[2 * (cl + 16 * q) + 1]);
+                bad |= !cfinite(xi);
                 stg_stream(x + c * kLM + i, xi);
-                if (i == 1 || i == kLM - 2) {  // two lanes per chunk: the accuracy probe (neighbours mostly in the ring)
-                    const bool hp = c > 0, hn = 2 * c + 2 < n_next;
-                    cplx xn = czero();
-                    if (i == 1 && hp) xn = lc > 0 ? b[2 * lc - 1] : xr[2 * c - 1];
-                    if (i != 1 && hn) xn = (lc < 127 && c + 1 < c_end) ? b[2 * lc + 2] : xr[2 * c + 2];
-                    flag |= deep_probe_plain(C, anorm, i, xi, xf, xl, hp, xn, hn, xn);
-                }
             }
         }
     }
-    return flag;
+    return bad ? 1 : 0;
 }
 
 // one large level: CTA 0 takes the special chunks, every other CTA streams `per` contiguous rounds of plain chunks
@@ -742,11 +762,13 @@ deep_backsub_level_kernel(UniformRows u, const __grid_constant__ DeepPlan dp, co
         __syncthreads();
         if ((int)threadIdx.x < deep_special_count(L))
             flag = deep_backsub_special(L, anorm, sg, threadIdx.x, xr, n_next, x);
+        // (warp 0 holds the special chunks' serial sweeps; the other warps of this CTA take the samples meanwhile)
+        flag |= deep_probe_samples(cs[l], anorm, L, xr, n_next, (int)threadIdx.x - 32, kDeepThreads - 32);
     } else {
         const int64_t b = blockIdx.x - 1;
         int64_t c_end = L.clo + (b + 1) * per * 128;
         if (c_end > L.chi) c_end = L.chi;
-        flag = deep_backsub_plain_staged(cs[l], anorm, L.clo + b * per * 128, c_end, xr, n_next, x, ring);
+        flag = deep_backsub_plain_staged(cs[l], L.clo + b * per * 128, c_end, xr, x, ring);
     }
     flag = (int)__reduce_or_sync(0xffffffffu, (unsigned)flag);
     if (flag != 0 && (threadIdx.x & 31) == 0 && status != nullptr) atomicOr(status, flag);

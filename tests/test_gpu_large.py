@@ -344,6 +344,17 @@ def test_large_solvers_near_resonance_and_zero_pivots_keep_reference_accuracy():
         for fused in (False, True):
             nodes, u = fh.solve_helmholtz_fem(N2, k2, fused=fused)
             assert rel_err(u, ref2) < 1e-10, (N2, fused, rel_err(u, ref2))
+    # a resonance of the PARTITION: the 14 interior rows of every 16-row chunk form a singular block when
+    # sin(15 theta) = 0, i.e. k h = 2 tan(pi / 30) -- nothing special for the matrix as a whole (LAPACK: 1e-17)
+    N3 = 100_000
+    for eps in (0.0, 1e-12, 1e-9, 1e-6):
+        k3 = 2.0 * N3 * np.tan(np.pi / 30.0) * (1.0 + eps)
+        b3 = banded1d.assemble_bands(N3, k3, 1.0 / N3)
+        ref3 = banded1d.solve_bands(*b3)
+        for fused in (False, True):
+            nodes, u = fh.solve_helmholtz_fem(N3, k3, fused=fused)
+            be = banded1d.residual_metrics(*b3, u)[0]
+            assert be < 1e-13 and rel_err(u, ref3) < 1e-9, (eps, fused, be, rel_err(u, ref3))
     n = 5001                                             # odd hollow matrix: structurally singular
     one, zero = np.ones(n, complex), np.zeros(n, complex)
     A = fh.fem1d.TridiagonalSystem(*(fh._lib.as_device(x.reshape(1, n), torch.complex128) for x in (one, zero, one)))
