@@ -92,6 +92,12 @@ _SIGNATURES = {
     "fh_q4_boundary_flags": (C.c_int, [_P, C.c_int64, C.c_double, C.c_double, C.c_int, _P, _P]),
     "fh_csr_apply_dirichlet_c128": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_double, C.c_double,
                                               C.c_double, C.c_double, _P]),
+    "fh_q4_boundary_lists": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_double, C.c_double, _P, _P, _P]),
+    "fh_compact_flags_i32": (C.c_int, [_P, C.c_int64, _P, _P, _P]),
+    "fh_q4_neumann_load_c128": (C.c_int, [_P, _P, _P, C.c_int64, _P, C.c_double, C.c_int, _P, C.c_int, _P, _P]),
+    "fh_q4_gauss_points": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int, _P, _P]),
+    "fh_q4_l2_error_workspace_bytes": (C.c_size_t, []),
+    "fh_q4_l2_error_c128": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P, C.c_int, _P, _P, C.c_size_t, _P]),
     "fh_csr_to_dense_c128": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P]),
     "fh_dense_lu_solve_c128": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P]),
     "fh_csr_bandwidth": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P]),

@@ -157,27 +157,40 @@ class BaseSolver(ABC):
             total += (1j**m) * k * jvp(m, k * r) * np.exp(1j * m * theta)
         return total
 
+    # where the incident-wave load g of the Neumann edges is evaluated: "host" (scipy's Bessel functions, as the
+    # reference: the load vector is bit-identical to its) or "device" (fh_q4_neumann_load_c128, CUDA's jn(): ~1e-11)
+    neumann_load = "host"
+
     def _neumann_vectors_device(self, ids):
-        """fem2d.py:82-137 for the listed elements: complex128[nb, 4].  The Bessel-function load g is evaluated on
-        the host at the Gauss points of the flagged edges and uploaded; the kernel integrates."""
-        lib = _lib.require_cuda()
-        _, on_edge, length = self._edge_geometry(ids, self.eqn.inner_radius)
+        """fem2d.py:82-137 for the listed elements: complex128[nb, 4].  The Bessel-function load g is evaluated at the
+        Gauss points of the flagged edges -- on the host and uploaded, or by the device kernel
+        (``neumann_load = "device"``) --; the edge kernel integrates."""
+        lib, m = _lib.require_cuda(), self._device_mesh()
+        ids_d, on_edge, length = self._edge_geometry(ids, self.eqn.inner_radius)
         gp, gw = roots_legendre(3)
         (_, gp_p), (_, gw_p) = _host_f64(gp), _host_f64(gw)
-        flags = on_edge.cpu().numpy()
-        nodes, elements = np.asarray(self.eqn.nodes), np.asarray(self.eqn.elements)
-        g = np.zeros((len(ids), 4, 3), dtype=complex)
-        for q, e in enumerate(ids):
-            coords = nodes[elements[e]]
-            for ed, (p0, p1) in enumerate(_EDGES):
-                if not flags[q, ed]:
-                    continue
-                for gi, xi in enumerate(gp):
-                    N = self.get_shape_fuctions_1d(xi)
-                    x = 0.0 + N[0] * coords[p0, 0] + N[1] * coords[p1, 0]   # fem2d.py:119-123, same rounding
-                    y = 0.0 + N[0] * coords[p0, 1] + N[1] * coords[p1, 1]
-                    g[q, ed, gi] = self.get_normal_derivative(x, y)
-        g_d = _lib.as_device(g, torch.complex128)
+        if self.neumann_load not in ("host", "device"):
+            raise ValueError("neumann_load must be 'host' or 'device'")
+        if self.neumann_load == "device":
+            g_d = torch.empty((len(ids), 4, 3), dtype=torch.complex128, device=on_edge.device)
+            check(lib.fh_q4_neumann_load_c128(ptr(m["nodes"]), ptr(m["elements"]), ptr(ids_d), len(ids), ptr(on_edge),
+                                              float(np.sqrt(self.k_squared)), int(self.n_fourier), gp_p, 3, ptr(g_d),
+                                              stream_ptr()), "fh_q4_neumann_load_c128")
+        else:
+            flags = on_edge.cpu().numpy()
+            nodes, elements = np.asarray(self.eqn.nodes), np.asarray(self.eqn.elements)
+            g = np.zeros((len(ids), 4, 3), dtype=complex)
+            for q, e in enumerate(ids):
+                coords = nodes[elements[e]]
+                for ed, (p0, p1) in enumerate(_EDGES):
+                    if not flags[q, ed]:
+                        continue
+                    for gi, xi in enumerate(gp):
+                        N = self.get_shape_fuctions_1d(xi)
+                        x = 0.0 + N[0] * coords[p0, 0] + N[1] * coords[p1, 0]   # fem2d.py:119-123, same rounding
+                        y = 0.0 + N[0] * coords[p0, 1] + N[1] * coords[p1, 1]
+                        g[q, ed, gi] = self.get_normal_derivative(x, y)
+            g_d = _lib.as_device(g, torch.complex128)
         Ne = torch.zeros((len(ids), 4), dtype=torch.complex128, device=g_d.device)
         check(lib.fh_q4_neumann_edge_vectors_c128(ptr(on_edge), ptr(length), len(ids), ptr(g_d), gp_p, gw_p, 3, ptr(Ne),
                                                   stream_ptr()), "fh_q4_neumann_edge_vectors_c128")
@@ -274,10 +287,13 @@ class BaseSolver(ABC):
 
     def apply_boundary_conditions(self, A=None, b=None, tol: float = 1e-10):
         """Dirichlet row replacement (fem2d_dirichlet.py:11-29, fem2d_dirichlet_sommerfeld.py:12-24,
-        fem2d_neumann_dirichlet.py:85-97) applied to the device CSR matrix / load in place.  ``A`` and ``b`` are
-        accepted for signature parity; the solver's own ``K`` / ``F`` are the ones modified and returned."""
+        fem2d_neumann_dirichlet.py:85-97): ``A[row] = 0; A[row, row] = 1; b[row] = g`` for the nodes within ``tol`` of a
+        Dirichlet circle (g = 1 inside, 0 outside), applied to the ``(A, b)`` passed in -- in place -- and returned, as the
+        reference does.  ``A``: a :class:`CsrMatrix` (device; the default, ``self.K``) or a dense numpy matrix;
+        ``b``: numpy / torch vector (default ``self.F``)."""
         lib, m = _lib.require_cuda(), self._device_mesh()
-        flags = torch.zeros(m["n"], dtype=torch.uint8, device=self.K.vals.device)
+        dev = m["nodes"].device
+        flags = torch.zeros(m["n"], dtype=torch.uint8, device=dev)
         mask = 0
         if self._dirichlet_inner:
             check(lib.fh_q4_boundary_flags(ptr(m["nodes"]), m["n"], float(self.inner_radius), float(tol), 1, ptr(flags),
@@ -287,12 +303,34 @@ class BaseSolver(ABC):
             check(lib.fh_q4_boundary_flags(ptr(m["nodes"]), m["n"], float(self.outer_radius), float(tol), 2, ptr(flags),
                                            stream_ptr()), "fh_q4_boundary_flags")
             mask |= 2
-        if mask:
-            check(lib.fh_csr_apply_dirichlet_c128(ptr(self.K.rowptr), ptr(self.K.colidx), ptr(self.K.vals),
-                                                  ptr(self._F_dev), ptr(flags), m["n"], mask, 1.0, 0.0, 0.0, 0.0,
-                                                  stream_ptr()), "fh_csr_apply_dirichlet_c128")
-            self.F = self._F_dev.cpu().numpy()
-        return self.K, self.F
+        own = A is None or A is getattr(self, "K", None)
+        A = self.K if A is None else A
+        if b is None or (own and b is self.F):
+            b_dev, b_own = self._F_dev, True
+        else:
+            b_dev, b_own = _lib.as_device(b, torch.complex128).clone(), False
+        if not mask:
+            return A, (self.F if b_own else b)
+        if isinstance(A, CsrMatrix):
+            check(lib.fh_csr_apply_dirichlet_c128(ptr(A.rowptr), ptr(A.colidx), ptr(A.vals), ptr(b_dev), ptr(flags),
+                                                  m["n"], mask, 1.0, 0.0, 0.0, 0.0, stream_ptr()),
+                  "fh_csr_apply_dirichlet_c128")
+        else:  # a dense matrix from the caller (the reference's type): same rule, rows picked by the device flags
+            f = flags.cpu().numpy()
+            rows = np.nonzero(f & mask)[0]
+            A[rows] = 0
+            A[rows, rows] = 1
+            g = np.where(f[rows] & 1 & mask, 1.0, 0.0)  # inner circle: 1, outer: 0 (an inner flag wins, as in the kernel)
+            b_host = np.array(b, dtype=complex) if not isinstance(b, np.ndarray) else b
+            b_host[rows] = g
+            return A, b_host
+        out = b_dev.cpu().numpy()
+        if b_own:
+            self.F = out
+        elif isinstance(b, np.ndarray):
+            b[...] = out
+            out = b
+        return A, out
 
     # which device solver np.linalg.solve maps to: "band" (sparse, default) or "dense"; "auto" = band unless the band is
     # no narrower than the matrix
@@ -377,18 +415,28 @@ class BaseSolver(ABC):
         raise NotImplementedError("Analytical solution not implemented")
 
     def compute_L2_error(self, u_num_real, u_num_imag):
-        """base.py:119-177: 2x2 Gauss quadrature of |u_h - u_exact|^2 det J (vectorised over elements on the host;
-        the analytic solution is a host special-function evaluation)."""
+        """base.py:119-177 on the device: ``fh_q4_gauss_points`` gives the (x, y) of every element's 2 x 2 Gauss points,
+        the class's analytic solution -- Bessel closed forms, host scipy, vectorised where the formula allows -- is
+        evaluated there, and ``fh_q4_l2_error_c128`` integrates |u_h - u_exact|^2 det J w_i w_j in the reference's
+        per-element order (the sum over elements is a fixed tree: agrees with the sequential sum to rounding)."""
+        lib, m = _lib.require_cuda(), self._device_mesh()
         gp, gw = roots_legendre(2)
-        nodes, elements = np.asarray(self.eqn.nodes), np.asarray(self.eqn.elements)
+        (_, gp_p), (_, gw_p) = _host_f64(gp), _host_f64(gw)
+        dev = m["nodes"].device
+        xy = torch.empty((m["ne"], 2, 2, 2), dtype=torch.float64, device=dev)
+        check(lib.fh_q4_gauss_points(ptr(m["nodes"]), ptr(m["elements"]), m["ne"], gp_p, 2, ptr(xy), stream_ptr()),
+              "fh_q4_gauss_points")
+        pts = xy.cpu().numpy().reshape(-1, 2)
+        try:
+            exact = np.asarray(self.get_analytical_solution(pts[:, 0], pts[:, 1]), dtype=complex)
+            if exact.shape != (len(pts),):
+                raise ValueError
+        except (ValueError, TypeError):  # a formula that only takes scalars
+            exact = np.array([self.get_analytical_solution(a, b) for a, b in pts], dtype=complex)
         u = np.asarray(u_num_real) + 1j * np.asarray(u_num_imag)
-        X, Y, U = nodes[elements, 0], nodes[elements, 1], u[elements]
-        total = 0.0
-        for i, xi in enumerate(gp):
-            for j, eta in enumerate(gp):
-                N, dxi, deta = self.get_shape_functions(xi, eta)
-                x, y, uh = X @ N, Y @ N, U @ N
-                detJ = (X @ dxi) * (Y @ deta) - (Y @ dxi) * (X @ deta)
-                exact = np.array([self.get_analytical_solution(a, b) for a, b in zip(x, y)])
-                total += np.sum(np.abs(uh - exact) ** 2 * detJ * gw[i] * gw[j])
-        return np.sqrt(total)
+        u_d, ex_d = _lib.as_device(u, torch.complex128), _lib.as_device(exact, torch.complex128)
+        ws = torch.empty(lib.fh_q4_l2_error_workspace_bytes(), dtype=torch.uint8, device=dev)
+        out = torch.empty(1, dtype=torch.float64, device=dev)
+        check(lib.fh_q4_l2_error_c128(ptr(m["nodes"]), ptr(m["elements"]), m["ne"], ptr(u_d), ptr(ex_d), gp_p, gw_p, 2,
+                                      ptr(out), ptr(ws), ws.numel(), stream_ptr()), "fh_q4_l2_error_c128")
+        return np.sqrt(float(out.item()))

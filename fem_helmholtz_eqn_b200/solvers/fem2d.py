@@ -1,8 +1,7 @@
 """``"default"`` solver: Neumann load on the inner circle, Sommerfeld / ABC (Robin) condition on the outer one.
 Mirrors ``src/solvers/fem2d.py`` (2-point Gauss on the Robin edges, 3-point on the Neumann edges)."""
-import numpy as np
-
 from .base import BaseSolver
+from .utils import get_solution
 
 
 class FEM2DSolver(BaseSolver):
@@ -17,3 +16,9 @@ class FEM2DSolver(BaseSolver):
     def neumann_element_matrices(self, idx):
         """fem2d.py:82-137 for one element -> N_e[4]."""
         return self._neumann_vectors_device([int(idx)])[0].cpu().numpy()
+
+    def get_analytical_solution(self, x, y) -> complex:
+        """fem2d.py:183-224: the closed form of ``solvers/utils.py:get_solution`` for this class's boundary conditions
+        and ``abc_order`` (the Hankel-function sum the reference also evaluates there is discarded by it, so it is not
+        computed here)."""
+        return get_solution(x, y, self.abc_order, self.k_squared, self.inner_radius, self.outer_radius, self.n_fourier)

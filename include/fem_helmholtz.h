@@ -309,6 +309,30 @@ FH_API int fh_csr_apply_dirichlet_c128(const int64_t *rowptr, const int32_t *col
                                 const uint8_t *flags, int64_t n, int mask, double g_inner_re, double g_inner_im,
                                 double g_outer_re, double g_outer_im, fh_stream_t stream);
 
+/* ---- what surrounds the 2D assembly in the reference's drivers, on the device ------------------------------
+ * Boundary detection (helmholtz.py:95-118): node_flag[i] = np.isclose(np.linalg.norm(nodes[i]), radius, atol=atol) (rtol =
+ * numpy's default 1e-5), elem_flag[e] = any node of element e flagged; int32 flags, fh_compact_flags_i32 turns either
+ * into the ascending index list np.where(...)[0] (list: int32[n], count: device int32[1]). */
+FH_API int fh_q4_boundary_lists(const double *nodes, int64_t n_nodes, const int32_t *elements, int64_t n_elements,
+                         double radius, double atol, int32_t *node_flag, int32_t *elem_flag, fh_stream_t stream);
+FH_API int fh_compact_flags_i32(const int32_t *flags, int64_t n, int32_t *list, int32_t *count, fh_stream_t stream);
+/* get_normal_derivative (fem2d.py:12-27) at the Gauss points of the flagged edges (fem2d.py:113-127):
+ * g_vals = complex128[n_ids][4][n_gauss] = sum_{m=-n_fourier}^{n_fourier} i^m k J_m'(k r) e^{i m theta}, the input of
+ * fh_q4_neumann_edge_vectors_c128.  J_m from CUDA's jn(): ~1e-11 absolute, not scipy's last bit (the host path is). */
+FH_API int fh_q4_neumann_load_c128(const double *nodes, const int32_t *elements, const int32_t *elem_ids, int64_t n_ids,
+                            const uint8_t *on_edge, double k, int n_fourier, const double *gauss_pts_host, int n_gauss,
+                            fh_c128 *g_vals, fh_stream_t stream);
+/* compute_L2_error (base.py:119-177).  fh_q4_gauss_points: xy = fp64[n_elements][n_gauss][n_gauss][2], the (x, y) of
+ * base.py:141-148 (where the caller evaluates the analytic solution -- Bessel closed forms, scipy, as the reference).
+ * fh_q4_l2_error_c128: sum_out[0] = sum over elements and Gauss points of |u_h - u_exact|^2 det J w_i w_j with
+ * u = complex128[n_nodes], u_exact = complex128[n_elements][n_gauss][n_gauss]; the caller takes the square root. */
+FH_API int fh_q4_gauss_points(const double *nodes, const int32_t *elements, int64_t n_elements,
+                       const double *gauss_pts_host, int n_gauss, double *xy, fh_stream_t stream);
+FH_API size_t fh_q4_l2_error_workspace_bytes(void);
+FH_API int fh_q4_l2_error_c128(const double *nodes, const int32_t *elements, int64_t n_elements, const fh_c128 *u,
+                        const fh_c128 *u_exact, const double *gauss_pts_host, const double *gauss_wts_host, int n_gauss,
+                        double *sum_out, void *workspace, size_t workspace_bytes, fh_stream_t stream);
+
 /* *.solve(): np.linalg.solve(K, F) (fem2d.py:176) -> dense LU with partial pivoting on the device.
  * A (n x n, row-major) and b are overwritten; piv: int32[n]; status: int32[1], non-zero = singular. */
 FH_API int fh_csr_to_dense_c128(const int64_t *rowptr, const int32_t *colidx, const fh_c128 *vals, int64_t n,

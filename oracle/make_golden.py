@@ -166,13 +166,51 @@ def golden_2d():
     return out
 
 
+def golden_2d_post():
+    """What follows the solve in the reference's 2D drivers: every class's analytic solution at the mesh nodes and
+    BaseSolver.compute_L2_error of the reference's own solution (base.py:119-177), the reference run unmodified."""
+    sys.modules.setdefault("gmsh", types.ModuleType("gmsh"))
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from src.helmholtz import HelmHoltz  # noqa: E402
+    from src.utils import get_solver  # noqa: E402
+
+    from oracle.ref2d import structured_annulus
+
+    out = {}
+    meshes = {"m0": (3, 12, 1.0, 1.5), "m1": (6, 24, 1.0, 1.5)}
+    runs = [("default", 0), ("default", 1), ("default", 3), ("dirichlet", 3),
+            ("dirichlet_sommerfeld", 0), ("dirichlet_sommerfeld", 2), ("neumann_dirichlet", 3)]
+    for mname, (n_r, n_t, ri, ro) in meshes.items():
+        m = structured_annulus(n_r, n_t, ri, ro)
+        eqn = HelmHoltz.__new__(HelmHoltz)
+        for key, val in vars(m).items():
+            setattr(eqn, key, val)
+        eqn.abc_order = 3
+        for kind, order in runs:
+            for k2, nf in ((5.0, 1), (30.25, 2)):
+                s = get_solver(kind, eqn, k_squared=k2, abc_order=order, inner_radius=ri, outer_radius=ro, n_fourier=nf)
+                ur, ui = s.solve()
+                tag = f"{mname}_{kind}_o{order}_k{k2}"
+                out[f"{tag}_u"] = ur + 1j * ui
+                out[f"{tag}_exact_nodes"] = np.array([s.get_analytical_solution(x, y) for x, y in m.nodes])
+                out[f"{tag}_l2"] = np.float64(s.compute_L2_error(ur, ui))
+                print("2D post", tag, "n_fourier", nf, "L2", out[f"{tag}_l2"], flush=True)
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "post":   # only the (later) fixture of the steps after the solve
+        np.savez_compressed(os.path.join(OUT, "ref2d_post.npz"), **golden_2d_post())
+        print("wrote", os.path.join(OUT, "ref2d_post.npz"))
+        return
     ns, stored = load_notebook_namespace()
     g1 = golden_1d(ns)
     np.savez_compressed(os.path.join(OUT, "ref1d.npz"), **g1)
     g2 = golden_2d()
     np.savez_compressed(os.path.join(OUT, "ref2d.npz"), **g2)
+    np.savez_compressed(os.path.join(OUT, "ref2d_post.npz"), **golden_2d_post())
     meta = {
         "generator": "oracle/make_golden.py (executes /root/reference unmodified)",
         "numpy": np.__version__, "scipy": scipy.__version__, "python": sys.version.split()[0],

@@ -26,6 +26,11 @@ def golden2d():
     return np.load(os.path.join(GOLDEN, "ref2d.npz"))
 
 
+@pytest.fixture(scope="session")
+def golden2d_post():
+    return np.load(os.path.join(GOLDEN, "ref2d_post.npz"))
+
+
 def golden_cases(g):
     """[(idx, N, k, L)] with k restored to int where the generator used an int."""
     out = []

@@ -112,3 +112,29 @@ def test_2d_host_objects_match_reference(golden2d):
     assert list(g["solver_names"]) == solvers
     with pytest.raises(AssertionError):
         get_solver("nope", eqn)
+
+
+def test_analytic_annulus_solutions_match_reference(golden2d, golden2d_post):
+    """solvers/utils.py (host scipy, like the reference's src/solvers/utils.py) and the four classes'
+    get_analytical_solution against the values the reference's own classes return at the mesh nodes -- bit for bit
+    when called point by point, to rounding when vectorised; the reference's order quirk (UnboundLocalError for the
+    Sommerfeld variant at abc_order=3, its default) is kept."""
+    from fem_helmholtz_eqn_b200.helmholtz import HelmHoltz
+    from fem_helmholtz_eqn_b200.utils import get_solver
+    g, gp = golden2d, golden2d_post
+    runs = [("default", 0), ("default", 1), ("default", 3), ("dirichlet", 3), ("dirichlet_sommerfeld", 0),
+            ("dirichlet_sommerfeld", 2), ("neumann_dirichlet", 3)]
+    for mname in ("m0", "m1"):
+        ri, ro = (float(v) for v in g[f"{mname}_radii"])
+        eqn = HelmHoltz.from_arrays(g[f"{mname}_nodes"], g[f"{mname}_elements"], ri, ro)
+        for kind, order in runs:
+            for k2, nf in ((5.0, 1), (30.25, 2)):
+                s = get_solver(kind, eqn, k_squared=k2, abc_order=order, inner_radius=ri, outer_radius=ro, n_fourier=nf)
+                want = gp[f"{mname}_{kind}_o{order}_k{k2}_exact_nodes"]
+                got = np.array([s.get_analytical_solution(x, y) for x, y in eqn.nodes])
+                assert np.array_equal(got, want), (mname, kind, order, k2)
+                vec = s.get_analytical_solution(eqn.nodes[:, 0], eqn.nodes[:, 1])
+                assert np.allclose(vec, want, rtol=1e-13, atol=1e-15)
+    s = get_solver("dirichlet_sommerfeld", eqn)          # abc_order=3: the reference's unhandled branch
+    with pytest.raises(UnboundLocalError):
+        s.get_analytical_solution(1.2, 0.1)

@@ -71,8 +71,8 @@ def test_factory_and_errors(golden2d):
         get_solver("robin", eqn)
     with pytest.raises(ValueError):
         get_solver("default", eqn, abc_order=7).assemble()
-    with pytest.raises(NotImplementedError):
-        get_solver("default", eqn).get_analytical_solution(1.0, 0.2)
+    with pytest.raises(NotImplementedError):       # mesh generation with gmsh is out of scope
+        HelmHoltz(mesher="gmsh")
 
 
 def test_dirichlet_against_analytic_bessel_solution():
@@ -146,3 +146,90 @@ def test_robin_matrix_S_is_available_on_demand(golden2d):
     assert np.allclose(K - S, np.asarray(plain.K), rtol=1e-14, atol=1e-14)
     with pytest.raises(AttributeError):
         plain.S
+
+
+RUNS_POST = [(kind, order, k2, nf) for kind, order in RUNS for k2, nf in ((5.0, 1), (30.25, 2))]
+
+
+@pytest.mark.parametrize("mname", ["m0", "m1"])
+def test_compute_l2_error_on_device_matches_reference(golden2d, golden2d_post, mname):
+    """f2: BaseSolver.compute_L2_error (base.py:119-177) -- Gauss points and the quadrature on the device, the analytic
+    solution on the host as in the reference -- against the reference's own value for the reference's own solution,
+    for all four classes (1e-12: the sum over elements is a tree here, sequential there)."""
+    g, gp = golden2d, golden2d_post
+    eqn, ri, ro = _eqn(g, mname)
+    for kind, order, k2, nf in RUNS_POST:
+        tag = f"{mname}_{kind}_o{order}_k{k2}"
+        s = get_solver(kind, eqn, k_squared=k2, abc_order=order, inner_radius=ri, outer_radius=ro, n_fourier=nf)
+        u = gp[f"{tag}_u"]
+        l2 = s.compute_L2_error(u.real, u.imag)
+        assert abs(l2 - gp[f"{tag}_l2"]) <= 1e-12 * gp[f"{tag}_l2"], (tag, l2, gp[f"{tag}_l2"])
+        ur, ui = s.solve()                         # ... and of this repo's own solution: the same number to 1e-8
+        assert abs(s.compute_L2_error(ur, ui) - gp[f"{tag}_l2"]) <= 1e-8 * gp[f"{tag}_l2"], tag
+
+
+@pytest.mark.parametrize("mname", ["m0", "m1"])
+def test_neumann_load_generated_on_device(golden2d, mname):
+    """f4: get_normal_derivative (fem2d.py:12-27) at the edge Gauss points by fh_q4_neumann_load_c128 (CUDA jn()):
+    the load vector agrees with the reference's (scipy Bessel functions) to 1e-10; the default host path is bit-exact."""
+    g = golden2d
+    eqn, ri, ro = _eqn(g, mname)
+    for kind in ("default", "neumann_dirichlet"):
+        for k2 in (5.0, 30.25):
+            tag = f"{mname}_{kind}_o3_k{k2}"
+            s = get_solver(kind, eqn, k_squared=k2, abc_order=3, inner_radius=ri, outer_radius=ro)
+            s.neumann_load = "device"
+            s.assemble()
+            want = g[f"{tag}_Fpre"]
+            assert np.abs(s.F - want).max() <= 1e-10 * np.abs(want).max(), (tag, np.abs(s.F - want).max())
+            ur, ui = s.solve()
+            assert rel_err(ur + 1j * ui, g[f"{tag}_u"]) < 1e-9
+    s = get_solver("default", eqn, k_squared=5.0, n_fourier=3, inner_radius=ri, outer_radius=ro)
+    host = s._neumann_vectors_device(list(eqn.inner_boundary_element_indices)).cpu().numpy()
+    s.neumann_load = "device"
+    dev = s._neumann_vectors_device(list(eqn.inner_boundary_element_indices)).cpu().numpy()
+    assert np.abs(dev - host).max() <= 1e-10 * np.abs(host).max()
+
+
+def test_boundary_lists_on_device_equal_the_host_lists(golden2d):
+    """f3: helmholtz.py:95-118 (boundary nodes by np.isclose on the node radius, elements touching them) by
+    fh_q4_boundary_lists + fh_compact_flags_i32: the same ascending lists as numpy gives, on the golden meshes, a fine
+    structured mesh and a scrambled numbering."""
+    g = golden2d
+    for mname in ("m0", "m1"):
+        ri, ro = (float(v) for v in g[f"{mname}_radii"])
+        eqn = HelmHoltz.from_arrays(g[f"{mname}_nodes"], g[f"{mname}_elements"], ri, ro, topology="device")
+        assert eqn.inner_boundary_element_indices == g[f"{mname}_inner_el"].tolist()
+        assert eqn.outer_boundary_element_indices == g[f"{mname}_outer_el"].tolist()
+    host = HelmHoltz(inner_radius=0.7, outer_radius=2.1, n_theta=300, n_r=41)
+    rng = np.random.default_rng(3)
+    new_of_old = rng.permutation(host.n_nodes)
+    nodes = np.empty_like(host.nodes)
+    nodes[new_of_old] = host.nodes
+    nodes += rng.uniform(-4e-6, 4e-6, nodes.shape)       # inside and outside the 1e-5 + 1e-5 R window
+    elements = new_of_old[np.asarray(host.elements)]
+    a = HelmHoltz.from_arrays(nodes, elements, 0.7, 2.1)
+    b = HelmHoltz.from_arrays(nodes, elements, 0.7, 2.1, topology="device")
+    for name in ("inner_boundary_node_indices", "outer_boundary_node_indices"):
+        assert np.array_equal(getattr(a, name), getattr(b, name)) and len(getattr(a, name)) > 0
+    assert a.inner_boundary_element_indices == b.inner_boundary_element_indices
+    assert a.outer_boundary_element_indices == b.outer_boundary_element_indices
+
+
+def test_apply_boundary_conditions_acts_on_the_matrix_it_is_given(golden2d):
+    """apply_boundary_conditions(A, b) modifies and returns ITS arguments (fem2d_dirichlet.py:11-29), a
+    device CSR matrix or the reference's dense type alike."""
+    g = golden2d
+    eqn, ri, ro = _eqn(g, "m0")
+    tag = "m0_dirichlet_o3_k5.0"
+    s = get_solver("dirichlet", eqn, k_squared=5.0, inner_radius=ri, outer_radius=ro)
+    s.assemble()
+    K_dense, F = np.asarray(s.K).copy(), s.F.copy()
+    A2, b2 = s.apply_boundary_conditions(K_dense, F)
+    assert A2 is K_dense and b2 is F
+    r, c = np.nonzero(A2)
+    assert np.array_equal(r, g[f"{tag}_K_rows"]) and np.array_equal(c, g[f"{tag}_K_cols"])
+    assert np.array_equal(A2[r, c], g[f"{tag}_K_vals"]) and np.array_equal(b2, g[f"{tag}_F"])
+    assert np.array_equal(_nonzeros(s.K)[2], g[f"{tag}_Kpre_vals"])         # the solver's own K is untouched
+    K3, F3 = s.apply_boundary_conditions()                                     # default: the solver's own pair
+    assert K3 is s.K and np.array_equal(F3, g[f"{tag}_F"]) and np.array_equal(_nonzeros(s.K)[2], g[f"{tag}_K_vals"])
