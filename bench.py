@@ -323,6 +323,18 @@ def other_configs(world, rank, dev, dist, peak):
             plan.close()
             del plan
             torch.cuda.empty_cache()
+        if not staged and world > 1:
+            # ... and without a library collective: the exchange carried out by the reduction kernel over peer memory
+            plan = D.PartitionedPlan(N4, exchange="peer")
+            try:
+                ms = timed(lambda: plan.solve(k4))
+                plan.solve(k4)
+                sub["peer_exchange"] = dict(rate(N4 + 1, ms, bpd, world), graph=plan.graph is not None,
+                                            backward_error=plan.backward_error(), status_flags=plan.flags())
+            finally:
+                plan.close()
+                del plan
+                torch.cuda.empty_cache()
         entry[label] = sub
     res["config4_N2^27_k1000"] = entry
     # ---- strong-scaling sweep + the final gather ------------------------------------------

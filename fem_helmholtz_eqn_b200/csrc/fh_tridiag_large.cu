@@ -777,49 +777,146 @@ deep_backsub_level_kernel(UniformRows u, const __grid_constant__ DeepPlan dp, co
 // Tiny dense solve of the gathered interface system (2P rows, P = number of ranks): one thread,
 // Gaussian elimination with partial pivoting.  iface: [P][4][2] = per rank (a, b, c, d) x (first, last).
 constexpr int kIfaceMax = 32;  // up to 16 ranks (one NVSwitch domain)
-__global__ void spike_interface_kernel(const cplx *__restrict__ iface, int P, cplx *__restrict__ x,
-                                       int32_t *__restrict__ status) {
-    __shared__ cplx A[kIfaceMax][kIfaceMax + 1];
+typedef cplx IfaceMat[kIfaceMax][kIfaceMax + 1];
+// Called by every thread of the CTA (A in shared memory; barriers inside); the solution is written by thread 0 to x
+// (shared or global), *bad_out (thread 0's) tells whether it is finite.  LOAD(p, q) = entry q of rank p's 8 numbers.
+template <class Load>
+__device__ __forceinline__ void spike_interface_solve(Load load, int P, IfaceMat &A, cplx *x, bool *bad_out) {
     const int n = 2 * P;
     for (int i = threadIdx.x; i < n * (n + 1); i += blockDim.x) A[i / (n + 1)][i % (n + 1)] = czero();
     __syncthreads();
-    if (threadIdx.x != 0) return;
-    for (int p = 0; p < P; ++p)
-        for (int r = 0; r < 2; ++r) {
-            const int i = 2 * p + r;
-            const cplx *q = iface + (size_t)p * 8;
-            if (i > 0) A[i][i - 1] = q[0 + r];
-            A[i][i] = q[2 + r];
-            if (i < n - 1) A[i][i + 1] = q[4 + r];
-            A[i][n] = q[6 + r];
-        }
-    bool bad = false;
-    for (int k = 0; k < n; ++k) {
-        int piv = k;
-        double best = A[k][k].re * A[k][k].re + A[k][k].im * A[k][k].im;
-        for (int i = k + 1; i < min(n, k + 3); ++i) {  // tridiagonal + fill: only two rows below can be non-zero
-            const double v = A[i][k].re * A[i][k].re + A[i][k].im * A[i][k].im;
-            if (v > best) best = v, piv = i;
-        }
-        if (best == 0.0) bad = true;
-        if (piv != k)
-            for (int j = k; j <= n; ++j) {
-                const cplx tmp = A[k][j];
-                A[k][j] = A[piv][j], A[piv][j] = tmp;
+    if (threadIdx.x == 0) {
+        for (int p = 0; p < P; ++p)
+            for (int r = 0; r < 2; ++r) {
+                const int i = 2 * p + r;
+                if (i > 0) A[i][i - 1] = load(p, 0 + r);
+                A[i][i] = load(p, 2 + r);
+                if (i < n - 1) A[i][i + 1] = load(p, 4 + r);
+                A[i][n] = load(p, 6 + r);
             }
-        const cplx inv = crecip(A[k][k]);
-        for (int i = k + 1; i < min(n, k + 3); ++i) {
-            const cplx w = A[i][k] * inv;
-            for (int j = k; j <= n; ++j) A[i][j] = nmsub(A[i][j], w, A[k][j]);
+        bool bad = false;
+        for (int k = 0; k < n; ++k) {
+            int piv = k;
+            double best = A[k][k].re * A[k][k].re + A[k][k].im * A[k][k].im;
+            for (int i = k + 1; i < min(n, k + 3); ++i) {  // tridiagonal + fill: only two rows below can be non-zero
+                const double v = A[i][k].re * A[i][k].re + A[i][k].im * A[i][k].im;
+                if (v > best) best = v, piv = i;
+            }
+            if (best == 0.0) bad = true;
+            if (piv != k)
+                for (int j = k; j <= n; ++j) {
+                    const cplx tmp = A[k][j];
+                    A[k][j] = A[piv][j], A[piv][j] = tmp;
+                }
+            const cplx inv = crecip(A[k][k]);
+            for (int i = k + 1; i < min(n, k + 3); ++i) {
+                const cplx w = A[i][k] * inv;
+                for (int j = k; j <= n; ++j) A[i][j] = nmsub(A[i][j], w, A[k][j]);
+            }
+        }
+        for (int k = n - 1; k >= 0; --k) {
+            cplx sum = A[k][n];
+            for (int j = k + 1; j < min(n, k + 4); ++j) sum = nmsub(sum, A[k][j], x[j]);
+            x[k] = sum * crecip(A[k][k]);
+            bad |= !cfinite(x[k]);
+        }
+        *bad_out = bad;
+    }
+    __syncthreads();
+}
+__global__ void spike_interface_kernel(const cplx *__restrict__ iface, int P, cplx *__restrict__ x,
+                                       int32_t *__restrict__ status) {
+    __shared__ IfaceMat A;
+    bool bad = false;
+    spike_interface_solve([&](int p, int q) { return iface[(size_t)p * 8 + q]; }, P, A, x, &bad);
+    if (threadIdx.x == 0 && bad && status != nullptr) atomicOr(status, 1);
+}
+
+// ---- the exchange over peer memory ---------------------------------------------------------------------------------
+// Config 4's one exchange step is 128 bytes per rank, and what surrounds it on a rank are single-CTA kernels a few
+// microseconds long: a library all-gather between them costs more than they do (NCCL's small-message latency plus
+// two kernel boundaries).  So the exchange is part of the kernel: after its reduction, the CTA stores its two interface
+// rows straight into every peer's exchange buffer (symmetric memory: the same allocation on every rank, mapped over
+// NVLink), publishes a sequence number per peer with a system-scope release, waits -- acquire -- until every peer's
+// number has arrived in its own buffer, solves the 2P-row interface system and goes on with the small back-substitution
+// levels.  One kernel per rank from the first level down to the interface and back up to the 2^14-row level.
+// Slots and flags are double-buffered by the parity of the solve counter (a rank can be at most one solve ahead of a
+// peer: it cannot pass the wait of solve s before every peer has published s, i.e. has left solve s - 1 behind); the
+// counter lives in device memory and is advanced by the kernel, so a captured graph can be replayed.
+struct PeerSlots {
+    cplx iface[2][kIfaceMax / 2][8];              // [parity][source rank][a0 a1 b0 b1 c0 c1 d0 d1]
+    unsigned long long flag[2][kIfaceMax / 2];    // [parity][source rank] = solve counter of the data in the slot
+};
+struct PeerExchange {
+    void *const *peer_bufs;     // device array [n_ranks]: every rank's PeerSlots as mapped into this process
+    int rank, n_ranks;
+    unsigned long long *seq;    // this rank's solve counter (device memory, starts at 0)
+    unsigned long long timeout_ns;
+};
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ cplx ld_volatile_global(const cplx *p) {  // (a peer wrote it: never from a stale L1 line)
+    double2 v;
+    asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+    return mk(v.x, v.y);
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__global__ void __launch_bounds__(kDeepThreads)
+deep_solve_exchange_kernel(UniformRows u, const __grid_constant__ DeepPlan dp, DeepConsts *cs, PeerExchange ex,
+                           cplx *__restrict__ x_iface_out, cplx *__restrict__ u_out, int32_t *__restrict__ status) {
+    __shared__ DeepStage sg;
+    __shared__ DeepCarry carry[2];
+    // the interface matrix is needed before the small levels are staged, the stage set after: one piece of memory
+    constexpr size_t kRaw = sizeof(DeepStageSet) > sizeof(IfaceMat) ? sizeof(DeepStageSet) : sizeof(IfaceMat);
+    __shared__ __align__(16) unsigned char raw[kRaw];
+    __shared__ cplx xs[kIfaceMax];
+    IfaceMat &A = *reinterpret_cast<IfaceMat *>(raw);
+    DeepStageSet &set = *reinterpret_cast<DeepStageSet *>(raw);
+    const int t = threadIdx.x, P = ex.n_ranks;
+    u.fetch_k();
+    deep_reduce_levels(u, dp, cs, sg, carry);
+    const unsigned long long seq = *ex.seq + 1;
+    const int par = (int)(seq & 1ull);
+    // publish: 8 numbers to each of the P ranks (its own buffer included), then one flag per rank
+    if (t < 8 * P) {
+        const int p = t >> 3, e = t & 7;
+        PeerSlots *dst = static_cast<PeerSlots *>(ex.peer_bufs[p]);
+        dst->iface[par][ex.rank][e] = dp.ptr[dp.levels].a[e];  // (a[2] b[2] c[2] d[2] are contiguous)
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (t < P) st_release_sys(&static_cast<PeerSlots *>(ex.peer_bufs[t])->flag[par][ex.rank], seq);
+    // wait for every rank's rows in this rank's buffer
+    const PeerSlots *mine = static_cast<const PeerSlots *>(ex.peer_bufs[ex.rank]);
+    if (t < P) {
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(&mine->flag[par][t]) < seq) {
+            if (global_timer_ns() - t0 > ex.timeout_ns) {  // a peer never arrived: report, do not hang the GPU
+                if (status != nullptr) atomicOr(status, 5);
+                break;
+            }
         }
     }
-    for (int k = n - 1; k >= 0; --k) {
-        cplx s = A[k][n];
-        for (int j = k + 1; j < min(n, k + 4); ++j) s = nmsub(s, A[k][j], x[j]);
-        x[k] = s * crecip(A[k][k]);
-        bad |= !cfinite(x[k]);
-    }
-    if (bad && status != nullptr) atomicOr(status, 1);
+    __syncthreads();
+    bool bad = false;
+    spike_interface_solve([&](int p, int q) { return ld_volatile_global(&mine->iface[par][p][q]); }, P, A, xs, &bad);
+    if (t == 0 && bad && status != nullptr) atomicOr(status, 1);
+    if (t < 2 * P) x_iface_out[t] = xs[t];
+    if (t < 2) dp.ptr[dp.levels].x[t] = xs[2 * ex.rank + t];
+    __syncthreads();  // (also: A is dead, `set` may be written)
+    deep_backsub_small_levels(u, dp, cs, set, u_out, status != nullptr ? status + 1 : nullptr);
+    if (t == 0) *ex.seq = seq;
 }
 
 // ---------------------------------------------------------------------------------------------- host side
@@ -1187,6 +1284,36 @@ int fh_helmholtz1d_spike_reduce_kdev_c128(const fh_problem1d *prob_host, const d
     FH_REQUIRE(k_k2_dev != nullptr, "NULL pointer");
     return helm_spike_reduce(prob_host, 0.0, 0.0, k_k2_dev, row_begin, n_rows, workspace, workspace_bytes, iface8,
                              stream);
+}
+
+size_t fh_spike_peer_buffer_bytes(void) { return sizeof(fh::PeerSlots); }
+
+int fh_helmholtz1d_spike_solve_peer_kdev_c128(const fh_problem1d *prob_host, const double *k_k2_dev, int64_t row_begin,
+                                              int64_t n_rows, void *workspace, size_t workspace_bytes,
+                                              void *const *peer_bufs_dev, int rank, int n_ranks,
+                                              unsigned long long *seq_dev, double timeout_s, fh_c128 *x_iface,
+                                              fh_c128 *u, int32_t *status2, fh_stream_t stream) {
+    using namespace fh;
+    FH_REQUIRE(prob_host && k_k2_dev && workspace && peer_bufs_dev && seq_dev && x_iface && u, "NULL pointer");
+    FH_REQUIRE(n_ranks >= 1 && 2 * n_ranks <= kIfaceMax && rank >= 0 && rank < n_ranks, "bad rank / n_ranks (<= %d ranks)",
+               kIfaceMax / 2);
+    FH_REQUIRE(n_rows > 2, "a generated slab needs more than 2 rows");
+    HelmRows src;
+    int rc = helm_rows_from(prob_host, 0.0, 0.0, row_begin, n_rows, src);
+    if (rc != FH_OK) return rc;
+    src.kk = k_k2_dev;
+    DeepPlan dp;
+    DeepConsts *cs = nullptr;
+    if (!deep_plan(src, workspace, workspace_bytes, dp, cs)) return kdev_unsupported();
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    PeerExchange ex;
+    ex.peer_bufs = peer_bufs_dev, ex.rank = rank, ex.n_ranks = n_ranks, ex.seq = seq_dev;
+    ex.timeout_ns = (unsigned long long)((timeout_s > 0.0 ? timeout_s : 2.0) * 1e9);
+    const UniformRows ur = as_uniform(src);
+    deep_solve_exchange_kernel<<<1, kDeepThreads, 0, st>>>(ur, dp, cs, ex, reinterpret_cast<cplx *>(x_iface),
+                                                           reinterpret_cast<cplx *>(u), status2);
+    FH_LAUNCH_CHECK("deep_solve_exchange_kernel");
+    return deep_backsub_big_levels(ur, dp, cs, reinterpret_cast<cplx *>(u), status2 != nullptr ? status2 + 1 : nullptr, st);
 }
 
 int fh_spike_solve_interface_c128(const fh_c128 *iface_all, int n_ranks, fh_c128 *x_iface, int32_t *status,

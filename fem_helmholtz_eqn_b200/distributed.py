@@ -202,19 +202,30 @@ class PartitionedPlan:
     "assembled + solved" figure of the metric for config 4.  Default: the rows are generated inside the solver
     (16 B per row written, the periodic recursion).
 
-    With more than one rank the graph holds NCCL kernels: it is opt-in there (``use_graph=True``; measured on 2 x B200:
-    0.32 ms against 0.35 ms call by call at N = 2^27), and :meth:`close` must run before
-    ``dist.destroy_process_group()`` -- tearing the communicator down under a live graph blocks.
+    ``exchange="peer"`` (generated rows, more than one rank): no library collective -- the single-CTA kernel that
+    reduces the slab stores its two interface rows into every peer's exchange buffer (symmetric memory over NVLink),
+    publishes / awaits a sequence number per peer, solves the interface system and carries on with the small
+    back-substitution levels (``fh_helmholtz1d_spike_solve_peer_kdev_c128``); captured as a graph by default.  Every
+    rank must call ``solve`` the same number of times.
+
+    With ``exchange="nccl"`` and more than one rank the graph holds NCCL kernels: it is opt-in there
+    (``use_graph=True``; measured on 2 x B200: 0.35 ms against 0.37 ms call by call at N = 2^27), and :meth:`close`
+    must run before ``dist.destroy_process_group()`` -- tearing the communicator down under a live graph blocks.
 
     Accuracy: the solvers are unpivoted; their interface-row probe sets ``status`` (bit 1: defect > 5e-14, bit 0:
     breakdown).  :meth:`flags` combines it over the ranks, :meth:`backward_error` measures the normwise backward error of
     the whole solution on the device (rows re-generated, 16 B per row), :meth:`solve_checked` does both and repairs."""
 
-    def __init__(self, N, L=1.0, theta=0.0, *, group=None, use_graph=None, staged=False, **bc):
+    def __init__(self, N, L=1.0, theta=0.0, *, group=None, use_graph=None, staged=False, exchange="nccl", **bc):
         self.lib = _lib.require_cuda()
         self.N, self.n, self.L, self.group = int(N), int(N) + 1, float(L), group
         self.world, self.rank = _world(group)
         self.staged = bool(staged)
+        if exchange not in ("nccl", "peer"):
+            raise ValueError("exchange must be 'nccl' or 'peer'")
+        if exchange == "peer" and staged:
+            raise ValueError("exchange='peer' is the generated-row path (staged=False)")
+        self.exchange = exchange if self.world > 1 else "nccl"
         if self.n < 3 * self.world:
             raise ValueError(f"mesh of {self.n} nodes is too small to split over {self.world} ranks")
         dev = self.device = _lib.device()
@@ -236,8 +247,21 @@ class PartitionedPlan:
         self.res4 = torch.zeros(4, dtype=torch.float64, device=dev)
         self.graph = None
         self._feed = fem1d._WavenumberFeed(self.k_dev)
+        if self.exchange == "peer":
+            # one exchange buffer per rank in symmetric memory (the same allocation on every rank, every rank's mapped
+            # into every process over NVLink); the kernels own it from here on
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+            grp = group if group is not None else dist.group.WORLD
+            self._peer_buf = symm_mem.empty(self.lib.fh_spike_peer_buffer_bytes(), dtype=torch.uint8, device=dev)
+            self._peer_buf.zero_()
+            self._peer = symm_mem.rendezvous(self._peer_buf, grp)
+            self._peer_ptrs = int(self._peer.buffer_ptrs_dev)
+            self.seq_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+            torch.cuda.synchronize()
+            dist.barrier(group=group)        # every buffer is zero before anybody's first kernel stores into it
         if use_graph is None:                # default: graph on one rank; with a collective inside it is opt-in
-            use_graph = self.world == 1
+            use_graph = self.world == 1 or self.exchange == "peer"
         self._set_k(1.0)
         self._launch()                       # warm-up: module load, NCCL communicator, driver entry points
         torch.cuda.synchronize()
@@ -265,6 +289,12 @@ class PartitionedPlan:
         lib, st = self.lib, stream_ptr()
         self.status.zero_()
         of, ol = int(self.rank > 0), int(self.rank < self.world - 1)
+        if self.exchange == "peer":  # reduce -> exchange over peer memory -> interface solve -> back-substitution
+            check(lib.fh_helmholtz1d_spike_solve_peer_kdev_c128(
+                C.byref(self.prob), ptr(self.k_dev), self.begin, self.n_rows, ptr(self.ws), self.ws_bytes,
+                C.c_void_p(self._peer_ptrs), self.rank, self.world, ptr(self.seq_dev), 2.0, ptr(self.x), ptr(self.u),
+                ptr(self.status), st), "fh_helmholtz1d_spike_solve_peer_kdev_c128")
+            return
         if self.staged:
             B = self.bands
             check(lib.fh_assemble_1d_slab_c128(C.byref(self.prob), 0.0, 0.0, ptr(self.k_dev), self.begin, self.n_rows,

@@ -197,6 +197,24 @@ FH_API int fh_helmholtz1d_spike_backsub_kdev_c128(const fh_problem1d *prob_host,
                                            size_t workspace_bytes, const fh_c128 *x_first_last, fh_c128 *u,
                                            int32_t *status, fh_stream_t stream);
 
+/* Steps 1-4 as ONE sequence without a library collective: the exchange is carried out by the kernel itself over peer
+ * memory (the B200-native form of this path's one exchange step: 128 bytes per rank between kernels a few microseconds
+ * long).  peer_bufs_dev: device array [n_ranks] of pointers to every rank's exchange buffer as mapped into this process
+ * (symmetric memory over NVLink: cudaIpc / VMM / torch.distributed._symmetric_memory; fh_spike_peer_buffer_bytes() bytes
+ * each, zero-initialised once, then owned by these calls).  After its reduction the single-CTA kernel stores its two
+ * interface rows into every peer's buffer, publishes its solve counter with a system-scope release, waits (acquire) for
+ * every peer's, solves the 2P-row interface system and back-substitutes.  seq_dev: this rank's solve counter (device
+ * uint64, zero before the first call, advanced by the kernel -- a captured graph of the call can be replayed).  Every
+ * rank must issue the same sequence of calls.  timeout_s (<= 0: 2 s): a peer that never arrives sets status2[0] |= 5
+ * instead of hanging the GPU.  x_iface: complex128[2 n_ranks] (as fh_spike_solve_interface_c128); status2: int32[2]
+ * (interface solve, back-substitution; may be NULL).  Uniform meshes (FH_E_UNSUPPORTED otherwise). */
+FH_API size_t fh_spike_peer_buffer_bytes(void);
+FH_API int fh_helmholtz1d_spike_solve_peer_kdev_c128(const fh_problem1d *prob_host, const double *k_k2_dev,
+                                              int64_t row_begin, int64_t n_rows, void *workspace,
+                                              size_t workspace_bytes, void *const *peer_bufs_dev, int rank,
+                                              int n_ranks, unsigned long long *seq_dev, double timeout_s,
+                                              fh_c128 *x_iface, fh_c128 *u, int32_t *status2, fh_stream_t stream);
+
 /* ---- residual / parity metrics on device -------------------------------------------------------
  * out[s] = { ||b - A u||_2^2, ||u||_2^2, ||b||_2^2, ||A||_inf } for each system s (device fp64[batch][4]). */
 FH_API int fh_tridiag_residual_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c128 *du, const fh_c128 *b,

@@ -385,6 +385,14 @@ def test_nccl_partitioned_two_gpus(tmp_path):
         "    b2, e2, ref = D.solve_partitioned(N, kk)\n"
         "    assert (b, e) == (b2, e2) and torch.equal(ul, ref) and not plan.singular(), kk\n"
         "plan.close()\n"
+        "peer = D.PartitionedPlan(N, exchange='peer')  # the exchange inside the kernel, over peer memory\n"
+        "assert peer.graph is not None\n"
+        "for kk in (1000.0, 37.5, 10.0, 999.0, 512.25):  # (odd and even solve counters: both slot parities)\n"
+        "    b, e, ul = peer.solve(kk)\n"
+        "    b2, e2, ref = D.solve_partitioned(N, kk)\n"
+        "    assert (b, e) == (b2, e2) and torch.equal(ul, ref) and peer.flags() == 0, kk\n"
+        "    assert peer.backward_error() < 1e-15\n"
+        "peer.close()\n"
         "lo, hi, U = D.sweep_sharded(4096, np.linspace(1, 1000, 64))\n"
         "assert U.shape == (32, 4097)\n"
         "dist.destroy_process_group(); print('rank', r, 'ok', be)\n")

@@ -1,7 +1,7 @@
 """BASELINE config 4 through distributed.PartitionedPlan under torchrun: checks the plan against solve_partitioned
 (same bits) and times solve(k) on the device (CUDA events, max over ranks).
 
-    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 tools/plan_probe.py [graph|eager] [log2 N]
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 tools/plan_probe.py [graph|eager|peer] [log2 N]
 """
 import json
 import os
@@ -21,7 +21,7 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 world, rank = dist.get_world_size(), dist.get_rank()
 print("rank", rank, "start", mode, flush=True)
-plan = D.PartitionedPlan(N, use_graph=(mode == "graph"))
+plan = (D.PartitionedPlan(N, exchange="peer") if mode == "peer" else D.PartitionedPlan(N, use_graph=(mode == "graph")))
 print("rank", rank, "plan built, graph =", plan.graph is not None, flush=True)
 for k in (1000.0, 37.5):
     b, e, u = plan.solve(k)
