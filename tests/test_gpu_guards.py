@@ -70,7 +70,8 @@ def test_batched_paths_write_exactly_their_outputs(N):
     check(lib.fh_helmholtz1d_sweep_fused_c128(C.byref(prob), ptr(ks_d.view), ptr(k2s_d.view), n_k, ptr(U2.view),
                                               ptr(st2.view), None, 0, stream_ptr()), "fused")
     U2.check(), st2.check()
-    assert torch.equal(U2.view, ref)
+    same_bits = lambda x, y: torch.equal(torch.view_as_real(x).view(torch.int64), torch.view_as_real(y).view(torch.int64))
+    assert same_bits(U2.view, ref)        # (bit patterns: a broken-down system -- k h = 2 at N = 1 -- holds NaNs in both)
     if N >= 2:
         b3 = [Guarded((n_k, n)) for _ in range(4)]
         U3, st3 = Guarded((n_k, n)), Guarded((n_k,), torch.int32)
@@ -80,7 +81,7 @@ def test_batched_paths_write_exactly_their_outputs(N):
         for g, want in zip(b3 + [U3, st3], [b.view for b in bands] + [ref, None]):
             g.check()
             if want is not None:
-                assert torch.equal(g.view, want)
+                assert same_bits(g.view, want)
     # pivoted kernel on the same bands (u must not alias b)
     X, stp = Guarded((n_k, n)), Guarded((n_k,), torch.int32)
     ws_bytes = lib.fh_tridiag_solve_pivoted_workspace_bytes(n, n_k)
@@ -88,7 +89,7 @@ def test_batched_paths_write_exactly_their_outputs(N):
     check(lib.fh_tridiag_solve_pivoted_c128(*(ptr(b.view) for b in bands), ptr(X.view), n, n_k, ptr(stp.view), ptr(ws.view),
                                             ws_bytes, stream_ptr()), "pivoted")
     X.check(), stp.check(), ws.check(written=False)
-    assert fh.tridiagonal_residual(*(b.view for b in bands), X.view)["backward"].max() < 1e-14
+    assert np.nanmax(fh.tridiagonal_residual(*(b.view for b in bands), X.view)["backward"]) < 1e-14
 
 
 @pytest.mark.parametrize("N", [4112, 4128, 16 * 1024 + 1, 131_089, 1024 * 1024 + 1])
