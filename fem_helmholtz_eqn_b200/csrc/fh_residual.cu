@@ -599,38 +599,61 @@ pivoted_gtsv_kernel(const cplx *__restrict__ dl, const cplx *__restrict__ d, con
     }
 }
 
-// Repair of the systems whose status carries the breakdown bit (bit 0), decided and carried out on the device:
-//   header[0] = number of such systems (from compact_flagged_kernel), list = their indices
+// Repair of the systems whose status carries the breakdown bit (bit 0), decided and carried out on the device.  Every
+// CTA scans its own contiguous share of status[] (no compaction pass, no list: on the usual step nothing is flagged and
+// the kernel is a 256 KB read) and deals with what it finds there:
 //   per system: normwise backward error of the solution that is there (refinement may already have repaired it);
 //               finite and <= accept_tol -> kept, bit 0 cleared;   otherwise -> re-solved with partial pivoting,
 //               status = 1 only if that solution is not finite either (singular to working precision)
-//   header[2] += kept, header[3] += re-solved, header[4] += singular
+//   header[0] += flagged, header[2] += kept, header[3] += re-solved, header[4] += singular
 __global__ void __launch_bounds__(kPivThreads)
 repair_flagged_kernel(const cplx *__restrict__ dl, const cplx *__restrict__ d, const cplx *__restrict__ du,
-                      const cplx *__restrict__ b, cplx *__restrict__ u, int64_t n, const int32_t *__restrict__ list,
+                      const cplx *__restrict__ b, cplx *__restrict__ u, int64_t n, int64_t batch, int64_t per_cta,
                       int32_t *__restrict__ header, double accept_tol, cplx *__restrict__ work,
                       int32_t *__restrict__ status) {
     __shared__ PivSmem sm;
+    __shared__ int found[kPivThreads], sorted[kPivThreads];
+    __shared__ int n_found;
     cplx *fac = work + (size_t)blockIdx.x * 4 * (size_t)n;
-    const int count = header[0];
-    for (int i = blockIdx.x; i < count; i += gridDim.x) {
-        const int64_t s = list[i], o = s * n;
-        double m4[4];
-        cta_residual(dl + o, d + o, du + o, b + o, u + o, n, sm.red, m4);
-        const double be = sqrt(m4[0]) / (m4[3] * sqrt(m4[1]) + sqrt(m4[2]));
-        if (be <= accept_tol) {  // (false for NaN)
-            if (threadIdx.x == 0) {
-                status[s] &= ~1;
-                atomicAdd(&header[2], 1);
+    const int64_t s_begin = (int64_t)blockIdx.x * per_cta;
+    const int64_t s_end = s_begin + per_cta < batch ? s_begin + per_cta : batch;
+    for (int64_t s0 = s_begin; s0 < s_end; s0 += kPivThreads) {
+        const int64_t mine = s0 + threadIdx.x;
+        const bool flagged = mine < s_end && (status[mine] & 1) != 0;
+        if (__syncthreads_or(flagged ? 1 : 0) == 0) continue;   // (the usual case)
+        if (threadIdx.x == 0) n_found = 0;
+        __syncthreads();
+        if (flagged) found[atomicAdd(&n_found, 1)] = (int)(mine - s0);
+        __syncthreads();
+        const int count = n_found;
+        if ((int)threadIdx.x < count) {   // ascending order, whatever order the atomics came in
+            const int v = found[threadIdx.x];
+            int rank = 0;
+            for (int w = 0; w < count; ++w) rank += found[w] < v ? 1 : 0;
+            sorted[rank] = v;
+        }
+        __syncthreads();
+        for (int i = 0; i < count; ++i) {
+            const int64_t s = s0 + sorted[i], o = s * n;
+            double m4[4];
+            cta_residual(dl + o, d + o, du + o, b + o, u + o, n, sm.red, m4);
+            const double be = sqrt(m4[0]) / (m4[3] * sqrt(m4[1]) + sqrt(m4[2]));
+            if (threadIdx.x == 0) atomicAdd(&header[0], 1);
+            if (be <= accept_tol) {  // (false for NaN)
+                if (threadIdx.x == 0) {
+                    status[s] &= ~1;
+                    atomicAdd(&header[2], 1);
+                }
+                continue;
             }
-            continue;
+            const bool singular = cta_pivoted_solve(dl + o, d + o, du + o, b + o, u + o, n, fac, sm);
+            if (threadIdx.x == 0) {
+                status[s] = singular ? 1 : 0;
+                atomicAdd(&header[3], 1);
+                if (singular) atomicAdd(&header[4], 1);
+            }
         }
-        const bool singular = cta_pivoted_solve(dl + o, d + o, du + o, b + o, u + o, n, fac, sm);
-        if (threadIdx.x == 0) {
-            status[s] = singular ? 1 : 0;
-            atomicAdd(&header[3], 1);
-            if (singular) atomicAdd(&header[4], 1);
-        }
+        __syncthreads();
     }
 }
 
@@ -710,13 +733,11 @@ extern "C" int fh_tridiag_repair_flagged_c128(const fh_c128 *dl, const fh_c128 *
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     char *ws = static_cast<char *>(workspace);
     int32_t *header = reinterpret_cast<int32_t *>(ws + p.off_header);
-    int32_t *list = reinterpret_cast<int32_t *>(ws + p.off_list);
     FH_CUDA(cudaMemsetAsync(header, 0, 8 * sizeof(int32_t), st));
-    compact_flagged_kernel<<<1, kCompactThreads, 0, st>>>(status, batch, 1, (int32_t)batch, list, header);
-    FH_LAUNCH_CHECK("compact_flagged_kernel");
+    const int64_t per_cta = (batch + slots - 1) / slots;
     repair_flagged_kernel<<<(unsigned)slots, kPivThreads, 0, st>>>(
         reinterpret_cast<const cplx *>(dl), reinterpret_cast<const cplx *>(d), reinterpret_cast<const cplx *>(du),
-        reinterpret_cast<const cplx *>(b), reinterpret_cast<cplx *>(u), n, list, header, accept_tol,
+        reinterpret_cast<const cplx *>(b), reinterpret_cast<cplx *>(u), n, batch, per_cta, header, accept_tol,
         reinterpret_cast<cplx *>(ws + p.off_work), status);
     FH_LAUNCH_CHECK("repair_flagged_kernel");
     return FH_OK;
