@@ -38,6 +38,46 @@ def test_invalid_arguments_are_reported_without_gpu():
     assert rc == -1 and b"n_elem" in lib.fh_last_error()
 
 
+def test_round2_entry_points_validate_their_arguments_without_gpu():
+    """Host-side halves of the entry points added in round 2: workspace queries and argument checks (no kernel runs)."""
+    lib = fh._lib.load()
+    n, batch = 4097, 1000
+    # workspaces: 64 B per row per re-solve in flight (+ the per-batch bookkeeping); queries are monotone
+    piv1, piv8 = lib.fh_tridiag_solve_pivoted_workspace_bytes(n, 1), lib.fh_tridiag_solve_pivoted_workspace_bytes(n, 8)
+    assert piv1 == 64 * n and piv8 == 8 * piv1
+    assert lib.fh_tridiag_solve_pivoted_workspace_bytes(n, 10**6) == 256 * piv1            # capped concurrency
+    rep = lib.fh_tridiag_repair_flagged_workspace_bytes(n, batch, 4)
+    assert rep > 4 * piv1 and rep > lib.fh_tridiag_repair_flagged_workspace_bytes(n, batch, 2)
+    assert lib.fh_helmholtz1d_residual_workspace_bytes() > 0 and lib.fh_spike_peer_buffer_bytes() >= 2 * 16 * 128
+    assert lib.fh_q4_l2_error_workspace_bytes() > 0
+    # the geometry table of the non-uniform assembly: 48 B per mesh row, only where it pays
+    assert lib.fh_assemble_1d_workspace_bytes(4096, 1, 8) == 48 * 4097
+    assert lib.fh_assemble_1d_workspace_bytes(4096, 1, 7) == 0 and lib.fh_assemble_1d_workspace_bytes(4096, 0, 100) == 0
+    p = fh._lib.Problem1d(n_elem=100, h=0.01, h_mode=0, bc_left=0, bc_right=1)
+    rc = lib.fh_assemble_1d_slab_c128(ctypes.byref(p), 1.0, 1.0, None, 50, 60, None, None, None, None, None)
+    assert rc == -1 and b"outside the mesh" in lib.fh_last_error()
+    rc = lib.fh_helmholtz1d_residual_c128(ctypes.byref(p), 1.0, 1.0, None, 0, 101, None, None, None, None, None, 0, None)
+    assert rc == -1 and b"NULL" in lib.fh_last_error()
+    rc = lib.fh_tridiag_repair_flagged_c128(None, None, None, None, None, 10, 10, None, 1e-13, None, 0, None)
+    assert rc == -1 and b"NULL" in lib.fh_last_error()
+    rc = lib.fh_helmholtz1d_spike_solve_peer_kdev_c128(ctypes.byref(p), None, 0, 101, None, 0, None, 0, 2, None, 2.0, None,
+                                                       None, None, None)
+    assert rc == -1 and b"NULL" in lib.fh_last_error()
+    rc = lib.fh_compact_flags_i32(None, 10, None, None, None)
+    assert rc == -1
+
+
+def test_pipeline_choice_is_host_logic():
+    from fem_helmholtz_eqn_b200 import fem1d
+    assert fem1d._pick_pipeline(None, False, 4096, False) == "one_pass"      # uniform mesh within the batched size
+    assert fem1d._pick_pipeline(None, False, 4112, False) == "staged"        # 4113 nodes: too long for the one-pass kernel
+    assert fem1d._pick_pipeline(None, False, 4096, True) == "staged"         # non-uniform mesh
+    assert fem1d._pick_pipeline(None, True, 4096, False) == "fused"          # the legacy switch
+    assert fem1d._pick_pipeline("staged", True, 4096, False) == "staged"     # an explicit choice wins
+    with pytest.raises(ValueError):
+        fem1d._pick_pipeline("fastest", False, 4096, False)
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
