@@ -80,6 +80,8 @@ _SIGNATURES = {
                                                         _P, _P]),
     "fh_helmholtz1d_spike_backsub_kdev_c128": (C.c_int, [C.POINTER(Problem1d), _P, C.c_int64, C.c_int64, _P, C.c_size_t,
                                                          _P, _P, _P, _P]),
+    "fh_helmholtz1d_spike_reduce_store_c128": (C.c_int, [C.POINTER(Problem1d), C.c_double, C.c_double, _P, C.c_int64,
+                                                         C.c_int64, _P, _P, _P, _P, _P, C.c_size_t, _P, _P]),
     "fh_spike_peer_buffer_bytes": (C.c_size_t, []),
     "fh_helmholtz1d_spike_solve_peer_kdev_c128": (C.c_int, [C.POINTER(Problem1d), _P, C.c_int64, C.c_int64, _P, C.c_size_t,
                                                             _P, C.c_int, C.c_int, _P, C.c_double, _P, _P, _P, _P]),

@@ -118,19 +118,39 @@ struct HelmRows {  // level-0 rows generated from the Helmholtz problem: local r
     int64_t g_off, n;
     __device__ __forceinline__ bool open_first_row() const { return g_off > 0; }
     __device__ __forceinline__ bool open_last_row() const { return g_off + n - 1 < p.n_elem; }
-    __device__ __forceinline__ void fill(LargeSmem &sm, int64_t row0, int rows) const {
+    // STORE: the generated rows are also written out (out_* = the slab's dl, d, du, b: what fh_assemble_1d_slab_c128 would
+    // have stored, bit for bit), so that "assemble the slab, keep A, solve" costs 64 B per row written here instead of
+    // 64 written by the assembly kernel + 64 read back by this one.
+    template <bool STORE>
+    __device__ __forceinline__ void fill_impl(LargeSmem &sm, int64_t row0, int rows, cplx *out_dl, cplx *out_d,
+                                              cplx *out_du, cplx *out_b) const {
         // scalar-h (the reference's mode): every interior row is the same -- evaluate it once per thread
         const bool scalar = p.h_mode == FH_H_SCALAR && p.n_elem >= 2;
+        double kv = k, k2v = k2;
+        if (kk != nullptr) kv = __ldg(kk), k2v = __ldg(kk + 1);
         cplx il = czero(), id = czero(), iu = czero(), ib = czero();
-        if (scalar) row_values(p, row_geom(p, 1), 1, k, k2, il, id, iu, ib);
+        if (scalar) row_values(p, row_geom(p, 1), 1, kv, k2v, il, id, iu, ib);
         for (int j = threadIdx.x; j < rows; j += kLT) {
             const int64_t g = g_off + row0 + j;
             cplx lo = il, di = id, hi = iu, rhs = ib;
-            if (!scalar || g == 0 || g == p.n_elem) row_values(p, row_geom(p, g), g, k, k2, lo, di, hi, rhs);
+            if (!scalar || g == 0 || g == p.n_elem) row_values(p, row_geom(p, g), g, kv, k2v, lo, di, hi, rhs);
             const int s = lswz(j);
             sm.a[s] = lo, sm.b[s] = di, sm.c[s] = hi, sm.d[s] = rhs;
+            if (STORE) {
+                const int64_t o = row0 + j;
+                stg_stream(out_dl + o, lo), stg_stream(out_d + o, di), stg_stream(out_du + o, hi), stg_stream(out_b + o, rhs);
+            }
         }
         __syncthreads();
+    }
+    __device__ __forceinline__ void fill(LargeSmem &sm, int64_t row0, int rows) const {
+        fill_impl<false>(sm, row0, rows, nullptr, nullptr, nullptr, nullptr);
+    }
+};
+struct HelmRowsStore : HelmRows {  // level 0 of "assemble + keep A + solve" on one long mesh / one slab of it
+    cplx *out_dl, *out_d, *out_du, *out_b;
+    __device__ __forceinline__ void fill(LargeSmem &sm, int64_t row0, int rows) const {
+        fill_impl<true>(sm, row0, rows, out_dl, out_d, out_du, out_b);
     }
 };
 
@@ -1314,6 +1334,34 @@ int fh_helmholtz1d_spike_solve_peer_kdev_c128(const fh_problem1d *prob_host, con
                                                            reinterpret_cast<cplx *>(u), status2);
     FH_LAUNCH_CHECK("deep_solve_exchange_kernel");
     return deep_backsub_big_levels(ur, dp, cs, reinterpret_cast<cplx *>(u), status2 != nullptr ? status2 + 1 : nullptr, st);
+}
+
+int fh_helmholtz1d_spike_reduce_store_c128(const fh_problem1d *prob_host, double k, double k2, const double *k_k2_dev,
+                                           int64_t row_begin, int64_t n_rows, fh_c128 *dl, fh_c128 *d, fh_c128 *du,
+                                           fh_c128 *b, void *workspace, size_t workspace_bytes, fh_c128 *iface8,
+                                           fh_stream_t stream) {
+    using namespace fh;
+    FH_REQUIRE(prob_host && dl && d && du && b && iface8, "NULL pointer");
+    FH_REQUIRE(n_rows > 2, "a generated slab needs more than 2 rows");
+    HelmRowsStore src;
+    int rc = helm_rows_from(prob_host, k, k2, row_begin, n_rows, src);
+    if (rc != FH_OK) return rc;
+    src.kk = k_k2_dev;
+    src.out_dl = reinterpret_cast<cplx *>(dl), src.out_d = reinterpret_cast<cplx *>(d);
+    src.out_du = reinterpret_cast<cplx *>(du), src.out_b = reinterpret_cast<cplx *>(b);
+    const LevelPlan pl = plan_levels(n_rows, 2);
+    if (workspace_bytes < pl.total || !workspace) {
+        set_error("workspace too small: need %zu bytes", pl.total);
+        return FH_E_WORKSPACE;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // level 0: rows generated, stored and reduced in one pass; the levels below as for stored bands (the slab's outermost
+    // rows keep their coupling to the neighbouring ranks: generated rows carry exact zeros at the mesh ends)
+    rc = reduce_all(src, pl, workspace, 1, 1, st);
+    if (rc != FH_OK) return rc;
+    const LevelPtrs top = level_ptrs(workspace, pl, pl.levels);
+    FH_CUDA(cudaMemcpyAsync(iface8, top.a, 8 * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
+    return FH_OK;
 }
 
 int fh_spike_solve_interface_c128(const fh_c128 *iface_all, int n_ranks, fh_c128 *x_iface, int32_t *status,

@@ -197,8 +197,9 @@ class PartitionedPlan:
     calls (at 2^24 rows per GPU the device work is ~0.1 ms -- less than issuing it call by call takes).
     Results are bit-identical to ``solve_partitioned(N, k)``.  Uniform meshes (the reference's only mode).
 
-    ``staged=True``: A is materialised, as ``assembly()`` does (nb:185-187) -- every rank assembles the bands of its
-    slab (64 B per row written), reduces and back-substitutes from the stored bands (64 + 64 + 16 + 18 B per row): the
+    ``staged=True``: A is materialised, as ``assembly()`` does (nb:185-187) -- every rank generates, stores and reduces
+    the bands of its slab in one pass (64 B per row written) and back-substitutes from the stored bands (64 read + 16
+    written, + 18 for the interface levels: 162 B per row in all; with a separate assembly kernel 226): the
     "assembled + solved" figure of the metric for config 4.  Default: the rows are generated inside the solver
     (16 B per row written, the periodic recursion).
 
@@ -296,11 +297,13 @@ class PartitionedPlan:
                 ptr(self.status), st), "fh_helmholtz1d_spike_solve_peer_kdev_c128")
             return
         if self.staged:
+            # level 0 generates the slab's rows, writes them out as the bands (bit-identical to the assembly kernel's) and
+            # reduces them in one pass: A is written once and read once (by the back-substitution)
             B = self.bands
-            check(lib.fh_assemble_1d_slab_c128(C.byref(self.prob), 0.0, 0.0, ptr(self.k_dev), self.begin, self.n_rows,
-                                               ptr(B[0]), ptr(B[1]), ptr(B[2]), ptr(B[3]), st), "fh_assemble_1d_slab_c128")
-            check(lib.fh_spike_reduce_c128(ptr(B[0]), ptr(B[1]), ptr(B[2]), ptr(B[3]), self.n_rows, of, ol, ptr(self.ws),
-                                           self.ws_bytes, ptr(self.iface), st), "fh_spike_reduce_c128")
+            check(lib.fh_helmholtz1d_spike_reduce_store_c128(C.byref(self.prob), 0.0, 0.0, ptr(self.k_dev), self.begin,
+                                                             self.n_rows, ptr(B[0]), ptr(B[1]), ptr(B[2]), ptr(B[3]),
+                                                             ptr(self.ws), self.ws_bytes, ptr(self.iface), st),
+                  "fh_helmholtz1d_spike_reduce_store_c128")
         else:
             check(lib.fh_helmholtz1d_spike_reduce_kdev_c128(C.byref(self.prob), ptr(self.k_dev), self.begin, self.n_rows,
                                                             ptr(self.ws), self.ws_bytes, ptr(self.iface), st),

@@ -175,6 +175,16 @@ FH_API int fh_spike_reduce_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c1
 FH_API int fh_helmholtz1d_spike_reduce_c128(const fh_problem1d *prob_host, double k, double k2, int64_t row_begin,
                                      int64_t n_rows, void *workspace, size_t workspace_bytes, fh_c128 *iface8,
                                      fh_stream_t stream);
+/* Step 1 for "assemble the slab, KEEP A, solve" (nb:203-204 on a mesh split over ranks; BASELINE config 4 with A
+ * materialised): the level-0 rows are generated, written out as the slab's bands dl, d, du, b (complex128[n_rows] each:
+ * what fh_assemble_1d_slab_c128 stores, bit for bit) and reduced in the same pass -- 64 B per row written instead of 64
+ * written by the assembly + 64 read back by fh_spike_reduce_c128; step 4 is fh_spike_backsub_c128 on the stored bands
+ * (open_first = slab does not start the mesh, open_last = does not end it).  162 instead of 226 B per row in all.
+ * k_k2_dev != NULL: (k, k**2) from device memory (graph replays). */
+FH_API int fh_helmholtz1d_spike_reduce_store_c128(const fh_problem1d *prob_host, double k, double k2,
+                                           const double *k_k2_dev, int64_t row_begin, int64_t n_rows, fh_c128 *dl,
+                                           fh_c128 *d, fh_c128 *du, fh_c128 *b, void *workspace,
+                                           size_t workspace_bytes, fh_c128 *iface8, fh_stream_t stream);
 FH_API int fh_spike_solve_interface_c128(const fh_c128 *iface_all, int n_ranks, fh_c128 *x_iface, int32_t *status,
                                   fh_stream_t stream);
 FH_API int fh_spike_backsub_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c128 *du, const fh_c128 *b,

@@ -309,8 +309,10 @@ def test_staged_partitioned_pieces_assembled_slabs(world):
             assert be_host < 1e-14
             # (both are rounding-level residuals, evaluated with different roundings: same size, not same digits)
             assert 0.5 * be_host < plan.backward_error() < 2.0 * be_host
-            if kk == k:
+            if kk == k:   # the plan writes A from its level-0 reduction: same bands, same solution, bit for bit
                 assert torch.equal(up, u)
+                for i in range(4):
+                    assert torch.equal(plan.bands[i], slabs[0][0][i])
         plan.close()
 
 
