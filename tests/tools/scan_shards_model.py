@@ -1,7 +1,7 @@
 """CPU scan of a wavenumber shard of the bench sweep with the numpy model of the batched kernel
 (tests/models/partition_pcr_model.py): which systems would the unpivoted elimination leave with a raw backward error
 above 1e-10, and does ONE refinement step bring them to LAPACK quality (the acceptance check of
-fem1d.resolve_nonfinite)?  No GPU.  ~1.5 ms per system: split the 65,536 systems of a shard over the cores.
+fem1d.repair_flagged)?  No GPU.  ~1.5 ms per system: split the 65,536 systems of a shard over the cores.
 
     python tests/tools/scan_shards_model.py WORLD RANK [first] [last]        # rank RANK of a WORLD-rank job: ks[RANK::WORLD]
 
