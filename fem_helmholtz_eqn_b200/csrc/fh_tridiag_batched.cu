@@ -686,6 +686,12 @@ tridiag_batched_kernel(const __grid_constant__ TensorMaps maps, const __grid_con
     if (CLUSTER > 1) cg::this_cluster().sync();  // no CTA leaves while its partner may still address it
 }
 
+}  // namespace fh
+
+#include "fh_tridiag_pipe.cuh"
+
+namespace fh {
+
 // ----------------------------------------------------------------------------------------------
 // Host side
 // ----------------------------------------------------------------------------------------------
@@ -712,8 +718,10 @@ static int launch_batched(const Source &src, const cplx *const bands[4], cplx *u
     // batch = number of right-hand sides / solutions (an upper bound when src.count is set); batch_matrices = number
     // of systems in the dl / d / du arrays when it differs (subset refinement)
     if (batch_matrices < 0) batch_matrices = batch;
-    auto kernel = tridiag_batched_kernel<CLUSTER, Source>;
-    const size_t smem = sizeof(BatchedSmem) + 1024;  // slack for the in-kernel 1024-byte round-up
+    // development switch: FH_BATCHED=serial launches the one-role-per-CTA kernel the pipeline replaced
+    static const bool serial = [] { const char *e = getenv("FH_BATCHED"); return e != nullptr && e[0] == 's'; }();
+    auto kernel = serial ? tridiag_batched_kernel<CLUSTER, Source> : tridiag_pipe_kernel<CLUSTER, Source>;
+    const size_t smem = (serial ? sizeof(BatchedSmem) : sizeof(PipeSmem)) + 1024;  // slack for the 1024-byte round-up
     if (smem > smem_optin_bytes()) {
         set_error("kernel needs %zu B of shared memory, device offers %zu", smem, smem_optin_bytes());
         return FH_E_UNSUPPORTED;
@@ -752,7 +760,7 @@ static int launch_batched(const Source &src, const cplx *const bands[4], cplx *u
     if (groups > batch) groups = batch;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(groups * CLUSTER));
-    cfg.blockDim = dim3(kT);
+    cfg.blockDim = dim3(serial ? kT : pipe_threads<Source>());
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];

@@ -1,0 +1,587 @@
+// The batched cluster solver as a PIPELINE of warp roles (included by fh_tridiag_batched.cu; same algorithm, same
+// row -> CTA -> thread maps, same tensor maps as tridiag_batched_kernel).
+//
+// Why: one system kept a CTA busy for ~8,800 cycles of which every phase is a dependent chain (8 warps, all
+// registers taken), while the memory side needed ~7,300: latency-bound at 0.83 of the HBM roofline, and nothing could
+// overlap because registers + shared memory hold exactly one system in flight and one in prefetch.  Here the phases of
+// CONSECUTIVE systems overlap on one SM:
+//
+//   warps 0..7   "E/B"  elimination of system s+1 (tile reads, downward / upward sweep, interface row), then
+//                       back-substitution + probe + TMA store of system s;
+//   warps 8..11  "I"    interface system of system s+1 in shared memory (cyclic-reduction step, PCR with one thread
+//                       per surviving row, cluster exchange through DSMEM, cut solve), concurrently with B(s), E(s+2);
+//   warps 12..15 "S"    (one-pass assemble+solve only) the band stores of A: tiles of identical rows filled and sent
+//                       by TMA, decoupled from everything else.
+//
+// What makes it fit: the state a thread must keep between its elimination and its back-substitution (7 rows x
+// (a, c, d) pre-scaled by the pivot reciprocal + the original interface row for the probe = 50 doubles) is PARKED IN
+// TENSOR MEMORY (tcgen05.st / tcgen05.ld, 32x32b: every thread owns one lane x 256 columns; two parking buffers of 100
+// columns).  The 256 KB of TMEM are otherwise idle in this kernel; measured (tools/tmem_probe.cu) 466 cycles to park
+// and 295 to un-park the 100 KB of a CTA.  Register budgets are re-balanced with setmaxnreg (E/B 200, I 96 of a
+// 384-thread CTA; E/B 192, I 88, S 40 of the 512-thread one-pass CTA).  Roles hand over through named barriers
+// (bar.arrive by the producer, bar.sync by the consumer):
+//   FullFree  I -> E   `full` (raw interface rows) consumed        FullReady  E -> I   `full` written
+//   X0 / X1   I -> B   interface unknowns of an even / odd system are in `xi`
+#pragma once
+
+#include "fh_tmem.cuh"
+
+namespace fh {
+
+constexpr int kEBThreads = kT;   // 256
+constexpr int kIThreads = kH;    // 128: one per interface row that survives the cyclic-reduction step
+constexpr int kSThreads = 128;
+constexpr int kParkDoubles = 6 * (kM - 1) + 8;   // 50
+constexpr int kParkCols = 2 * kParkDoubles;      // 100 columns of 32 bits per thread and system
+constexpr uint32_t kParkStride = 128;            // columns between a thread's two parking buffers
+static_assert(kParkCols == 100 && kParkCols <= (int)kParkStride, "parking layout");
+
+enum : int { kBarEB = 1, kBarI = 2, kBarFullReady = 3, kBarFullFree = 4, kBarX0 = 5, kBarX1 = 6, kBarS = 7 };
+constexpr int kRegsEB = 200, kRegsI = 96;                      // 256 * 200 + 128 * 96 <= 384 * 168
+constexpr int kRegsEB1 = 192, kRegsI1 = 88, kRegsS1 = 40;      // 256 * 192 + 128 * 88 + 128 * 40 = 512 * 128
+
+// PCR arrays of the I group: kH rows each, kHalfPad zero rows before and after (the largest PCR stride); the pad behind
+// one array is the pad in front of the next
+constexpr int kPcrArr = kH + kHalfPad;                 // entries from one array to the next: 192
+constexpr int kPcrEntries = kHalfPad + 4 * kPcrArr;    // 832
+
+struct __align__(1024) PipeSmem {
+    cplx stage[4][kSlots];      // TMA destination: bands of the NEXT system (one-pass: 2 x 4 band tiles of 16 KB)
+    cplx xs[kSlots];            // TMA source: solution of the system being back-substituted
+    cplx row0[3][kT];           // normalised first rows of the chunks (read by the thread above)
+    cplx full[4][kT + 1];       // raw interface rows A, C, D, V; entry kT is a zero row
+    cplx half[2][kPcrEntries];  // PCR ping-pong over the odd interface rows: [pad][A][pad][C][pad][D][pad][V][pad]
+    cplx xi[2][kT + 2];         // [parity]: 0, the kT interface unknowns, x_partner
+    cplx headst[4][kHeadMax];   // head rows of the next system (cp.async by one thread)
+    cplx headf[2][2][kHeadMax]; // [parity]: elimination factors of the head rows (kept for the back-substitution)
+    cplx xchg[2][2];            // [parity][{Y, V}] written by the partner CTA (st.async)
+    RowGeom bgeom[2];
+    unsigned long long full_bar;
+    unsigned long long xchg_bar[2];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ int named_bar_or(int id, int threads, bool pred) {
+    int r;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        "setp.ne.s32 p, %1, 0;\n\t"
+        "bar.red.or.pred q, %2, %3, p;\n\t"
+        "selp.s32 %0, 1, 0, q;\n\t"
+        "}"
+        : "=r"(r)
+        : "r"((int)pred), "r"(id), "r"(threads)
+        : "memory");
+    return r;
+}
+__device__ __forceinline__ void tma_store_3d_from(const CUtensorMap *map, int c0, int c1, int c2, uint32_t smem_addr) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(smem_addr)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+
+__device__ __forceinline__ void park100(uint32_t ta, const uint32_t *v) {
+    tmem_st32(ta, v), tmem_st32(ta + 32, v + 32), tmem_st32(ta + 64, v + 64), tmem_st4(ta + 96, v + 96);
+}
+__device__ __forceinline__ void unpark100(uint32_t ta, uint32_t *v) {
+    tmem_ld32(ta, v), tmem_ld32(ta + 32, v + 32), tmem_ld32(ta + 64, v + 64), tmem_ld4(ta + 96, v + 96);
+}
+__device__ __forceinline__ void put2(uint32_t *v, int i, cplx z) {
+    v[4 * i] = (uint32_t)__double2loint(z.re), v[4 * i + 1] = (uint32_t)__double2hiint(z.re);
+    v[4 * i + 2] = (uint32_t)__double2loint(z.im), v[4 * i + 3] = (uint32_t)__double2hiint(z.im);
+}
+__device__ __forceinline__ cplx get2(const uint32_t *v, int i) {
+    return mk(__hiloint2double((int)v[4 * i + 1], (int)v[4 * i]), __hiloint2double((int)v[4 * i + 3], (int)v[4 * i + 2]));
+}
+
+template <class Source>
+constexpr int pipe_threads() {
+    return kEBThreads + kIThreads + (Source::kStoreBands ? kSThreads : 0);
+}
+
+#ifdef FH_TRACE
+// role traces: E/B warp leaders stamp slots 0..15 (elimination 0..5, back-substitution 6..11), the first I warp 16..27
+#define FH_TRP(w, k)                                                                                          \
+    do {                                                                                                      \
+        if (g_trace != nullptr && it == (uint32_t)g_trace_iter && blockIdx.x < 2 && (t & 31) == 0) {          \
+            unsigned long long gt__;                                                                          \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt__));                                          \
+            g_trace[((blockIdx.x * 16 + (w)) * 16 + (k)) * 2] = clock64();                                    \
+            g_trace[((blockIdx.x * 16 + (w)) * 16 + (k)) * 2 + 1] = (long long)gt__;                          \
+        }                                                                                                     \
+    } while (0)
+#else
+#define FH_TRP(w, k) do { } while (0)
+#endif
+
+template <int CLUSTER, class Source>
+__global__ void __launch_bounds__(pipe_threads<Source>(), 1)
+tridiag_pipe_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ StoreMaps umaps, Source src,
+                    cplx *__restrict__ u, int64_t n, int64_t batch, int levels, int32_t *__restrict__ status) {
+    extern __shared__ unsigned char smem_raw[];
+    PipeSmem &sm = *reinterpret_cast<PipeSmem *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+
+    const int t = threadIdx.x, warp = t >> 5;
+    int rank = 0;
+    int64_t first_sys = blockIdx.x, sys_stride = gridDim.x;
+    if (CLUSTER > 1) {
+        rank = (int)cg::this_cluster().block_rank();
+        first_sys = blockIdx.x / CLUSTER;
+        sys_stride = gridDim.x / CLUSTER;
+    }
+    const LocalMap map = make_map<CLUSTER>(n, rank);
+    const bool has_cut = CLUSTER > 1 && (n & 1);
+    const int64_t cut_row = n / 2;
+
+    for (int i = t; i < 2 * kPcrEntries; i += (int)blockDim.x) {  // zero rows beyond either end of the PCR arrays
+        const int c = i % kPcrEntries;
+        if (c < kHalfPad || (c - kHalfPad) % kPcrArr >= kH) (&sm.half[0][0])[i] = czero();
+    }
+    if (t < 4) sm.full[t][kT] = czero();
+    if (t < 2) sm.xi[t][0] = czero();
+    if (t == 0) {
+        mbar_init(&sm.full_bar, 1);
+        mbar_init(&sm.xchg_bar[0], 1);
+        mbar_init(&sm.xchg_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(&sm.tmem_base, 512);  // one CTA per SM: all of tensor memory
+    if constexpr (Source::kUniform) {
+        if (t < 2) sm.bgeom[t] = row_geom(src.p, t == 0 ? 0 : src.p.n_elem);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if (CLUSTER > 1) cg::this_cluster().sync();  // partner's barriers exist before anything is sent
+    else __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    auto matrix_of = [&](int64_t sys) -> int64_t {
+        if constexpr (Source::kSubset) return src.list[sys];
+        else return sys;
+    };
+    if constexpr (Source::kSubset) batch = *src.count < batch ? *src.count : batch;
+
+    if (t < kEBThreads) {
+        // =============================================================================================== E/B
+        if constexpr (Source::kStoreBands) reg_inc<kRegsEB1>();
+        else reg_inc<kRegsEB>();
+        const bool active = t >= map.first_active;
+        const CUtensorMap *tmaps = maps.band[rank];
+        const CUtensorMap *map_lo = map.dir > 0 ? &tmaps[0] : &tmaps[2];
+        const CUtensorMap *map_hi = map.dir > 0 ? &tmaps[2] : &tmaps[0];
+        const int feeder = map.first_active % kT;
+        // this warp's lane quadrant of tensor memory; warps w and w + 4 share a quadrant and split its columns
+        const uint32_t tpark = sm.tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(warp >> 2) * 256u;
+
+        HelmState hs;
+        if constexpr (!Source::kStaged) {
+            if (src.p.h_mode == FH_H_SCALAR) hs.g_mid = row_geom(src.p, src.p.n_elem > 1 ? 1 : 0);
+        }
+        auto prefetch = [&](int64_t sys) {
+            if constexpr (Source::kStaged) {
+                if (t == feeder) {
+                    const int64_t sysm = matrix_of(sys);
+                    mbar_expect_tx(&sm.full_bar, 4 * kTileBytes);
+                    tma_load_3d(sm.stage[0], map_lo, 0, map.box_c1, (int)sysm, &sm.full_bar);
+                    tma_load_3d(sm.stage[1], &tmaps[1], 0, map.box_c1, (int)sysm, &sm.full_bar);
+                    tma_load_3d(sm.stage[2], map_hi, 0, map.box_c1, (int)sysm, &sm.full_bar);
+                    tma_load_3d(sm.stage[3], &tmaps[3], 0, map.box_c1, (int)sys, &sm.full_bar);
+                    const cplx *lo = map.dir > 0 ? src.dl : src.du, *hi = map.dir > 0 ? src.du : src.dl;
+                    for (int j = 0; j < map.head; ++j) {
+                        const int64_t g = sysm * n + map.global_row(j);
+                        cp_async16(&sm.headst[0][j], lo + g);
+                        cp_async16(&sm.headst[1][j], src.d + g);
+                        cp_async16(&sm.headst[2][j], hi + g);
+                        cp_async16(&sm.headst[3][j], src.b + sys * n + map.global_row(j));
+                    }
+                    cp_async_commit();
+                }
+            }
+        };
+        if (first_sys < batch) prefetch(first_sys);
+
+        uint32_t it = 0;
+        int64_t prev = -1;
+        for (int64_t sys = first_sys;; sys += sys_stride, ++it) {
+            const bool have = sys < batch;
+            if (have) {
+                // ------------------------------------------------------------------------ E: elimination of `sys`
+                const uint32_t parity = it & 1;
+                if constexpr (!Source::kStaged) {
+                    hs.k = __ldg(src.ks + sys), hs.k2 = __ldg(src.k2s + sys);
+                    if (src.p.h_mode == FH_H_SCALAR && src.p.n_elem >= 2)
+                        row_values(src.p, hs.g_mid, 1, hs.k, hs.k2, hs.il, hs.id, hs.iu, hs.ib);
+                }
+                FH_TRP(warp, 0);
+                cplx a[kM], b[kM], c[kM], d[kM];
+                uint32_t tile_addr = 0, tile_x = 0;
+                if constexpr (Source::kStaged) {
+                    mbar_wait(&sm.full_bar, parity);
+                    if (map.head > 0 && t == feeder) cp_async_wait_all();
+                    const int tt = map.dir > 0 ? t : kT - 1 - t;
+                    const int r = tt / kPer8;
+                    tile_addr = smem_u32(&sm.stage[0][0]) + (uint32_t)r * 128u;
+                    tile_x = (uint32_t)(r & 7);
+                }
+                FH_TRP(warp, 1);
+                cplx ia, ic, fa, fb, fc, fd, la, lb, lc, ld;
+                if constexpr (Source::kUniform) {
+                    ia = map.dir > 0 ? hs.il : hs.iu, ic = map.dir > 0 ? hs.iu : hs.il;
+                    cplx lo, hi;
+                    const int64_t g = map.global_row(0);
+                    row_values(src.p, sm.bgeom[g == 0 ? 0 : 1], g, hs.k, hs.k2, lo, fb, hi, fd);
+                    fa = map.dir > 0 ? lo : hi, fc = map.dir > 0 ? hi : lo;
+                    if (CLUSTER == 1) row_values(src.p, sm.bgeom[1], n - 1, hs.k, hs.k2, la, lb, lc, ld);
+                }
+                auto load_row = [&](int i) {
+                    if (!active) {
+                        a[i] = czero(), b[i] = cone(), c[i] = czero(), d[i] = czero();
+                    } else if constexpr (Source::kStaged) {
+                        const int tt = map.dir > 0 ? t : kT - 1 - t;
+                        const uint32_t e = (uint32_t)((map.dir > 0 ? i : kM - 1 - i) + kM * (tt % kPer8));
+                        const uint32_t ad = tile_addr + ((e ^ tile_x) << 4);
+                        a[i] = lds_volatile(ad), b[i] = lds_volatile(ad + kTileBytes);
+                        c[i] = lds_volatile(ad + 2 * kTileBytes), d[i] = lds_volatile(ad + 3 * kTileBytes);
+                    } else if constexpr (Source::kUniform) {
+                        a[i] = ia, b[i] = hs.id, c[i] = ic, d[i] = hs.ib;
+                        if (i == 0 && map.head == 0 && t == map.first_active) a[i] = fa, b[i] = fb, c[i] = fc, d[i] = fd;
+                        if (i == kM - 1 && CLUSTER == 1 && t == kT - 1) a[i] = la, b[i] = lb, c[i] = lc, d[i] = ld;
+                    } else {
+                        helm_row(src, hs, map, map.head + (t - map.first_active) * kM + i, a[i], b[i], c[i], d[i]);
+                    }
+                    if (i == 0 && map.head == 0 && t == map.first_active) a[0] = czero();
+                    if (i == kM - 1 && CLUSTER == 1 && t == kT - 1) c[kM - 1] = czero();
+                };
+                load_row(0);
+                load_row(1);
+                // head rows (far end, at most 8): serial Thomas by one thread, folded into its row 0; the factors wait
+                // in shared memory for the back-substitution
+                if (map.head > 0 && t == feeder) {
+                    cplx cp = czero(), dp = czero();
+#pragma unroll 1
+                    for (int j = 0; j < map.head; ++j) {
+                        cplx ha, hb, hc, hd;
+                        if constexpr (Source::kStaged) {
+                            ha = sm.headst[0][j], hb = sm.headst[1][j], hc = sm.headst[2][j], hd = sm.headst[3][j];
+                        } else {
+                            helm_row(src, hs, map, j, ha, hb, hc, hd);
+                        }
+                        if (j == 0) ha = czero();
+                        if (CLUSTER == 1 && j == map.n_loc - 1) hc = czero();
+                        const cplx inv = frecip(nmsub(hb, ha, cp));
+                        dp = nmsub(hd, ha, dp) * inv;
+                        cp = hc * inv;
+                        sm.headf[parity][0][j] = cp, sm.headf[parity][1][j] = dp;
+                    }
+                    if (map.chunks > 0) {
+                        b[0] = nmsub(b[0], a[0], cp);
+                        d[0] = nmsub(d[0], a[0], dp);
+                        a[0] = czero();
+                    }
+                }
+                cplx a7o, b7o, c7o, d7o;  // the original interface row, for the probe
+                b[0] = frecip(b[0]);
+#pragma unroll
+                for (int i = 1; i < kM; ++i) {
+                    if (i + 1 < kM) load_row(i + 1);
+                    if (i == kM - 1) a7o = a[i], b7o = b[i], c7o = c[i], d7o = d[i];
+                    const cplx w = a[i] * b[i - 1];
+                    b[i] = nmsub(b[i], w, c[i - 1]);
+                    d[i] = nmsub(d[i], w, d[i - 1]);
+                    a[i] = -(w * a[i - 1]);
+                    if (i < kM - 1) b[i] = frecip(b[i]);
+                }
+                FH_TRP(warp, 2);
+                if constexpr (Source::kStaged) {
+                    named_bar_sync(kBarEB, kEBThreads);  // every thread has drained the staging tiles ...
+                    if (sys + sys_stride < batch) prefetch(sys + sys_stride);  // ... refill them
+                }
+                FH_TRP(warp, 3);
+#pragma unroll
+                for (int i = kM - 3; i >= 0; --i) {
+                    const cplx w = c[i] * b[i + 1];
+                    a[i] = nmsub(a[i], w, a[i + 1]);
+                    d[i] = nmsub(d[i], w, d[i + 1]);
+                    c[i] = -(w * c[i + 1]);
+                }
+                // rows 0..6 in the form the back-substitution wants: x_i = d'_i - a'_i x_left - c'_i x_7
+                uint32_t pk[kParkCols];
+#pragma unroll
+                for (int i = 0; i < kM - 1; ++i) {
+                    a[i] = a[i] * b[i], c[i] = c[i] * b[i], d[i] = d[i] * b[i];
+                    put2(pk, 3 * i, a[i]), put2(pk, 3 * i + 1, c[i]), put2(pk, 3 * i + 2, d[i]);
+                }
+                put2(pk, 21, a7o), put2(pk, 22, b7o), put2(pk, 23, c7o), put2(pk, 24, d7o);
+                sm.row0[0][t] = a[0];
+                sm.row0[1][t] = c[0];
+                sm.row0[2][t] = d[0];
+                tmem_wait_st();  // (the previous system's park has long completed: orders it before its un-park below)
+                park100(tpark + parity * kParkStride, pk);
+                if (t == kStoreThread) tma_store_wait_read();  // the previous TMA store has finished reading xs
+                FH_TRP(warp, 4);
+                // all E/B threads + the I group's "full consumed": row0 is visible, xs and full are free
+                named_bar_sync(kBarFullFree, kEBThreads + kIThreads);
+                FH_TRP(warp, 5);
+                {
+                    cplx rb = b[kM - 1];
+                    cplx rA = a[kM - 1], rC = czero(), rD = d[kM - 1], rV = czero();
+                    if (t < kT - 1) {
+                        const cplx nA = sm.row0[0][t + 1], nC = sm.row0[1][t + 1], nD = sm.row0[2][t + 1];
+                        rb = nmsub(rb, c[kM - 1], nA);
+                        rC = -(c[kM - 1] * nC);
+                        rD = nmsub(rD, c[kM - 1], nD);
+                    } else if (CLUSTER > 1) {
+                        rV = c[kM - 1];  // coupling to the partner CTA's interface unknown / the cut unknown
+                    }
+                    const cplx inv = frecip(rb);
+                    sm.full[0][t] = rA * inv, sm.full[1][t] = rC * inv, sm.full[2][t] = rD * inv;
+                    if (CLUSTER > 1) sm.full[3][t] = rV * inv;
+                }
+                named_bar_arrive(kBarFullReady, kEBThreads + kIThreads);
+                FH_TRP(warp, 6);
+            }
+            if (prev >= 0) {
+                // ------------------------------------------------------------------------ B: back-substitution of `prev`
+                const uint32_t pp = (it - 1) & 1;
+                uint32_t pk[kParkCols];
+                if (!have) {  // last system: no elimination ran in this iteration (its waits are made up for here)
+                    tmem_wait_st();
+                    if (t == kStoreThread) tma_store_wait_read();
+                    named_bar_sync(kBarEB, kEBThreads);
+                }
+                unpark100(tpark + pp * kParkStride, pk);
+                named_bar_sync(pp ? kBarX1 : kBarX0, kEBThreads + kIThreads);  // the I group has solved the interface
+                FH_TRP(warp, 7);
+                const cplx X = sm.xi[pp][1 + t], xl = sm.xi[pp][t], x_partner = sm.xi[pp][kT + 1];
+                tmem_wait_ld();
+                bool bad = !cfinite(X) || !cfinite(x_partner);
+                cplx xr[kM];
+#pragma unroll
+                for (int i = 0; i < kM - 1; ++i)
+                    xr[i] = nmsub(nmsub(get2(pk, 3 * i + 2), get2(pk, 3 * i), xl), get2(pk, 3 * i + 1), X);
+                xr[kM - 1] = X;
+                const cplx x0 = xr[0], x6 = xr[kM - 2];
+                if (active) {
+                    const int tt = map.dir > 0 ? t - map.first_active : kT - 1 - t;
+                    const int r = tt / kPer8;
+                    const uint32_t base = smem_u32(&sm.xs[0]) + (uint32_t)r * 128u, x = (uint32_t)(r & 7);
+#pragma unroll
+                    for (int i = 0; i < kM; ++i) {
+                        const uint32_t e = (uint32_t)((map.dir > 0 ? i : kM - 1 - i) + kM * (tt % kPer8));
+                        sts_volatile(base + ((e ^ x) << 4), xr[i]);
+                    }
+                }
+                if (map.head > 0 && t == feeder) {
+                    cplx xn = x0;
+                    cplx *out = u + prev * n;
+#pragma unroll 1
+                    for (int j = map.head - 1; j >= 0; --j) {
+                        const cplx hcp = sm.headf[pp][0][j], hdp = sm.headf[pp][1][j];
+                        xn = (map.chunks == 0 && j == map.head - 1) ? hdp : nmsub(hdp, hcp, xn);
+                        bad |= !cfinite(xn);
+                        stg_stream(out + map.global_row(j), xn);
+                    }
+                }
+                fence_proxy_async();  // make this thread's xs writes visible to the TMA engine
+                const int any_nonfinite = named_bar_or(kBarEB, kEBThreads, bad);
+                FH_TRP(warp, 8);
+                if (t == kStoreThread) {
+                    if (map.chunks > 0) {
+                        tma_store_3d(&umaps.r[rank], 0, 0, (int)prev, sm.xs);
+                        tma_store_commit();
+                    }
+                    if (status != nullptr && any_nonfinite) atomicOr(&status[prev], 1);
+                }
+                {   // probe: defect of the original interface row with the computed solution
+                    const cplx a7o = get2(pk, 21), b7o = get2(pk, 22), c7o = get2(pk, 23), d7o = get2(pk, 24);
+                    cplx xn = x_partner;
+                    if (active && t < kT - 1) xn = sm.xs[map.xs_slot(t + 1, 0)];
+                    const cplx r = nmsub(nmsub(nmsub(d7o, a7o, x6), b7o, X), c7o, xn);
+                    const double scale = abs1(a7o) * abs1(x6) + abs1(b7o) * abs1(X) + abs1(c7o) * abs1(xn) + abs1(d7o);
+                    const bool off = active && abs1(r) > kProbeTol * scale;
+                    const bool severe = active && abs1(r) > kSevereTol * scale;
+                    const bool any_off = __any_sync(0xffffffffu, off), any_severe = __any_sync(0xffffffffu, severe);
+                    if (any_off && (t & 31) == 0 && status != nullptr) atomicOr(&status[prev], any_severe ? 3 : 2);
+                }
+                FH_TRP(warp, 9);
+            }
+            if (!have) break;
+            prev = sys;
+        }
+        if (t == kStoreThread) tma_store_wait_read();
+    } else if (t < kEBThreads + kIThreads) {
+        // =============================================================================================== I
+        if constexpr (Source::kStoreBands) reg_dec<kRegsI1>();
+        else reg_dec<kRegsI>();
+        const int j = t - kEBThreads;  // row among the kH odd interface rows: interface row r = 2 j + 1
+        const int r = 2 * j + 1;
+        constexpr uint32_t kArr = kPcrArr * sizeof(cplx);
+        const uint32_t hb0 = smem_u32(&sm.half[0][kHalfPad + j]), hb1 = smem_u32(&sm.half[1][kHalfPad + j]);
+        HelmState hs;
+        if constexpr (!Source::kStaged) {
+            if (src.p.h_mode == FH_H_SCALAR) hs.g_mid = row_geom(src.p, src.p.n_elem > 1 ? 1 : 0);
+        }
+        named_bar_arrive(kBarFullFree, kEBThreads + kIThreads);  // nothing to protect before the first system
+        uint32_t it = 0;
+        for (int64_t sys = first_sys; sys < batch; sys += sys_stride, ++it) {
+            const uint32_t parity = it & 1;
+            if (CLUSTER > 1 && j == 0) mbar_expect_tx(&sm.xchg_bar[parity], 2 * sizeof(cplx));
+            // the cut row (lo x(rank 0 side) + diag x_cut + hi x(rank 1 side) = rhs): requested before the wait
+            cplx cl = czero(), cb = cone(), ch = czero(), cd = czero();
+            if (has_cut) {
+                if constexpr (Source::kStaged) {
+                    const int64_t g = matrix_of(sys) * n + cut_row;
+                    cl = ldg_stream(src.dl + g), cb = ldg_stream(src.d + g), ch = ldg_stream(src.du + g);
+                    cd = ldg_stream(src.b + sys * n + cut_row);
+                } else {
+                    hs.k = __ldg(src.ks + sys), hs.k2 = __ldg(src.k2s + sys);
+                    if (src.p.h_mode == FH_H_SCALAR && src.p.n_elem >= 2)
+                        row_values(src.p, hs.g_mid, 1, hs.k, hs.k2, hs.il, hs.id, hs.iu, hs.ib);
+                    const Row4 cr = helm_any_row(src, hs, cut_row);
+                    cl = cr.lo, cb = cr.b, ch = cr.hi, cd = cr.d;
+                }
+            }
+            FH_TRP(8 + (j >> 5), 0);
+            named_bar_sync(kBarFullReady, kEBThreads + kIThreads);
+            FH_TRP(8 + (j >> 5), 1);
+            // cyclic-reduction step: the odd row r absorbs its even neighbours r - 1 and r + 1 (row kT is a zero row);
+            // the even row below stays in registers and is solved from its own equation at the end
+            cplx A, C, D, V = czero();
+            const cplx eA = sm.full[0][r - 1], eC = sm.full[1][r - 1], eD = sm.full[2][r - 1];
+            {
+                const cplx oA = sm.full[0][r], oC = sm.full[1][r], oD = sm.full[2][r];
+                const cplx pA = sm.full[0][r + 1], pC = sm.full[1][r + 1], pD = sm.full[2][r + 1];
+                const PcrPivot pv = pcr_pivot(oA, eC, oC, pA);
+                A = -pcr_scale(oA * eA, pv);
+                C = -pcr_scale(oC * pC, pv);
+                D = pcr_scale(nmsub(nmsub(oD, oA, eD), oC, pD), pv);
+                if (CLUSTER > 1) V = pcr_scale(sm.full[3][r], pv);  // (the even rows have no V)
+            }
+            sts_volatile(hb0, A), sts_volatile(hb0 + kArr, C), sts_volatile(hb0 + 2 * kArr, D);
+            if (CLUSTER > 1) sts_volatile(hb0 + 3 * kArr, V);
+            if (sys + sys_stride < batch) named_bar_arrive(kBarFullFree, kEBThreads + kIThreads);  // `full` consumed
+            named_bar_sync(kBarI, kIThreads);
+            FH_TRP(8 + (j >> 5), 2);
+            int cur = 0;
+#pragma unroll 1
+            for (int lv = 0, sb = (int)sizeof(cplx); lv < levels; ++lv, sb <<= 1) {  // rows beyond either end: zero rows
+                const uint32_t rd = cur ? hb1 : hb0, wr = cur ? hb0 : hb1;
+                const cplx Cm = lds_volatile(rd + kArr - sb), Ap = lds_volatile(rd + sb);
+                const cplx Am = lds_volatile(rd - sb), Cp = lds_volatile(rd + kArr + sb);
+                const cplx Dm = lds_volatile(rd + 2 * kArr - sb), Dp = lds_volatile(rd + 2 * kArr + sb);
+                const PcrPivot pv = pcr_pivot(A, Cm, C, Ap);
+                const cplx nD = pcr_scale(nmsub(nmsub(D, A, Dm), C, Dp), pv);
+                if (CLUSTER > 1) {
+                    const cplx Vm = lds_volatile(rd + 3 * kArr - sb), Vp = lds_volatile(rd + 3 * kArr + sb);
+                    V = pcr_scale(nmsub(nmsub(V, A, Vm), C, Vp), pv);
+                    sts_volatile(wr + 3 * kArr, V);
+                }
+                A = -pcr_scale(A * Am, pv);
+                C = -pcr_scale(C * Cp, pv);
+                D = nD;
+                sts_volatile(wr, A), sts_volatile(wr + kArr, C), sts_volatile(wr + 2 * kArr, D);
+                cur ^= 1;
+                named_bar_sync(kBarI, kIThreads);
+            }
+            FH_TRP(8 + (j >> 5), 3);
+            // now x(row 2j+1) = D - V * x_partner
+            cplx x_partner = czero();
+            if (CLUSTER > 1) {
+                if (j == kH - 1) {
+                    const uint32_t rbar = map_to_rank(&sm.xchg_bar[parity], rank ^ 1);
+                    st_async_remote(map_to_rank(&sm.xchg[parity][0], rank ^ 1), D, rbar);
+                    st_async_remote(map_to_rank(&sm.xchg[parity][1], rank ^ 1), V, rbar);
+                }
+                const cplx Ym = sm.half[cur][kHalfPad + 2 * kPcrArr + kH - 1], Vm = sm.half[cur][kHalfPad + 3 * kPcrArr + kH - 1];
+                mbar_wait(&sm.xchg_bar[parity], (it >> 1) & 1);
+                const cplx Yp = sm.xchg[parity][0], Vp = sm.xchg[parity][1];
+                if (has_cut) {
+                    // x_0 = Y0 - V0 x_cut, x_1 = Y1 - V1 x_cut (subscript = cluster rank); same operand order on both
+                    // CTAs, so both obtain the same bits
+                    const cplx Y0 = rank == 0 ? Ym : Yp, V0 = rank == 0 ? Vm : Vp;
+                    const cplx Y1 = rank == 0 ? Yp : Ym, V1 = rank == 0 ? Vp : Vm;
+                    const cplx den = nmsub(nmsub(cb, cl, V0), ch, V1);
+                    x_partner = nmsub(nmsub(cd, cl, Y0), ch, Y1) * frecip(den);
+                    if (rank == 0 && j == kH - 1) stg_stream(u + sys * n + cut_row, x_partner);
+                } else {
+                    const cplx x_me = nmsub(Ym, Vm, Yp) * frecip(nmsub(cone(), Vm, Vp));
+                    x_partner = nmsub(Yp, Vp, x_me);
+                }
+            }
+            FH_TRP(8 + (j >> 5), 4);
+            const cplx xo = nmsub(D, V, x_partner);
+            sm.xi[parity][1 + r] = xo;
+            if (j == 0) sm.xi[parity][kT + 1] = x_partner;
+            named_bar_sync(kBarI, kIThreads);
+            const cplx xlo = sm.xi[parity][r - 1];  // interface unknown of row r - 2 (entry 0 is a zero)
+            sm.xi[parity][r] = nmsub(nmsub(eD, eA, xlo), eC, xo);
+            named_bar_arrive(parity ? kBarX1 : kBarX0, kEBThreads + kIThreads);
+            FH_TRP(8 + (j >> 5), 5);
+        }
+    } else {
+        // =============================================================================================== S
+        if constexpr (Source::kStoreBands) {
+            reg_dec<kRegsS1>();
+            // A is kept: on a uniform mesh every interior row of a system holds the same four numbers.  Four 16 KB
+            // tiles (128 chunks of 8 identical rows: dl, d, du, b) are filled once per system and sent to every block of
+            // 128 interior chunks by TMA stores; the rows that differ or fall outside the chunk grid (the chunks holding
+            // mesh row 0 / n - 1, head rows, the cut row) are written by single lanes.  Two sets of tiles: the fill of
+            // system s + 1 does not wait for the engine to have read the tiles of system s.  Values =
+            // fh_assemble_1d_c128's, bit for bit (same generator).
+            const int ts = t - (kEBThreads + kIThreads), ws = ts >> 5, lane = ts & 31;
+            const HostMap hm = host_map(n, CLUSTER);
+            const RowGeom g_mid = row_geom(src.p, 1);
+            const int count = map.chunks - hm.front[rank] - hm.back[rank];
+            uint32_t it = 0;
+            for (int64_t sys = first_sys; sys < batch; sys += sys_stride, ++it) {
+                const uint32_t buf = it & 1;
+                const double k = __ldg(src.ks + sys), k2 = __ldg(src.k2s + sys);
+                cplx il, id, iu, ib;
+                row_values(src.p, g_mid, 1, k, k2, il, id, iu, ib);
+                if (it >= 2 && lane == 0) tma_store_wait_read1();  // the tiles sent two systems ago have been read
+                named_bar_sync(kBarS, kSThreads);
+                const uint32_t tile0 = smem_u32(&sm.stage[0][0]) + buf * 4u * kBandTileBytes;
+                const uint32_t mine = tile0 + (uint32_t)ts * 16u;
+#pragma unroll
+                for (uint32_t rep = 0; rep < kBandTileBytes; rep += kSThreads * 16u) {
+                    sts_volatile(mine + rep, il), sts_volatile(mine + kBandTileBytes + rep, id);
+                    sts_volatile(mine + 2 * kBandTileBytes + rep, iu), sts_volatile(mine + 3 * kBandTileBytes + rep, ib);
+                }
+                fence_proxy_async();
+                named_bar_sync(kBarS, kSThreads);
+                if (lane == 0) {  // one band per warp
+                    for (int c = 0; c < count; c += kBandTileChunks)
+                        tma_store_3d_from(&maps.band[rank][ws], 0, c, (int)sys, tile0 + (uint32_t)ws * kBandTileBytes);
+                    tma_store_commit();
+                }
+                if (ws == 1) {
+                    cplx r0l, r0d, r0u, r0b, rNl, rNd, rNu, rNb;
+                    row_values(src.p, sm.bgeom[0], 0, k, k2, r0l, r0d, r0u, r0b);
+                    row_values(src.p, sm.bgeom[1], n - 1, k, k2, rNl, rNd, rNu, rNb);
+                    int64_t g = -1;  // the special row of this lane, if any
+                    const int64_t grid0 = hm.row0[rank];
+                    if (lane < map.head) g = map.global_row(lane);                                       // lanes 0..7: head rows
+                    if (lane == 8 && has_cut && rank == 0) g = cut_row;                                  // lane 8: the cut row
+                    if (lane >= 16 && lane < 24 && hm.front[rank]) g = grid0 + (lane - 16);              // first chunk
+                    if (lane >= 24 && hm.back[rank]) g = grid0 + 8 * (int64_t)(map.chunks - 1) + (lane - 24);  // last chunk
+                    if (g >= 0) {
+                        cplx vl = il, vd = id, vu = iu, vb = ib;
+                        if (g == 0) vl = r0l, vd = r0d, vu = r0u, vb = r0b;
+                        if (g == n - 1) vl = rNl, vd = rNd, vu = rNu, vb = rNb;
+                        const int64_t o = sys * n + g;
+                        stg_stream(src.out_dl + o, vl), stg_stream(src.out_d + o, vd);
+                        stg_stream(src.out_du + o, vu), stg_stream(src.out_b + o, vb);
+                    }
+                }
+            }
+            if (lane == 0) tma_store_wait_read();
+        }
+    }
+    if (CLUSTER > 1) cg::this_cluster().sync();  // no CTA leaves while its partner may still address it
+    else __syncthreads();
+    if (warp == 0) tmem_dealloc(sm.tmem_base, 512);
+}
+
+}  // namespace fh
+static_assert(sizeof(fh::PipeSmem) + 1024 <= 232448, "PipeSmem exceeds the 227 KB a CTA can have on sm_100");
