@@ -718,9 +718,16 @@ static int launch_batched(const Source &src, const cplx *const bands[4], cplx *u
     // batch = number of right-hand sides / solutions (an upper bound when src.count is set); batch_matrices = number
     // of systems in the dl / d / du arrays when it differs (subset refinement)
     if (batch_matrices < 0) batch_matrices = batch;
-    // development switch: FH_BATCHED=serial launches the one-role-per-CTA kernel the pipeline replaced
-    static const bool serial = [] { const char *e = getenv("FH_BATCHED"); return e != nullptr && e[0] == 's'; }();
-    auto kernel = serial ? tridiag_batched_kernel<CLUSTER, Source> : tridiag_pipe_kernel<CLUSTER, Source>;
+    // The pipeline of warp roles (fh_tridiag_pipe.cuh) serves stored bands and rows generated on a uniform mesh; rows
+    // generated on a non-uniform mesh (per-row geometry with IEEE divisions, far more registers) stay with the
+    // one-role-per-CTA kernel.  Development switch: FH_BATCHED=serial launches that kernel for every source.
+    constexpr bool kPipe = Source::kStaged || Source::kUniform;
+    static const bool serial = [] { const char *e = getenv("FH_BATCHED"); return !kPipe || (e != nullptr && e[0] == 's'); }();
+    auto pipe_or_serial = [] {
+        if constexpr (kPipe) return tridiag_pipe_kernel<CLUSTER, Source>;
+        else return tridiag_batched_kernel<CLUSTER, Source>;
+    };
+    auto kernel = serial ? tridiag_batched_kernel<CLUSTER, Source> : pipe_or_serial();
     const size_t smem = (serial ? sizeof(BatchedSmem) : sizeof(PipeSmem)) + 1024;  // slack for the 1024-byte round-up
     if (smem > smem_optin_bytes()) {
         set_error("kernel needs %zu B of shared memory, device offers %zu", smem, smem_optin_bytes());

@@ -24,6 +24,8 @@
 //   X0 / X1   I -> B   interface unknowns of an even / odd system are in `xi`
 #pragma once
 
+#include <type_traits>
+
 #include "fh_tmem.cuh"
 
 namespace fh {
@@ -38,7 +40,7 @@ static_assert(kParkCols == 100 && kParkCols <= (int)kParkStride, "parking layout
 
 enum : int { kBarEB = 1, kBarI = 2, kBarFullReady = 3, kBarFullFree = 4, kBarX0 = 5, kBarX1 = 6, kBarS = 7 };
 constexpr int kRegsEB = 200, kRegsI = 96;                      // 256 * 200 + 128 * 96 <= 384 * 168
-constexpr int kRegsEB1 = 192, kRegsI1 = 88, kRegsS1 = 40;      // 256 * 192 + 128 * 88 + 128 * 40 = 512 * 128
+constexpr int kRegsEB1 = 184, kRegsI1 = 88, kRegsS1 = 56;      // 256 * 184 + 128 * 88 + 128 * 56 = 512 * 128
 
 // PCR arrays of the I group: kH rows each, kHalfPad zero rows before and after (the largest PCR stride); the pad behind
 // one array is the pad in front of the next
@@ -55,10 +57,11 @@ struct __align__(1024) PipeSmem {
     cplx headst[4][kHeadMax];   // head rows of the next system (cp.async by one thread)
     cplx headf[2][2][kHeadMax]; // [parity]: elimination factors of the head rows (kept for the back-substitution)
     cplx xchg[2][2];            // [parity][{Y, V}] written by the partner CTA (st.async)
-    RowGeom bgeom[2];
+    RowGeom bgeom[3];           // generated rows, uniform mesh: geometry of mesh row 0, row N and the interior rows
     unsigned long long full_bar;
     unsigned long long xchg_bar[2];
     uint32_t tmem_base;
+    uint32_t i_done;            // systems the I group has finished (paces the S group)
 };
 
 __device__ __forceinline__ int named_bar_or(int id, int threads, bool pred) {
@@ -120,6 +123,7 @@ template <int CLUSTER, class Source>
 __global__ void __launch_bounds__(pipe_threads<Source>(), 1)
 tridiag_pipe_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ StoreMaps umaps, Source src,
                     cplx *__restrict__ u, int64_t n, int64_t batch, int levels, int32_t *__restrict__ status) {
+    static_assert(Source::kStaged || Source::kUniform, "generated rows: the pipeline covers uniform meshes only");
     extern __shared__ unsigned char smem_raw[];
     PipeSmem &sm = *reinterpret_cast<PipeSmem *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
 
@@ -147,9 +151,10 @@ tridiag_pipe_kernel(const __grid_constant__ TensorMaps maps, const __grid_consta
         mbar_init(&sm.xchg_bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (t == 0) sm.i_done = 0;
     if (warp == 0) tmem_alloc(&sm.tmem_base, 512);  // one CTA per SM: all of tensor memory
     if constexpr (Source::kUniform) {
-        if (t < 2) sm.bgeom[t] = row_geom(src.p, t == 0 ? 0 : src.p.n_elem);
+        if (t < 3) sm.bgeom[t] = row_geom(src.p, t == 0 ? 0 : t == 1 ? src.p.n_elem : 1);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     if (CLUSTER > 1) cg::this_cluster().sync();  // partner's barriers exist before anything is sent
@@ -173,11 +178,17 @@ tridiag_pipe_kernel(const __grid_constant__ TensorMaps maps, const __grid_consta
         const int feeder = map.first_active % kT;
         // this warp's lane quadrant of tensor memory; warps w and w + 4 share a quadrant and split its columns
         const uint32_t tpark = sm.tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(warp >> 2) * 256u;
+        // Generated rows on a uniform mesh: every interior row of a system holds the same three REAL numbers and a zero
+        // right-hand side, so every chunk that holds interior rows only is eliminated to the same seven (a', c') pairs
+        // and the same interface row.  A warp whose 32 chunks are all of that kind ("plain warp") carries the sweeps out
+        // on the real parts alone -- the imaginary lanes of the complex arithmetic would only move zeros, so the real
+        // parts come out bit for bit as in the complex sweeps -- and keeps the 17 numbers its back-substitution needs
+        // in registers instead of parking 50 complex ones in tensor memory.  The warp that holds the CTA's first
+        // active chunk (mesh row 0 / N, or the head rows folded into it), warps with inactive threads and, single-CTA,
+        // the last warp (mesh row N) take the general complex path below.
+        bool plain = false;
+        if constexpr (Source::kUniform) plain = 32 * warp > map.first_active && (CLUSTER > 1 || warp != kEBThreads / 32 - 1);
 
-        HelmState hs;
-        if constexpr (!Source::kStaged) {
-            if (src.p.h_mode == FH_H_SCALAR) hs.g_mid = row_geom(src.p, src.p.n_elem > 1 ? 1 : 0);
-        }
         auto prefetch = [&](int64_t sys) {
             if constexpr (Source::kStaged) {
                 if (t == feeder) {
@@ -201,6 +212,16 @@ tridiag_pipe_kernel(const __grid_constant__ TensorMaps maps, const __grid_consta
         };
         if (first_sys < batch) prefetch(first_sys);
 
+        // the loop over the systems, compiled once for plain warps and once for the others: what a plain warp carries
+        // from a system's elimination to its back-substitution must not weigh on the register budget of the general path
+        auto eb_loop = [&](auto plain_tag) {
+        constexpr bool kPlain = decltype(plain_tag)::value;
+        constexpr int kCarry = kPlain ? kM - 1 : 1;
+        double ca[kCarry], cc[kCarry], c3[3];  // plain warps: a'_i, c'_i (i < 7) and the interior row (a, b, c) of `sys` ...
+        double pa[kCarry], pc[kCarry], p3[3];  // ... and of `prev`
+#pragma unroll
+        for (int i = 0; i < kCarry; ++i) ca[i] = cc[i] = pa[i] = pc[i] = 0.0;
+        c3[0] = c3[1] = c3[2] = p3[0] = p3[1] = p3[2] = 0.0;
         uint32_t it = 0;
         int64_t prev = -1;
         for (int64_t sys = first_sys;; sys += sys_stride, ++it) {
@@ -208,131 +229,166 @@ tridiag_pipe_kernel(const __grid_constant__ TensorMaps maps, const __grid_consta
             if (have) {
                 // ------------------------------------------------------------------------ E: elimination of `sys`
                 const uint32_t parity = it & 1;
-                if constexpr (!Source::kStaged) {
-                    hs.k = __ldg(src.ks + sys), hs.k2 = __ldg(src.k2s + sys);
-                    if (src.p.h_mode == FH_H_SCALAR && src.p.n_elem >= 2)
-                        row_values(src.p, hs.g_mid, 1, hs.k, hs.k2, hs.il, hs.id, hs.iu, hs.ib);
+                double hk = 0.0, hk2 = 0.0;
+                cplx il = czero(), id = cone(), iu = czero(), ib = czero();  // the interior row (generated, uniform mesh)
+                if constexpr (Source::kUniform) {
+                    hk = __ldg(src.ks + sys), hk2 = __ldg(src.k2s + sys);
+                    row_values(src.p, sm.bgeom[2], 1, hk, hk2, il, id, iu, ib);
                 }
                 FH_TRP(warp, 0);
-                cplx a[kM], b[kM], c[kM], d[kM];
-                uint32_t tile_addr = 0, tile_x = 0;
-                if constexpr (Source::kStaged) {
-                    mbar_wait(&sm.full_bar, parity);
-                    if (map.head > 0 && t == feeder) cp_async_wait_all();
-                    const int tt = map.dir > 0 ? t : kT - 1 - t;
-                    const int r = tt / kPer8;
-                    tile_addr = smem_u32(&sm.stage[0][0]) + (uint32_t)r * 128u;
-                    tile_x = (uint32_t)(r & 7);
-                }
-                FH_TRP(warp, 1);
-                cplx ia, ic, fa, fb, fc, fd, la, lb, lc, ld;
-                if constexpr (Source::kUniform) {
-                    ia = map.dir > 0 ? hs.il : hs.iu, ic = map.dir > 0 ? hs.iu : hs.il;
-                    cplx lo, hi;
-                    const int64_t g = map.global_row(0);
-                    row_values(src.p, sm.bgeom[g == 0 ? 0 : 1], g, hs.k, hs.k2, lo, fb, hi, fd);
-                    fa = map.dir > 0 ? lo : hi, fc = map.dir > 0 ? hi : lo;
-                    if (CLUSTER == 1) row_values(src.p, sm.bgeom[1], n - 1, hs.k, hs.k2, la, lb, lc, ld);
-                }
-                auto load_row = [&](int i) {
-                    if (!active) {
-                        a[i] = czero(), b[i] = cone(), c[i] = czero(), d[i] = czero();
-                    } else if constexpr (Source::kStaged) {
+                cplx a7, b7, c7, d7;  // the thread's interface row after the sweeps (b7 not inverted)
+                if constexpr (kPlain) {
+                    const double ra = map.dir > 0 ? il.re : iu.re, rb = id.re, rc = map.dir > 0 ? iu.re : il.re;
+                    FH_TRP(warp, 1);
+                    double A[kM], B[kM], C[kM];
+                    A[0] = ra, C[0] = rc;
+                    B[0] = rb * fast_rcp(rb * rb);  // (the real lane of frecip)
+#pragma unroll
+                    for (int i = 1; i < kM; ++i) {
+                        const double w = ra * B[i - 1];
+                        B[i] = fma(-w, rc, rb);
+                        A[i] = -(w * A[i - 1]);
+                        C[i] = rc;
+                        if (i < kM - 1) B[i] = B[i] * fast_rcp(B[i] * B[i]);
+                    }
+                    FH_TRP(warp, 2);
+                    FH_TRP(warp, 3);
+#pragma unroll
+                    for (int i = kM - 3; i >= 0; --i) {
+                        const double w = C[i] * B[i + 1];
+                        A[i] = fma(-w, A[i + 1], A[i]);
+                        C[i] = -(w * C[i + 1]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < kM - 1; ++i) ca[i] = A[i] * B[i], cc[i] = C[i] * B[i];
+                    c3[0] = ra, c3[1] = rb, c3[2] = rc;
+                    sm.row0[0][t] = mk(ca[0], 0.0);
+                    sm.row0[1][t] = mk(cc[0], 0.0);
+                    sm.row0[2][t] = czero();
+                    a7 = mk(A[kM - 1], 0.0), b7 = mk(B[kM - 1], 0.0), c7 = mk(rc, 0.0), d7 = czero();
+                } else {
+                    cplx a[kM], b[kM], c[kM], d[kM];
+                    uint32_t tile_addr = 0, tile_x = 0;
+                    if constexpr (Source::kStaged) {
+                        mbar_wait(&sm.full_bar, parity);
+                        if (map.head > 0 && t == feeder) cp_async_wait_all();
                         const int tt = map.dir > 0 ? t : kT - 1 - t;
-                        const uint32_t e = (uint32_t)((map.dir > 0 ? i : kM - 1 - i) + kM * (tt % kPer8));
-                        const uint32_t ad = tile_addr + ((e ^ tile_x) << 4);
-                        a[i] = lds_volatile(ad), b[i] = lds_volatile(ad + kTileBytes);
-                        c[i] = lds_volatile(ad + 2 * kTileBytes), d[i] = lds_volatile(ad + 3 * kTileBytes);
-                    } else if constexpr (Source::kUniform) {
-                        a[i] = ia, b[i] = hs.id, c[i] = ic, d[i] = hs.ib;
-                        if (i == 0 && map.head == 0 && t == map.first_active) a[i] = fa, b[i] = fb, c[i] = fc, d[i] = fd;
-                        if (i == kM - 1 && CLUSTER == 1 && t == kT - 1) a[i] = la, b[i] = lb, c[i] = lc, d[i] = ld;
-                    } else {
-                        helm_row(src, hs, map, map.head + (t - map.first_active) * kM + i, a[i], b[i], c[i], d[i]);
+                        const int r = tt / kPer8;
+                        tile_addr = smem_u32(&sm.stage[0][0]) + (uint32_t)r * 128u;
+                        tile_x = (uint32_t)(r & 7);
                     }
-                    if (i == 0 && map.head == 0 && t == map.first_active) a[0] = czero();
-                    if (i == kM - 1 && CLUSTER == 1 && t == kT - 1) c[kM - 1] = czero();
-                };
-                load_row(0);
-                load_row(1);
-                // head rows (far end, at most 8): serial Thomas by one thread, folded into its row 0; the factors wait
-                // in shared memory for the back-substitution
-                if (map.head > 0 && t == feeder) {
-                    cplx cp = czero(), dp = czero();
-#pragma unroll 1
-                    for (int j = 0; j < map.head; ++j) {
-                        cplx ha, hb, hc, hd;
-                        if constexpr (Source::kStaged) {
-                            ha = sm.headst[0][j], hb = sm.headst[1][j], hc = sm.headst[2][j], hd = sm.headst[3][j];
-                        } else {
-                            helm_row(src, hs, map, j, ha, hb, hc, hd);
+                    FH_TRP(warp, 1);
+                    // generated rows: mesh row g in the CTA's local orientation (only the threads that own a mesh boundary
+                    // row or head rows come here)
+                    auto gen_row = [&](int64_t g, cplx &ra, cplx &rb, cplx &rc, cplx &rd) {
+                        if constexpr (Source::kUniform) {
+                            cplx lo = il, hi = iu;
+                            rb = id, rd = ib;
+                            if (g == 0 || g == n - 1) row_values(src.p, sm.bgeom[g == 0 ? 0 : 1], g, hk, hk2, lo, rb, hi, rd);
+                            ra = map.dir > 0 ? lo : hi, rc = map.dir > 0 ? hi : lo;
                         }
-                        if (j == 0) ha = czero();
-                        if (CLUSTER == 1 && j == map.n_loc - 1) hc = czero();
-                        const cplx inv = frecip(nmsub(hb, ha, cp));
-                        dp = nmsub(hd, ha, dp) * inv;
-                        cp = hc * inv;
-                        sm.headf[parity][0][j] = cp, sm.headf[parity][1][j] = dp;
+                    };
+                    auto load_row = [&](int i) {
+                        if (!active) {
+                            a[i] = czero(), b[i] = cone(), c[i] = czero(), d[i] = czero();
+                        } else if constexpr (Source::kStaged) {
+                            const int tt = map.dir > 0 ? t : kT - 1 - t;
+                            const uint32_t e = (uint32_t)((map.dir > 0 ? i : kM - 1 - i) + kM * (tt % kPer8));
+                            const uint32_t ad = tile_addr + ((e ^ tile_x) << 4);
+                            a[i] = lds_volatile(ad), b[i] = lds_volatile(ad + kTileBytes);
+                            c[i] = lds_volatile(ad + 2 * kTileBytes), d[i] = lds_volatile(ad + 3 * kTileBytes);
+                        } else {
+                            a[i] = map.dir > 0 ? il : iu, b[i] = id, c[i] = map.dir > 0 ? iu : il, d[i] = ib;
+                            // a mesh boundary row can only sit in the first slot of the first active thread (local row 0,
+                            // when there are no head rows) or, single-CTA, in the last slot of the last thread
+                            if (i == 0 && map.head == 0 && t == map.first_active) gen_row(map.global_row(0), a[i], b[i], c[i], d[i]);
+                            if (i == kM - 1 && CLUSTER == 1 && t == kT - 1) gen_row(n - 1, a[i], b[i], c[i], d[i]);
+                        }
+                        if (i == 0 && map.head == 0 && t == map.first_active) a[0] = czero();
+                        if (i == kM - 1 && CLUSTER == 1 && t == kT - 1) c[kM - 1] = czero();
+                    };
+                    load_row(0);
+                    load_row(1);
+                    // head rows (far end, at most 8): serial Thomas by one thread, folded into its row 0; the factors wait
+                    // in shared memory for the back-substitution
+                    if (map.head > 0 && t == feeder) {
+                        cplx cp = czero(), dp = czero();
+#pragma unroll 1
+                        for (int j = 0; j < map.head; ++j) {
+                            cplx ha, hb, hc, hd;
+                            if constexpr (Source::kStaged) {
+                                ha = sm.headst[0][j], hb = sm.headst[1][j], hc = sm.headst[2][j], hd = sm.headst[3][j];
+                            } else {
+                                gen_row(map.global_row(j), ha, hb, hc, hd);
+                            }
+                            if (j == 0) ha = czero();
+                            if (CLUSTER == 1 && j == map.n_loc - 1) hc = czero();
+                            const cplx inv = frecip(nmsub(hb, ha, cp));
+                            dp = nmsub(hd, ha, dp) * inv;
+                            cp = hc * inv;
+                            sm.headf[parity][0][j] = cp, sm.headf[parity][1][j] = dp;
+                        }
+                        if (map.chunks > 0) {
+                            b[0] = nmsub(b[0], a[0], cp);
+                            d[0] = nmsub(d[0], a[0], dp);
+                            a[0] = czero();
+                        }
                     }
-                    if (map.chunks > 0) {
-                        b[0] = nmsub(b[0], a[0], cp);
-                        d[0] = nmsub(d[0], a[0], dp);
-                        a[0] = czero();
+                    cplx a7o, b7o, c7o, d7o;  // the original interface row, for the probe
+                    b[0] = frecip(b[0]);
+#pragma unroll
+                    for (int i = 1; i < kM; ++i) {
+                        if (i + 1 < kM) load_row(i + 1);
+                        if (i == kM - 1) a7o = a[i], b7o = b[i], c7o = c[i], d7o = d[i];
+                        const cplx w = a[i] * b[i - 1];
+                        b[i] = nmsub(b[i], w, c[i - 1]);
+                        d[i] = nmsub(d[i], w, d[i - 1]);
+                        a[i] = -(w * a[i - 1]);
+                        if (i < kM - 1) b[i] = frecip(b[i]);
                     }
-                }
-                cplx a7o, b7o, c7o, d7o;  // the original interface row, for the probe
-                b[0] = frecip(b[0]);
+                    FH_TRP(warp, 2);
+                    if constexpr (Source::kStaged) {
+                        named_bar_sync(kBarEB, kEBThreads);  // every thread has drained the staging tiles ...
+                        if (sys + sys_stride < batch) prefetch(sys + sys_stride);  // ... refill them
+                    }
+                    FH_TRP(warp, 3);
 #pragma unroll
-                for (int i = 1; i < kM; ++i) {
-                    if (i + 1 < kM) load_row(i + 1);
-                    if (i == kM - 1) a7o = a[i], b7o = b[i], c7o = c[i], d7o = d[i];
-                    const cplx w = a[i] * b[i - 1];
-                    b[i] = nmsub(b[i], w, c[i - 1]);
-                    d[i] = nmsub(d[i], w, d[i - 1]);
-                    a[i] = -(w * a[i - 1]);
-                    if (i < kM - 1) b[i] = frecip(b[i]);
-                }
-                FH_TRP(warp, 2);
-                if constexpr (Source::kStaged) {
-                    named_bar_sync(kBarEB, kEBThreads);  // every thread has drained the staging tiles ...
-                    if (sys + sys_stride < batch) prefetch(sys + sys_stride);  // ... refill them
-                }
-                FH_TRP(warp, 3);
+                    for (int i = kM - 3; i >= 0; --i) {
+                        const cplx w = c[i] * b[i + 1];
+                        a[i] = nmsub(a[i], w, a[i + 1]);
+                        d[i] = nmsub(d[i], w, d[i + 1]);
+                        c[i] = -(w * c[i + 1]);
+                    }
+                    // rows 0..6 in the form the back-substitution wants: x_i = d'_i - a'_i x_left - c'_i x_7
+                    uint32_t pk[kParkCols];
 #pragma unroll
-                for (int i = kM - 3; i >= 0; --i) {
-                    const cplx w = c[i] * b[i + 1];
-                    a[i] = nmsub(a[i], w, a[i + 1]);
-                    d[i] = nmsub(d[i], w, d[i + 1]);
-                    c[i] = -(w * c[i + 1]);
+                    for (int i = 0; i < kM - 1; ++i) {
+                        a[i] = a[i] * b[i], c[i] = c[i] * b[i], d[i] = d[i] * b[i];
+                        put2(pk, 3 * i, a[i]), put2(pk, 3 * i + 1, c[i]), put2(pk, 3 * i + 2, d[i]);
+                    }
+                    put2(pk, 21, a7o), put2(pk, 22, b7o), put2(pk, 23, c7o), put2(pk, 24, d7o);
+                    sm.row0[0][t] = a[0];
+                    sm.row0[1][t] = c[0];
+                    sm.row0[2][t] = d[0];
+                    tmem_wait_st();  // (the previous system's park has long completed: orders it before its un-park below)
+                    park100(tpark + parity * kParkStride, pk);
+                    a7 = a[kM - 1], b7 = b[kM - 1], c7 = c[kM - 1], d7 = d[kM - 1];
                 }
-                // rows 0..6 in the form the back-substitution wants: x_i = d'_i - a'_i x_left - c'_i x_7
-                uint32_t pk[kParkCols];
-#pragma unroll
-                for (int i = 0; i < kM - 1; ++i) {
-                    a[i] = a[i] * b[i], c[i] = c[i] * b[i], d[i] = d[i] * b[i];
-                    put2(pk, 3 * i, a[i]), put2(pk, 3 * i + 1, c[i]), put2(pk, 3 * i + 2, d[i]);
-                }
-                put2(pk, 21, a7o), put2(pk, 22, b7o), put2(pk, 23, c7o), put2(pk, 24, d7o);
-                sm.row0[0][t] = a[0];
-                sm.row0[1][t] = c[0];
-                sm.row0[2][t] = d[0];
-                tmem_wait_st();  // (the previous system's park has long completed: orders it before its un-park below)
-                park100(tpark + parity * kParkStride, pk);
                 if (t == kStoreThread) tma_store_wait_read();  // the previous TMA store has finished reading xs
                 FH_TRP(warp, 4);
                 // all E/B threads + the I group's "full consumed": row0 is visible, xs and full are free
                 named_bar_sync(kBarFullFree, kEBThreads + kIThreads);
                 FH_TRP(warp, 5);
                 {
-                    cplx rb = b[kM - 1];
-                    cplx rA = a[kM - 1], rC = czero(), rD = d[kM - 1], rV = czero();
+                    cplx rb = b7;
+                    cplx rA = a7, rC = czero(), rD = d7, rV = czero();
                     if (t < kT - 1) {
                         const cplx nA = sm.row0[0][t + 1], nC = sm.row0[1][t + 1], nD = sm.row0[2][t + 1];
-                        rb = nmsub(rb, c[kM - 1], nA);
-                        rC = -(c[kM - 1] * nC);
-                        rD = nmsub(rD, c[kM - 1], nD);
+                        rb = nmsub(rb, c7, nA);
+                        rC = -(c7 * nC);
+                        rD = nmsub(rD, c7, nD);
                     } else if (CLUSTER > 1) {
-                        rV = c[kM - 1];  // coupling to the partner CTA's interface unknown / the cut unknown
+                        rV = c7;  // coupling to the partner CTA's interface unknown / the cut unknown
                     }
                     const cplx inv = frecip(rb);
                     sm.full[0][t] = rA * inv, sm.full[1][t] = rC * inv, sm.full[2][t] = rD * inv;
@@ -348,18 +404,27 @@ tridiag_pipe_kernel(const __grid_constant__ TensorMaps maps, const __grid_consta
                 if (!have) {  // last system: no elimination ran in this iteration (its waits are made up for here)
                     tmem_wait_st();
                     if (t == kStoreThread) tma_store_wait_read();
-                    named_bar_sync(kBarEB, kEBThreads);
+                    named_bar_sync(kBarEB, kEBThreads);  // (orders the store wait before the writes to xs)
                 }
-                unpark100(tpark + pp * kParkStride, pk);
+                if constexpr (!kPlain) unpark100(tpark + pp * kParkStride, pk);
                 named_bar_sync(pp ? kBarX1 : kBarX0, kEBThreads + kIThreads);  // the I group has solved the interface
                 FH_TRP(warp, 7);
                 const cplx X = sm.xi[pp][1 + t], xl = sm.xi[pp][t], x_partner = sm.xi[pp][kT + 1];
-                tmem_wait_ld();
                 bool bad = !cfinite(X) || !cfinite(x_partner);
                 cplx xr[kM];
+                cplx a7o, b7o, c7o, d7o;
+                if constexpr (kPlain) {
 #pragma unroll
-                for (int i = 0; i < kM - 1; ++i)
-                    xr[i] = nmsub(nmsub(get2(pk, 3 * i + 2), get2(pk, 3 * i), xl), get2(pk, 3 * i + 1), X);
+                    for (int i = 0; i < kM - 1; ++i)  // (the real coefficients' share of the complex nmsub chain)
+                        xr[i] = mk(fma(-pc[i], X.re, fma(-pa[i], xl.re, 0.0)), fma(-pc[i], X.im, fma(-pa[i], xl.im, 0.0)));
+                    a7o = mk(p3[0], 0.0), b7o = mk(p3[1], 0.0), c7o = mk(p3[2], 0.0), d7o = czero();
+                } else {
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < kM - 1; ++i)
+                        xr[i] = nmsub(nmsub(get2(pk, 3 * i + 2), get2(pk, 3 * i), xl), get2(pk, 3 * i + 1), X);
+                    a7o = get2(pk, 21), b7o = get2(pk, 22), c7o = get2(pk, 23), d7o = get2(pk, 24);
+                }
                 xr[kM - 1] = X;
                 const cplx x0 = xr[0], x6 = xr[kM - 2];
                 if (active) {
@@ -394,7 +459,6 @@ tridiag_pipe_kernel(const __grid_constant__ TensorMaps maps, const __grid_consta
                     if (status != nullptr && any_nonfinite) atomicOr(&status[prev], 1);
                 }
                 {   // probe: defect of the original interface row with the computed solution
-                    const cplx a7o = get2(pk, 21), b7o = get2(pk, 22), c7o = get2(pk, 23), d7o = get2(pk, 24);
                     cplx xn = x_partner;
                     if (active && t < kT - 1) xn = sm.xs[map.xs_slot(t + 1, 0)];
                     const cplx r = nmsub(nmsub(nmsub(d7o, a7o, x6), b7o, X), c7o, xn);
@@ -408,6 +472,18 @@ tridiag_pipe_kernel(const __grid_constant__ TensorMaps maps, const __grid_consta
             }
             if (!have) break;
             prev = sys;
+            if constexpr (kPlain) {
+#pragma unroll
+                for (int i = 0; i < kM - 1; ++i) pa[i] = ca[i], pc[i] = cc[i];
+                p3[0] = c3[0], p3[1] = c3[1], p3[2] = c3[2];
+            }
+        }
+        };
+        if constexpr (Source::kUniform) {
+            if (plain) eb_loop(std::true_type{});
+            else eb_loop(std::false_type{});
+        } else {
+            eb_loop(std::false_type{});
         }
         if (t == kStoreThread) tma_store_wait_read();
     } else if (t < kEBThreads + kIThreads) {
@@ -418,10 +494,6 @@ tridiag_pipe_kernel(const __grid_constant__ TensorMaps maps, const __grid_consta
         const int r = 2 * j + 1;
         constexpr uint32_t kArr = kPcrArr * sizeof(cplx);
         const uint32_t hb0 = smem_u32(&sm.half[0][kHalfPad + j]), hb1 = smem_u32(&sm.half[1][kHalfPad + j]);
-        HelmState hs;
-        if constexpr (!Source::kStaged) {
-            if (src.p.h_mode == FH_H_SCALAR) hs.g_mid = row_geom(src.p, src.p.n_elem > 1 ? 1 : 0);
-        }
         named_bar_arrive(kBarFullFree, kEBThreads + kIThreads);  // nothing to protect before the first system
         uint32_t it = 0;
         for (int64_t sys = first_sys; sys < batch; sys += sys_stride, ++it) {
@@ -434,12 +506,8 @@ tridiag_pipe_kernel(const __grid_constant__ TensorMaps maps, const __grid_consta
                     const int64_t g = matrix_of(sys) * n + cut_row;
                     cl = ldg_stream(src.dl + g), cb = ldg_stream(src.d + g), ch = ldg_stream(src.du + g);
                     cd = ldg_stream(src.b + sys * n + cut_row);
-                } else {
-                    hs.k = __ldg(src.ks + sys), hs.k2 = __ldg(src.k2s + sys);
-                    if (src.p.h_mode == FH_H_SCALAR && src.p.n_elem >= 2)
-                        row_values(src.p, hs.g_mid, 1, hs.k, hs.k2, hs.il, hs.id, hs.iu, hs.ib);
-                    const Row4 cr = helm_any_row(src, hs, cut_row);
-                    cl = cr.lo, cb = cr.b, ch = cr.hi, cd = cr.d;
+                } else {  // uniform mesh: the cut row is an interior row (n >= 2057 here)
+                    row_values(src.p, sm.bgeom[2], 1, __ldg(src.ks + sys), __ldg(src.k2s + sys), cl, cb, ch, cd);
                 }
             }
             FH_TRP(8 + (j >> 5), 0);
@@ -517,65 +585,61 @@ tridiag_pipe_kernel(const __grid_constant__ TensorMaps maps, const __grid_consta
             const cplx xlo = sm.xi[parity][r - 1];  // interface unknown of row r - 2 (entry 0 is a zero)
             sm.xi[parity][r] = nmsub(nmsub(eD, eA, xlo), eC, xo);
             named_bar_arrive(parity ? kBarX1 : kBarX0, kEBThreads + kIThreads);
+            if constexpr (Source::kStoreBands) {
+                if (j == 0) *(volatile uint32_t *)&sm.i_done = it + 1;
+            }
             FH_TRP(8 + (j >> 5), 5);
         }
     } else {
         // =============================================================================================== S
         if constexpr (Source::kStoreBands) {
             reg_dec<kRegsS1>();
-            // A is kept: on a uniform mesh every interior row of a system holds the same four numbers.  Four 16 KB
-            // tiles (128 chunks of 8 identical rows: dl, d, du, b) are filled once per system and sent to every block of
-            // 128 interior chunks by TMA stores; the rows that differ or fall outside the chunk grid (the chunks holding
-            // mesh row 0 / n - 1, head rows, the cut row) are written by single lanes.  Two sets of tiles: the fill of
-            // system s + 1 does not wait for the engine to have read the tiles of system s.  Values =
-            // fh_assemble_1d_c128's, bit for bit (same generator).
-            const int ts = t - (kEBThreads + kIThreads), ws = ts >> 5, lane = ts & 31;
+            // A is kept: on a uniform mesh every interior row of a system holds the same four numbers, so what is
+            // written need not come from the rows the other roles eliminate.  The S warps hold the interior row in
+            // registers and stream it over the CTA's share of the four band arrays with plain 16-byte stores (a warp
+            // covers 512 contiguous bytes per instruction); the thread whose store covered mesh row 0 / N then overwrites
+            // it with that row's own values (same thread, same address: program order).  No shared memory, no barrier, no
+            // dependence on the other roles: the stores run ahead of the solves and fill the write bandwidth the
+            // latency-bound solver phases leave idle.  (Round 2 first sent tiles of identical rows by TMA stores: they
+            // queued in front of the solution store in the SM's one bulk-copy queue, and the E/B warps waited ~5,000
+            // cycles per system for their solution tile to come free.)  Values = fh_assemble_1d_c128's, bit for bit.
+            const int ts = t - (kEBThreads + kIThreads);
             const HostMap hm = host_map(n, CLUSTER);
-            const RowGeom g_mid = row_geom(src.p, 1);
-            const int count = map.chunks - hm.front[rank] - hm.back[rank];
+            const int64_t lo = rank == 0 ? 0 : hm.n_loc[0] + hm.cut;                 // first row this CTA writes ...
+            const int64_t cnt = rank == 0 ? hm.n_loc[0] + hm.cut : n - lo;           // ... and how many (rank 0: + cut row)
             uint32_t it = 0;
             for (int64_t sys = first_sys; sys < batch; sys += sys_stride, ++it) {
-                const uint32_t buf = it & 1;
                 const double k = __ldg(src.ks + sys), k2 = __ldg(src.k2s + sys);
                 cplx il, id, iu, ib;
-                row_values(src.p, g_mid, 1, k, k2, il, id, iu, ib);
-                if (it >= 2 && lane == 0) tma_store_wait_read1();  // the tiles sent two systems ago have been read
-                named_bar_sync(kBarS, kSThreads);
-                const uint32_t tile0 = smem_u32(&sm.stage[0][0]) + buf * 4u * kBandTileBytes;
-                const uint32_t mine = tile0 + (uint32_t)ts * 16u;
-#pragma unroll
-                for (uint32_t rep = 0; rep < kBandTileBytes; rep += kSThreads * 16u) {
-                    sts_volatile(mine + rep, il), sts_volatile(mine + kBandTileBytes + rep, id);
-                    sts_volatile(mine + 2 * kBandTileBytes + rep, iu), sts_volatile(mine + 3 * kBandTileBytes + rep, ib);
+                row_values(src.p, sm.bgeom[2], 1, k, k2, il, id, iu, ib);
+                FH_TRP(12 + (ts >> 5), 0);
+#ifndef FH_S_AHEAD
+#define FH_S_AHEAD 2
+#endif
+                if (FH_S_AHEAD >= 0) {  // pacing: at most FH_S_AHEAD systems ahead of the interface solves
+                    if ((ts & 31) == 0)
+                        while ((int)(it - *(volatile uint32_t *)&sm.i_done) > FH_S_AHEAD) __nanosleep(100);
+                    __syncwarp();
                 }
-                fence_proxy_async();
-                named_bar_sync(kBarS, kSThreads);
-                if (lane == 0) {  // one band per warp
-                    for (int c = 0; c < count; c += kBandTileChunks)
-                        tma_store_3d_from(&maps.band[rank][ws], 0, c, (int)sys, tile0 + (uint32_t)ws * kBandTileBytes);
-                    tma_store_commit();
+                const int64_t o0 = sys * n + lo, oe = o0 + cnt;
+#pragma unroll 4
+                for (int64_t o = o0 + ts; o < oe; o += kSThreads) {
+                    stg_stream(src.out_dl + o, il), stg_stream(src.out_d + o, id);
+                    stg_stream(src.out_du + o, iu), stg_stream(src.out_b + o, ib);
                 }
-                if (ws == 1) {
-                    cplx r0l, r0d, r0u, r0b, rNl, rNd, rNu, rNb;
-                    row_values(src.p, sm.bgeom[0], 0, k, k2, r0l, r0d, r0u, r0b);
-                    row_values(src.p, sm.bgeom[1], n - 1, k, k2, rNl, rNd, rNu, rNb);
-                    int64_t g = -1;  // the special row of this lane, if any
-                    const int64_t grid0 = hm.row0[rank];
-                    if (lane < map.head) g = map.global_row(lane);                                       // lanes 0..7: head rows
-                    if (lane == 8 && has_cut && rank == 0) g = cut_row;                                  // lane 8: the cut row
-                    if (lane >= 16 && lane < 24 && hm.front[rank]) g = grid0 + (lane - 16);              // first chunk
-                    if (lane >= 24 && hm.back[rank]) g = grid0 + 8 * (int64_t)(map.chunks - 1) + (lane - 24);  // last chunk
-                    if (g >= 0) {
-                        cplx vl = il, vd = id, vu = iu, vb = ib;
-                        if (g == 0) vl = r0l, vd = r0d, vu = r0u, vb = r0b;
-                        if (g == n - 1) vl = rNl, vd = rNd, vu = rNu, vb = rNb;
+#pragma unroll 1
+                for (int e = 0; e < 2; ++e) {  // the two mesh-boundary rows
+                    const int64_t g = e == 0 ? 0 : n - 1;
+                    if (g >= lo && g < lo + cnt && (int)((g - lo) % kSThreads) == ts) {
+                        cplx vl, vd, vu, vb;
+                        row_values(src.p, sm.bgeom[e], g, k, k2, vl, vd, vu, vb);
                         const int64_t o = sys * n + g;
                         stg_stream(src.out_dl + o, vl), stg_stream(src.out_d + o, vd);
                         stg_stream(src.out_du + o, vu), stg_stream(src.out_b + o, vb);
                     }
                 }
+                FH_TRP(12 + (ts >> 5), 4);
             }
-            if (lane == 0) tma_store_wait_read();
         }
     }
     if (CLUSTER > 1) cg::this_cluster().sync();  // no CTA leaves while its partner may still address it

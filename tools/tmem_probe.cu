@@ -67,6 +67,22 @@ __global__ void __launch_bounds__(384, 1) probe(long long *out, int reps) {
         }
         asm volatile("bar.sync 1, 256;");
         long long c3 = clock64();
+        // alignment: do xN moves need N-aligned columns?  (x8 at 4 mod 8, x16 at 12 mod 16, x4 at 20)
+        long long bad_al = 0;
+        {
+#pragma unroll
+            for (int i = 0; i < kCols; ++i) v[i] = (uint32_t)(t * 77 + i) * 2246822519u;
+            const uint32_t tb = ta + 128;
+            tmem_st8(tb + 4, v), tmem_st16(tb + 12, v + 8), tmem_st4(tb + 28, v + 24), tmem_st32(tb + 36, v + 28);
+            tmem_wait_st();
+            tmem_ld4(tb + 4, r), tmem_ld8(tb + 8, r + 4), tmem_ld16(tb + 16, r + 12), tmem_ld32(tb + 32, r + 28), tmem_ld8(tb + 60, r + 56), tmem_ld4(tb + 64, r + 60);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 56; ++i) bad_al += (r[i] != v[i]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) bad_al += (r[56 + i] != v[56 + i]) + (r[60 + i] != v[60 + i]);
+        }
+        atomicAdd((unsigned long long *)&out[blockIdx.x * 8 + 5], (unsigned long long)bad_al);
         // hand-over with the other warp group: this group produces, the other consumes
         for (int k = 0; k < 64; ++k) {
             asm volatile("bar.sync 4, 384;");          // mailbox consumed
@@ -109,8 +125,9 @@ int main() {
         printf("SM-block %3d: st %.0f cyc/park (%.1f B/cyc)  ld %.0f cyc/unpark (%.1f B/cyc)  round trip %.0f cyc  "
                "mismatches %lld  hand-over errors %lld\n", b, (double)h[b * 8] / reps, bytes * reps / h[b * 8],
                (double)h[b * 8 + 1] / reps, bytes * reps / h[b * 8 + 1], (double)h[b * 8 + 2] / reps, h[b * 8 + 3], h[b * 8 + 4]);
-    long long bad = 0;
-    for (int b = 0; b < 148; ++b) bad += h[b * 8 + 3] + h[b * 8 + 4];
+    long long bad = 0, bad_al = 0;
+    for (int b = 0; b < 148; ++b) bad += h[b * 8 + 3] + h[b * 8 + 4], bad_al += h[b * 8 + 5];
+    printf("unaligned xN moves (x8 at 4 mod 8, x16 at 12 mod 16, x32 at 36): %lld mismatches\n", bad_al);
     printf("total errors over 148 CTAs: %lld\n", bad);
     return bad != 0;
 }
