@@ -5,10 +5,13 @@ solves/s (k-sweep)").
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one pass of the hot path over one batch of synthetic input: the staged pipeline
-(band assembly kernel -> batched tridiagonal solve kernel) over the wavenumber sweep of BASELINE
+One "step" = one pass of the hot path over one batch of synthetic input: assembly of A (kept in
+HBM, bit-identical to the assembly kernel's bands) + the batched tridiagonal solve + the two safety
+nets, through the pipeline `solve_helmholtz_sweep` uses by default on a uniform mesh (one pass: the
+rows are generated, written out and solved in one kernel), over the wavenumber sweep of BASELINE
 configs[2]: 65,536 wavenumbers x the 4,096-element mesh per GPU (k in [1, 1000], Neumann +
-Sommerfeld rows, complex128).  Multi-GPU: every rank takes its own contiguous slice of a sweep of
+Sommerfeld rows, complex128).  The two-kernel staged pipeline (band assembly kernel -> batched solve
+kernel, round 1's headline) is timed right after it and reported under "staged".  Multi-GPU: every rank takes its own contiguous slice of a sweep of
 N x 65,536 wavenumbers (independent systems, no data-path collective) -> weak scaling.
 
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput; `e2e` goes through the public
@@ -34,7 +37,8 @@ N_K_PER_GPU = 65536    # wavenumbers per GPU
 K_MIN, K_MAX = 1.0, 1000.0
 BYTES_ASSEMBLY = 64    # per DOF: dl, d, du, b written (scalar-h mode)
 BYTES_SOLVE = 80       # per DOF: 4 bands read + u written
-METRIC = "assembled+solved DOF/s (k-sweep, staged assembly -> batched tridiagonal solve)"
+BYTES_ONE_PASS = 80    # per DOF: 4 bands + u written, nothing read
+METRIC = "assembled+solved DOF/s (k-sweep: A assembled and kept, batched tridiagonal solve)"
 
 
 def measured_peak_gbs():
@@ -203,9 +207,11 @@ def workload_config(n_gpus):
                         "(k in [1,1000], Neumann + Sommerfeld rows)",
             "n_elem": N_ELEM, "n_k_per_gpu": N_K_PER_GPU, "n_k_total": N_K_PER_GPU * n_gpus,
             "dof_per_step": N_K_PER_GPU * n_gpus * (N_ELEM + 1),
-            "pipeline": "staged: fh_assemble_1d_c128 -> fh_tridiag_solve_batched_c128",
+            "pipeline": "one pass (the default of solve_helmholtz_sweep): fh_helmholtz1d_sweep_assemble_solve_c128 writes the "
+                        "bands of A and solves from registers, then refinement + breakdown repair from the stored bands; "
+                        "the staged pair fh_assemble_1d_c128 -> fh_tridiag_solve_batched_c128 is reported under 'staged'",
             "parallelism": f"k-sharded x{n_gpus} (rank r owns ks[r::{n_gpus}]), no data-path collective",
-            "l2": "inputs larger than L2 (17.2 GB of bands + 4.3 GB of solutions per step; no flush needed)"}
+            "l2": "outputs larger than L2 (17.2 GB of bands + 4.3 GB of solutions written per step; no flush needed)"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -457,37 +463,68 @@ def run_gpu(args):
         fem1d.refine_flagged(bands[0], bands[1], bands[2], bands[3], U, status, sync=False, ws=refine_ws)
         fem1d.repair_flagged(bands[0], bands[1], bands[2], bands[3], U, status, sync=False, ws=repair_ws)
 
+    # one pass that KEEPS A: rows generated, written out as the bands and solved from registers (80 B/DOF of traffic
+    # instead of 144) -- the default pipeline of solve_helmholtz_sweep on a uniform mesh, and the headline step
+    def one_pass():
+        check(lib.fh_helmholtz1d_sweep_assemble_solve_c128(C.byref(prob), ptr(ks_d), ptr(k2s_d), n_k, ptr(bands[0]),
+                                                           ptr(bands[1]), ptr(bands[2]), ptr(bands[3]), ptr(U),
+                                                           ptr(status), None, 0, stream_ptr()), "one-pass")
+
     for _ in range(args.warmup):
-        assemble()
-        solve()
+        one_pass()
         safety_nets()
     barrier()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
         t_begin.record()
         for s in range(args.steps):
             ev[s][0].record()
-            assemble()
+            one_pass()
             ev[s][1].record()
-            solve()
-            ev[s][2].record()
             safety_nets()
-            ev[s][3].record()
+            ev[s][2].record()
         t_end.record()
         barrier()
     flagged, done = (int(v) for v in refine_ws[:8].view(torch.int32).tolist())
     assert flagged == done, "more systems flagged than the refinement workspace holds"
     repaired = fem1d.repair_counts(repair_ws)  # of the last step (every step sees the same wavenumbers)
     total_ms = t_begin.elapsed_time(t_end)
-    asm_ms = [e[0].elapsed_time(e[1]) for e in ev]
-    sol_ms = [e[1].elapsed_time(e[2]) for e in ev]
-    ref_ms = [e[2].elapsed_time(e[3]) for e in ev]
+    op_ms = [e[0].elapsed_time(e[1]) for e in ev]
+    ref_ms = [e[1].elapsed_time(e[2]) for e in ev]
     assert int((status & 1).sum()) == 0, "a system is singular to working precision (flag kept by the pivoted re-solve)"
 
-    # parity inside the bench: device-side backward error of what the timed steps produced
+    # parity inside the bench: device-side backward error of what the timed steps produced, against the bands the
+    # ASSEMBLY kernel writes (the one-pass kernel's own bands are compared with them bit for bit)
+    U_head = U.clone()
+    band_sums = bands.view(torch.int64).sum(dim=(1, 2))  # wrap-around integer checksum of the bit patterns of each band
     res = fh.tridiagonal_residual(bands[0], bands[1], bands[2], bands[3], U)
     backward_max = float(res["backward"].max())
+
+    # the two-kernel staged pipeline (round 1's headline): assembly kernel -> batched solve kernel -> safety nets
+    for _ in range(2):
+        assemble()
+        solve()
+        safety_nets()
+    barrier()
+    sev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    for s in range(args.steps):
+        sev[s][0].record()
+        assemble()
+        sev[s][1].record()
+        solve()
+        sev[s][2].record()
+        safety_nets()
+        sev[s][3].record()
+    barrier()
+    staged_ms = sev[0][0].elapsed_time(sev[-1][3]) / args.steps
+    asm_ms = [e[0].elapsed_time(e[1]) for e in sev]
+    sol_ms = [e[1].elapsed_time(e[2]) for e in sev]
+    staged_ref_ms = [e[2].elapsed_time(e[3]) for e in sev]
+    staged_berr = float(fh.tridiagonal_residual(bands[0], bands[1], bands[2], bands[3], U)["backward"].max())
+    # same bands, same arithmetic: the two pipelines agree bit for bit (solutions compared directly, bands by checksum)
+    same_as_staged = bool(torch.equal(U, U_head)) and bool(torch.equal(bands.view(torch.int64).sum(dim=(1, 2)), band_sums))
+    del U_head
 
     # fused variant (bands never stored), reported separately
     for _ in range(2):
@@ -500,26 +537,6 @@ def run_gpu(args):
     f1.record()
     barrier()
     fused_ms = f0.elapsed_time(f1) / args.steps
-
-    # one-pass variant that KEEPS A: rows generated, written out as the bands and solved from registers (80 B/DOF of
-    # traffic instead of 144), refinement from the stored bands included -- reported separately
-    def one_pass():
-        check(lib.fh_helmholtz1d_sweep_assemble_solve_c128(C.byref(prob), ptr(ks_d), ptr(k2s_d), n_k, ptr(bands[0]),
-                                                           ptr(bands[1]), ptr(bands[2]), ptr(bands[3]), ptr(U),
-                                                           ptr(status), None, 0, stream_ptr()), "one-pass")
-        safety_nets()
-
-    for _ in range(2):
-        one_pass()
-    barrier()
-    o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    o0.record()
-    for _ in range(args.steps):
-        one_pass()
-    o1.record()
-    barrier()
-    one_pass_ms = o0.elapsed_time(o1) / args.steps
-    one_pass_berr = float(fh.tridiagonal_residual(bands[0], bands[1], bands[2], bands[3], U)["backward"].max())
 
     # end-to-end through the public host-to-host API
     e2e = None
@@ -569,14 +586,14 @@ def run_gpu(args):
         del plan
 
     # max over ranks
-    vals = torch.tensor([total_ms, e2e_s, fused_ms,
-                         statistics.mean(sol_ms), statistics.mean(asm_ms), float(done), backward_max, one_pass_ms,
-                         one_pass_berr, float(repaired["flagged"]), float(repaired["kept"]), float(repaired["resolved"]),
-                         ceil_s, l2_s], dtype=torch.float64, device=dev)
+    vals = torch.tensor([total_ms, e2e_s, fused_ms, statistics.mean(sol_ms), statistics.mean(asm_ms), float(done),
+                         backward_max, staged_ms, staged_berr, float(repaired["flagged"]), float(repaired["kept"]),
+                         float(repaired["resolved"]), ceil_s, l2_s, statistics.mean(op_ms), statistics.mean(ref_ms),
+                         statistics.mean(staged_ref_ms), 0.0 if same_as_staged else 1.0], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-    (total_ms, e2e_s, fused_ms, sol_mean, asm_mean, refined_max, backward_max, one_pass_ms,
-     one_pass_berr, brk_flagged, brk_kept, brk_resolved, ceil_s, l2_s) = vals.tolist()
+    (total_ms, e2e_s, fused_ms, sol_mean, asm_mean, refined_max, backward_max, staged_ms, staged_berr, brk_flagged,
+     brk_kept, brk_resolved, ceil_s, l2_s, op_mean, ref_mean, staged_ref_mean, differs) = vals.tolist()
 
     configs = None
     if not args.no_configs:  # every rank takes part (config 4 holds a collective)
@@ -590,47 +607,66 @@ def run_gpu(args):
         ms_per_step = total_ms / args.steps
         value = dof_all / (ms_per_step * 1e-3)
         peak, peak_kind = measured_peak_gbs()
-        achieved = BYTES_SOLVE * dof_rank / (sol_mean * 1e-3) / 1e9
-        traffic = None
+        achieved = BYTES_ONE_PASS * dof_rank / (op_mean * 1e-3) / 1e9
+        achieved_solve = BYTES_SOLVE * dof_rank / (sol_mean * 1e-3) / 1e9
+        traffic = {}
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["solve_bytes_per_launch"]
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         except Exception:
             pass
+        traffic_note = ("profiles/ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of this kernel from a "
+                        "committed `ncu --set full` capture of the same launch -- a constant of that capture, not "
+                        "measured in this run")
+        peak_note = (f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured"
+                     else "fallback 6.65 TB/s (B200_PROFILING.md)")
+        staged_ms_all = staged_ms
         out = {
             "metric": METRIC, "value": value, "unit": "DOF/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "complex128", "data": "synthetic",
             "config": dict(workload_config(world), n_k_per_gpu=n_k, n_k_total=n_k * world, dof_per_step=n_k * world * n),
             "solves_per_s": n_k * world / (ms_per_step * 1e-3),
-            "roofline": {"bound": "hbm", "kernel": "tridiag_batched_kernel<2, BandSource>",
+            "roofline": {"bound": "hbm", "kernel": "tridiag_pipe_kernel<2, HelmSourceT<true, true>> "
+                                                   "(fh_helmholtz1d_sweep_assemble_solve_c128)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured"
-                         else "fallback 6.65 TB/s (B200_PROFILING.md)",
-                         "algorithmic_bytes_per_launch": BYTES_SOLVE * dof_rank, "traffic": traffic,
-                         "traffic_source": "profiles/ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of "
-                                           "this kernel from a committed `ncu --set full` capture of this command -- a "
-                                           "constant of that capture, not measured in this run",
-                         "launch_ms": sol_mean},
-            "stages": {"assembly_ms": asm_mean, "solve_ms": sol_mean, "refine_ms": statistics.mean(ref_ms),
-                       "solve_ms_per_step": [round(v, 3) for v in sol_ms],
+                         "peak_source": peak_note,
+                         "algorithmic_bytes_per_launch": BYTES_ONE_PASS * dof_rank,
+                         "algorithmic_bytes_per_dof": "64 written (dl, d, du, b) + 16 written (u), nothing read",
+                         "traffic": traffic.get("one_pass_bytes_per_launch"), "traffic_source": traffic_note,
+                         "launch_ms": op_mean},
+            "stages": {"one_pass_kernel_ms": op_mean, "refine_and_repair_ms": ref_mean,
+                       "one_pass_kernel_ms_per_step": [round(v, 3) for v in op_ms],
                        "refined_systems_per_step_max_over_ranks": int(refined_max),
                        "breakdown_flags_per_step_max_over_ranks": int(brk_flagged),
                        "breakdowns_kept_after_verification_max_over_ranks": int(brk_kept),
                        "pivoted_resolves_per_step_max_over_ranks": int(brk_resolved),
+                       "step_gbs": BYTES_ONE_PASS * dof_rank / (ms_per_step * 1e-3) / 1e9,
+                       "step_frac": BYTES_ONE_PASS * dof_rank / (ms_per_step * 1e-3) / 1e9 / peak},
+            "staged": {"what": "the two-kernel pipeline (round 1's headline): fh_assemble_1d_c128 -> "
+                               "fh_tridiag_solve_batched_c128 -> refinement + repair; same outputs, bit for bit",
+                       "ms_per_step": staged_ms_all, "value": dof_all / (staged_ms_all * 1e-3), "unit": "DOF/s",
+                       "bytes_per_dof": BYTES_ASSEMBLY + BYTES_SOLVE,
+                       "assembly_ms": asm_mean, "solve_ms": sol_mean, "refine_and_repair_ms": staged_ref_mean,
+                       "solve_ms_per_step": [round(v, 3) for v in sol_ms],
                        "assembly_gbs": BYTES_ASSEMBLY * dof_rank / (asm_mean * 1e-3) / 1e9,
                        "assembly_frac": BYTES_ASSEMBLY * dof_rank / (asm_mean * 1e-3) / 1e9 / peak,
-                       "staged_gbs": (BYTES_ASSEMBLY + BYTES_SOLVE) * dof_rank / (ms_per_step * 1e-3) / 1e9,
-                       "staged_frac": (BYTES_ASSEMBLY + BYTES_SOLVE) * dof_rank / (ms_per_step * 1e-3) / 1e9 / peak},
+                       "solve_roofline": {"bound": "hbm", "kernel": "tridiag_pipe_kernel<2, BandSource> "
+                                                                    "(fh_tridiag_solve_batched_c128)",
+                                          "achieved": achieved_solve, "peak": peak, "unit": "GB/s",
+                                          "frac": achieved_solve / peak,
+                                          "algorithmic_bytes_per_launch": BYTES_SOLVE * dof_rank,
+                                          "traffic": traffic.get("solve_bytes_per_launch"), "launch_ms": sol_mean},
+                       "staged_gbs": (BYTES_ASSEMBLY + BYTES_SOLVE) * dof_rank / (staged_ms_all * 1e-3) / 1e9,
+                       "staged_frac": (BYTES_ASSEMBLY + BYTES_SOLVE) * dof_rank / (staged_ms_all * 1e-3) / 1e9 / peak,
+                       "backward_error_max": staged_berr,
+                       "identical_to_one_pass_outputs": not differs},
             "fused": {"ms_per_step": fused_ms, "value": dof_all / (fused_ms * 1e-3), "unit": "DOF/s",
-                      "bytes_per_dof": 16},
-            "one_pass": {"ms_per_step": one_pass_ms, "value": dof_all / (one_pass_ms * 1e-3), "unit": "DOF/s",
-                         "bytes_per_dof": BYTES_ASSEMBLY + 16, "backward_error_max": one_pass_berr,
-                         "what": "fh_helmholtz1d_sweep_assemble_solve_c128 + refinement: A is written (bit-identical "
-                                 "bands) and the systems are solved in the same pass, A is never read back"},
+                      "bytes_per_dof": 16, "what": "fh_helmholtz1d_sweep_fused_c128: A never stored (no safety nets: "
+                                                   "nothing to refine from)"},
             "parity": {"backward_error_max": backward_max, "bar": 1e-10},
-            # per step: assembly, solve, 4 refinement kernels (compact, residual, correction solve, update), 2 repair
+            # per step: the one-pass kernel, 4 refinement kernels (compact, residual, correction solve, update), 2 repair
             # kernels (compact, verify-or-pivot)
-            "gpu_launches": 8 * args.steps,
+            "gpu_launches": 7 * args.steps,
             "clocks": clocks.summary(),
         }
         if configs is not None:
