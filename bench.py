@@ -664,9 +664,9 @@ def run_gpu(args):
                       "bytes_per_dof": 16, "what": "fh_helmholtz1d_sweep_fused_c128: A never stored (no safety nets: "
                                                    "nothing to refine from)"},
             "parity": {"backward_error_max": backward_max, "bar": 1e-10},
-            # per step: the one-pass kernel, 4 refinement kernels (compact, residual, correction solve, update), 2 repair
-            # kernels (compact, verify-or-pivot)
-            "gpu_launches": 7 * args.steps,
+            # per step: the one-pass kernel, 2 refinement kernels (flag compaction; the one-pass refinement solve:
+            # residual + correction solve + update), the repair kernel (scan + verify-or-pivot)
+            "gpu_launches": 4 * args.steps,
             "clocks": clocks.summary(),
         }
         if configs is not None:

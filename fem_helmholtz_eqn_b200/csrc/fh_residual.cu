@@ -217,62 +217,88 @@ extern "C" int fh_helmholtz1d_residual_c128(const fh_problem1d *prob_host, doubl
 // ---------------------------------------------------------------------------------------------------------
 // Selective iterative refinement, entirely on the device (no host round trip): the batched solver flags the systems
 // whose interface-row probe found a defect (status bit 1, value 2); exactly those get one step  r = b - A u,
-// A e = r, u += e.  Four stream-ordered launches:
-//   1. compact_flagged_kernel   status -> ascending list of flagged systems + their number (one CTA, block scan)
-//   2. residual_subset_kernel   r_i = b - A u of system list[i]                (compact rows)
-//   3. the batched solver       A(list[i]) e_i = r_i, matrices read in place   (fh_tridiag_batched.cu)
-//   4. correct_subset_kernel    u(list[i]) += e_i; status bit 1 cleared, bit 0 of the correction solve merged in
-// Launch sizes depend on the capacity of the workspace only; the kernels read the count from device memory.
+// A e = r, u += e.  Two stream-ordered launches:
+//   1. compact_flagged_kernel   status -> ascending list of flagged systems + their number (one CTA, ballots + scan)
+//   2. the batched solver as tridiag_pipe_kernel<., BandRefineSource> (fh_tridiag_pipe.cuh): the residual is formed
+//      while the rows of system list[i] are read, the correction is added to u by a TMA reduce-add, status bit 1 is
+//      cleared and bit 0 of the correction solve merged in -- 96 B of traffic per refined row.
+// Round 1 / early round 2 ran this as four launches (compaction, residual_subset_kernel into a compact r, the solver
+// on compact r -> e, correct_subset_kernel: 240 B per refined row, 0.32 ms for the 1,732 flagged systems of the
+// 65,536-wavenumber sweep against 0.19 ms now, tools/refine_probe.py); they remain behind the development switch
+// FH_REFINE=staged -- the two give the same bits (tests/test_gpu_1d.py spells the step out through the C ABI).
+// Launch sizes depend on the batch only; the kernels read the count from device memory.
 namespace fh {
 
 int batched_solve_subset(const cplx *dl, const cplx *d, const cplx *du, const cplx *r, cplx *e, int64_t n, int64_t batch,
                          const int32_t *list, const int32_t *count, int64_t cap, int32_t *status, cudaStream_t stream);
+int batched_refine_subset(const cplx *dl, const cplx *d, const cplx *du, const cplx *b, cplx *u, int64_t n, int64_t batch,
+                          const int32_t *list, const int32_t *count, int64_t cap, int32_t *status, cudaStream_t stream);
 
 constexpr int kCompactThreads = 1024;
+constexpr int kCompactWords = 2;  // 32-system flag words per thread and tile: a tile is 65,536 systems
 
-// header[0] = number of flagged systems, header[1] = number refined by this call (min(flagged, cap)).  One CTA; every
-// thread owns a run of consecutive systems (so the list comes out ascending): it counts its flagged ones, one block-wide
-// exclusive scan places the runs, and a second pass over the run (L1 hits) writes the indices.  Two barriers in all
-// (the first version walked status[] in tiles of 1024 with two barriers per tile: 52 us for 65,536 systems, a seventh
-// of the whole refinement).
+// header[0] = number of flagged systems, header[1] = number refined by this call (min(flagged, cap)).  One CTA walks
+// the status array in tiles of 65,536 systems: every warp reads its share with coalesced loads (32 consecutive systems
+// per instruction, eight instructions in flight) and turns each into one ballot word in shared memory; every thread then
+// owns two consecutive words, counts their bits, one block-wide exclusive scan places the threads, and the set bits are
+// written out as indices -- the list comes out ascending.  Three barriers per tile.  (The first versions read
+// status[] one int per thread and run: 52, then 46 us for 65,536 systems, a seventh of the whole refinement.)
 __global__ void __launch_bounds__(kCompactThreads)
 compact_flagged_kernel(const int32_t *__restrict__ status, int64_t batch, int32_t mask, int32_t cap,
                        int32_t *__restrict__ list, int32_t *__restrict__ header) {
+    __shared__ uint32_t bits[kCompactThreads * kCompactWords];
     __shared__ int warp_tot[kCompactThreads / 32];
+    __shared__ int tile_total;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int64_t per = (batch + kCompactThreads - 1) / kCompactThreads;
-    const int64_t s_begin = (int64_t)t * per, s_end = s_begin + per < batch ? s_begin + per : batch;
-    int count = 0;
-    for (int64_t s = s_begin; s < s_end; ++s) count += (status[s] & mask) != 0 ? 1 : 0;
-    int incl = count;  // inclusive scan inside the warp ...
+    constexpr int kWarpWords = 32 * kCompactWords;
+    constexpr int64_t kTile = (int64_t)kCompactThreads * kCompactWords * 32;
+    int running = 0;
+    for (int64_t base = 0; base < batch; base += kTile) {
+#pragma unroll 8
+        for (int q = 0; q < kWarpWords; ++q) {
+            const int64_t s = base + ((int64_t)(warp * kWarpWords + q) << 5) + lane;
+            const bool f = s < batch && (status[s] & mask) != 0;
+            const uint32_t w = __ballot_sync(0xffffffffu, f);
+            if (lane == (q & 31)) bits[warp * kWarpWords + q] = w;
+        }
+        __syncwarp();
+        uint32_t w[kCompactWords];
+        int count = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    if (lane == 31) warp_tot[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {  // ... and over the 32 warp totals
-        const int v = warp_tot[lane];
-        int w = v;
+        for (int j = 0; j < kCompactWords; ++j) w[j] = bits[t * kCompactWords + j], count += __popc(w[j]);
+        int incl = count;  // inclusive scan inside the warp ...
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const int q = __shfl_up_sync(0xffffffffu, w, o);
-            if (lane >= o) w += q;
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
         }
-        warp_tot[lane] = w - v;  // exclusive
-        if (lane == 31) {
-            header[0] = w;
-            header[1] = w < cap ? w : cap;
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {  // ... and over the 32 warp totals
+            const int v = warp_tot[lane];
+            int x = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int q = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += q;
+            }
+            warp_tot[lane] = x - v;  // exclusive
+            if (lane == 31) tile_total = x;
         }
+        __syncthreads();
+        int pos = running + warp_tot[warp] + incl - count;
+#pragma unroll
+        for (int j = 0; j < kCompactWords; ++j) {
+            const int64_t s0 = base + ((int64_t)(t * kCompactWords + j) << 5);
+            for (uint32_t m = w[j]; m != 0; m &= m - 1, ++pos)
+                if (pos < cap) list[pos] = (int32_t)(s0 + __ffs((int)m) - 1);
+        }
+        running += tile_total;
+        __syncthreads();  // (warp_tot / tile_total are rewritten by the next tile)
     }
-    __syncthreads();
-    int pos = warp_tot[warp] + incl - count;
-    for (int64_t s = s_begin; s < s_end && count > 0; ++s) {
-        if ((status[s] & mask) != 0) {
-            if (pos < cap) list[pos] = (int32_t)s;
-            ++pos;
-        }
+    if (t == 0) {
+        header[0] = running;
+        header[1] = running < cap ? running : cap;
     }
 }
 
@@ -308,12 +334,21 @@ struct RefinePlan {  // carving of the workspace
     int64_t cap;
     size_t off_header, off_list, off_status, off_r, off_e, total;
 };
+static bool refine_staged() {  // development switch: the four-launch refinement of round 1
+    static const bool v = [] { const char *e = getenv("FH_REFINE"); return e != nullptr && e[0] == 's'; }();
+    return v;
+}
 static RefinePlan refine_plan(int64_t n, int64_t batch, size_t workspace_bytes) {
     RefinePlan p;
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     p.off_header = 0;
     p.off_list = up(2 * sizeof(int32_t));
     p.off_status = p.off_list + up(sizeof(int32_t) * (size_t)batch);
+    if (!refine_staged()) {  // one pass: the header and the list are all there is; every flagged system fits
+        p.cap = workspace_bytes >= p.off_status ? batch : 0;
+        p.off_r = p.off_e = p.total = p.off_status;
+        return p;
+    }
     const size_t fixed = p.off_status + up(sizeof(int32_t) * (size_t)batch);
     const size_t per_system = 2 * sizeof(cplx) * (size_t)n;
     int64_t cap = workspace_bytes > fixed ? (int64_t)((workspace_bytes - fixed) / per_system) : 0;
@@ -332,6 +367,7 @@ extern "C" size_t fh_tridiag_refine_flagged_workspace_bytes(int64_t n, int64_t b
     if (max_systems > batch) max_systems = batch;
     if (max_systems < 1) max_systems = 1;
     const fh::RefinePlan p = fh::refine_plan(n, batch, (size_t)0);
+    if (!fh::refine_staged()) return p.total;  // (max_systems: what the four-launch version sized its r / e arrays by)
     return p.off_r + 2 * sizeof(fh::cplx) * (size_t)n * (size_t)max_systems;
 }
 
@@ -358,6 +394,10 @@ extern "C" int fh_tridiag_refine_flagged_c128(const fh_c128 *dl, const fh_c128 *
     const int32_t mask = 2;  // FH_STATUS_SMALL_PIVOT
     compact_flagged_kernel<<<1, kCompactThreads, 0, st>>>(status, batch, mask, (int32_t)p.cap, list, header);
     FH_LAUNCH_CHECK("compact_flagged_kernel");
+    if (!refine_staged())
+        return batched_refine_subset(reinterpret_cast<const cplx *>(dl), reinterpret_cast<const cplx *>(d),
+                                     reinterpret_cast<const cplx *>(du), reinterpret_cast<const cplx *>(b),
+                                     reinterpret_cast<cplx *>(u), n, batch, list, header + 1, p.cap, status, st);
     const unsigned grid = (unsigned)(8 * sm_count());
     residual_subset_kernel<<<grid, kResThreads, 0, st>>>(
         reinterpret_cast<const cplx *>(dl), reinterpret_cast<const cplx *>(d), reinterpret_cast<const cplx *>(du),

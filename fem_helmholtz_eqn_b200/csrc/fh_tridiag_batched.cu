@@ -722,12 +722,19 @@ static int launch_batched(const Source &src, const cplx *const bands[4], cplx *u
     // generated on a non-uniform mesh (per-row geometry with IEEE divisions, far more registers) stay with the
     // one-role-per-CTA kernel.  Development switch: FH_BATCHED=serial launches that kernel for every source.
     constexpr bool kPipe = Source::kStaged || Source::kUniform;
-    static const bool serial = [] { const char *e = getenv("FH_BATCHED"); return !kPipe || (e != nullptr && e[0] == 's'); }();
+    static const bool serial = [] {
+        const char *e = getenv("FH_BATCHED");
+        return !kPipe || (!Source::kRefine && e != nullptr && e[0] == 's');
+    }();
     auto pipe_or_serial = [] {
         if constexpr (kPipe) return tridiag_pipe_kernel<CLUSTER, Source>;
         else return tridiag_batched_kernel<CLUSTER, Source>;
     };
-    auto kernel = serial ? tridiag_batched_kernel<CLUSTER, Source> : pipe_or_serial();
+    auto serial_or_pipe = [] {  // (the one-pass refinement exists as a pipeline instance only)
+        if constexpr (Source::kRefine) return tridiag_pipe_kernel<CLUSTER, Source>;
+        else return tridiag_batched_kernel<CLUSTER, Source>;
+    };
+    auto kernel = serial ? serial_or_pipe() : pipe_or_serial();
     const size_t smem = (serial ? sizeof(BatchedSmem) : sizeof(PipeSmem)) + 1024;  // slack for the 1024-byte round-up
     if (smem > smem_optin_bytes()) {
         set_error("kernel needs %zu B of shared memory, device offers %zu", smem, smem_optin_bytes());
@@ -743,7 +750,9 @@ static int launch_batched(const Source &src, const cplx *const bands[4], cplx *u
     memset(&maps, 0, sizeof(maps));
     memset(&umaps, 0, sizeof(umaps));
     for (int r = 0; r < CLUSTER; ++r) {  // every rank sees only its own chunks: loads zero-fill, stores clip
-        int rc = make_tensor_map(&umaps.r[r], u, n, batch, h.row0[r], h.chunks[r], kChunks8);
+        // (refinement in place: the solutions are those of the whole batch, addressed through the list)
+        int rc = make_tensor_map(&umaps.r[r], u, n, Source::kRefine ? batch_matrices : batch, h.row0[r], h.chunks[r],
+                                 kChunks8);
         if (rc != FH_OK) return rc;
         if (Source::kStoreBands) {  // store views over the interior chunks of the rank, in boxes of kBandTileChunks chunks
             for (int i = 0; i < 4; ++i) {
@@ -754,14 +763,14 @@ static int launch_batched(const Source &src, const cplx *const bands[4], cplx *u
         }
         if (Source::kStaged) {
             for (int i = 0; i < 4; ++i) {
-                rc = make_tensor_map(&maps.band[r][i], bands[i], n, i < 3 ? batch_matrices : batch, h.row0[r],
-                                     h.chunks[r], kChunks8);
+                rc = make_tensor_map(&maps.band[r][i], bands[i], n, i < 3 || Source::kRefine ? batch_matrices : batch,
+                                     h.row0[r], h.chunks[r], kChunks8);
                 if (rc != FH_OK) return rc;
             }
         }
     }
     FH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (status != nullptr) FH_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t) * batch, stream));
+    if (status != nullptr && !Source::kRefine) FH_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t) * batch, stream));
     int64_t groups = sm_count() / CLUSTER;  // one CTA per SM (~194 KB of shared memory each)
     if (groups < 1) groups = 1;
     if (groups > batch) groups = batch;
@@ -809,6 +818,19 @@ int batched_solve_subset(const cplx *dl, const cplx *d, const cplx *du, const cp
     const cplx *const bands[4] = {dl, d, du, r};
     if (n <= kStageRows) return launch_batched<1>(src, bands, e, n, cap, status, stream, batch);
     return launch_batched<2>(src, bands, e, n, cap, status, stream, batch);
+}
+
+// One refinement step  u(list[i]) += A(list[i])^-1 (b - A u)(list[i]),  i < min(*count, cap), in one pass over the
+// flagged systems (BandRefineSource): status[list[i]] loses the small-pivot bit and gains the breakdown bit if the
+// correction solve breaks down.
+int batched_refine_subset(const cplx *dl, const cplx *d, const cplx *du, const cplx *b, cplx *u, int64_t n, int64_t batch,
+                          const int32_t *list, const int32_t *count, int64_t cap, int32_t *status, cudaStream_t stream) {
+    BandRefineSource src;
+    src.dl = dl, src.d = d, src.du = du, src.b = b;
+    src.list = list, src.count = count, src.u_old = u;
+    const cplx *const bands[4] = {dl, d, du, b};
+    if (n <= kStageRows) return launch_batched<1>(src, bands, u, n, cap, status, stream, batch);
+    return launch_batched<2>(src, bands, u, n, cap, status, stream, batch);
 }
 
 }  // namespace fh

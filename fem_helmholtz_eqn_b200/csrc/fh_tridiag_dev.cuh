@@ -101,6 +101,7 @@ struct BandSource {  // staged pipeline: bands live in global memory
     static constexpr bool kUniform = false;
     static constexpr bool kSubset = false;
     static constexpr bool kStoreBands = false;
+    static constexpr bool kRefine = false;
 };
 
 // Refinement of a SUBSET of a batch (fh_tridiag_refine_flagged_c128): the matrix of compact system i is system
@@ -111,6 +112,21 @@ struct BandSubsetSource : BandSource {
     const int32_t *list;
     const int32_t *count;
     static constexpr bool kSubset = true;
+};
+
+// One step of iterative refinement of a subset IN ONE PASS (fh_tridiag_refine_flagged_c128 since round 2): compact
+// system i is system list[i] of ALL five arrays.  The right-hand side of the correction solve, r = b - A u, is formed
+// while the rows are read (each thread fetches the ten solution values its eight rows touch), the correction leaves
+// as a TMA reduce-add onto u (cp.reduce.async.bulk.tensor .add, f64: u += e happens in L2), the small-pivot flag of the
+// system is cleared and a breakdown of the correction solve sets the breakdown bit in the batch's own status array:
+// 96 bytes of HBM traffic per refined row instead of the 240 of the residual / solve / update kernels it replaces, and
+// bit-identical to them (same operation order in the residual, the same solve, the same IEEE addition).
+struct BandRefineSource : BandSource {
+    const int32_t *list;
+    const int32_t *count;
+    const cplx *u_old;  // the solutions being refined (the array the store maps address)
+    static constexpr bool kSubset = true;
+    static constexpr bool kRefine = true;
 };
 
 // fused pipeline: bands are generated, never stored.  UNIFORM = scalar-h mesh with at least two elements: every
@@ -127,6 +143,7 @@ struct HelmSourceT {
     static constexpr bool kUniform = UNIFORM;
     static constexpr bool kSubset = false;
     static constexpr bool kStoreBands = STORE;
+    static constexpr bool kRefine = false;
 };
 
 struct HelmState {  // per-thread state of the generator

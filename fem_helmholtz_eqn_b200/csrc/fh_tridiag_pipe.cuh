@@ -39,7 +39,8 @@ constexpr uint32_t kParkStride = 128;            // columns between a thread's t
 static_assert(kParkCols == 100 && kParkCols <= (int)kParkStride, "parking layout");
 
 enum : int { kBarEB = 1, kBarI = 2, kBarFullReady = 3, kBarFullFree = 4, kBarX0 = 5, kBarX1 = 6, kBarS = 7 };
-constexpr int kRegsEB = 200, kRegsI = 96;                      // 256 * 200 + 128 * 96 <= 384 * 168
+constexpr int kRegsEB = 200, kRegsI = 96;                      // 256 * 200 + 128 * 96 <= 384 * 168 (208 / 96 = all 64 K
+                                                               // registers: setmaxnreg.inc never returns -- measured)
 constexpr int kRegsEB1 = 184, kRegsI1 = 88, kRegsS1 = 56;      // 256 * 184 + 128 * 88 + 128 * 56 = 512 * 128
 
 // PCR arrays of the I group: kH rows each, kHalfPad zero rows before and after (the largest PCR stride); the pad behind
@@ -83,6 +84,21 @@ __device__ __forceinline__ void tma_store_3d_from(const CUtensorMap *map, int c0
                  "r"(c0), "r"(c1), "r"(c2), "r"(smem_addr)
                  : "memory");
 }
+// u += tile: the TMA engine hands the tile to L2, which carries out the IEEE additions (f64 tensor map)
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap *map, int c0, int c1, int c2, const void *src) {
+    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(src))
+                 : "memory");
+}
+__device__ __forceinline__ void red_add(cplx *p, cplx v) {  // *p += v (two fp64 reductions in L2)
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(&p->re), "d"(v.re) : "memory");
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(&p->im), "d"(v.im) : "memory");
+}
+__device__ __forceinline__ cplx ldg_cg(const cplx *p) {  // coherent (L2) read of data this kernel also updates elsewhere
+    double2 v;
+    asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return mk(v.x, v.y);
+}
 __device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 __device__ __forceinline__ void park100(uint32_t ta, const uint32_t *v) {
@@ -97,6 +113,44 @@ __device__ __forceinline__ void put2(uint32_t *v, int i, cplx z) {
 }
 __device__ __forceinline__ cplx get2(const uint32_t *v, int i) {
     return mk(__hiloint2double((int)v[4 * i + 1], (int)v[4 * i]), __hiloint2double((int)v[4 * i + 3], (int)v[4 * i + 2]));
+}
+
+// v[j] <- v[j ^ c], c in 0..7 (three conditional exchange stages; register arrays stay statically indexed)
+__device__ __forceinline__ void xor_permute8(cplx (&v)[8], int c) {
+#pragma unroll
+    for (int bit = 1; bit < 8; bit <<= 1) {
+        const bool sw = (c & bit) != 0;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            if ((m & bit) == 0) {
+                const cplx a = v[m], b = v[m | bit];
+                v[m] = mk(sw ? b.re : a.re, sw ? b.im : a.im);
+                v[m | bit] = mk(sw ? a.re : b.re, sw ? a.im : b.im);
+            }
+        }
+    }
+}
+__device__ __forceinline__ cplx shfl_from(cplx z, int lane) {
+    return mk(__shfl_sync(0xffffffffu, z.re, lane), __shfl_sync(0xffffffffu, z.im, lane));
+}
+__device__ __forceinline__ cplx shfl_up1(cplx z) {
+    return mk(__shfl_up_sync(0xffffffffu, z.re, 1), __shfl_up_sync(0xffffffffu, z.im, 1));
+}
+__device__ __forceinline__ cplx shfl_down1(cplx z) {
+    return mk(__shfl_down_sync(0xffffffffu, z.re, 1), __shfl_down_sync(0xffffffffu, z.im, 1));
+}
+// In: v[k] = row 32 k + lane of a warp's 256 rows (how coalesced loads deliver them).  Out: v[i] = row 8 lane + i (how
+// the elimination owns them).  Thread T wants register k = T >> 2 of the lanes 8 (T & 3) + i; in step j it reads lane
+// 8 (T & 3) + (j ^ (T >> 2)), which offers its register j ^ (lane & 7) -- i.e. register T >> 2: eight shuffles in which
+// every lane sends and receives something useful, framed by two XOR permutations of the registers.
+__device__ __forceinline__ void warp_rows_to_threads(cplx (&v)[8], int lane) {
+    xor_permute8(v, lane & 7);
+    cplx w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[j] = shfl_from(v[j], 8 * (lane & 3) + (j ^ (lane >> 2)));
+    xor_permute8(w, lane >> 2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = w[j];
 }
 
 template <class Source>
@@ -197,14 +251,15 @@ tridiag_pipe_kernel(const __grid_constant__ TensorMaps maps, const __grid_consta
                     tma_load_3d(sm.stage[0], map_lo, 0, map.box_c1, (int)sysm, &sm.full_bar);
                     tma_load_3d(sm.stage[1], &tmaps[1], 0, map.box_c1, (int)sysm, &sm.full_bar);
                     tma_load_3d(sm.stage[2], map_hi, 0, map.box_c1, (int)sysm, &sm.full_bar);
-                    tma_load_3d(sm.stage[3], &tmaps[3], 0, map.box_c1, (int)sys, &sm.full_bar);
+                    const int64_t sysb = Source::kRefine ? sysm : sys;  // right-hand sides: compact unless refining in place
+                    tma_load_3d(sm.stage[3], &tmaps[3], 0, map.box_c1, (int)sysb, &sm.full_bar);
                     const cplx *lo = map.dir > 0 ? src.dl : src.du, *hi = map.dir > 0 ? src.du : src.dl;
                     for (int j = 0; j < map.head; ++j) {
                         const int64_t g = sysm * n + map.global_row(j);
                         cp_async16(&sm.headst[0][j], lo + g);
                         cp_async16(&sm.headst[1][j], src.d + g);
                         cp_async16(&sm.headst[2][j], hi + g);
-                        cp_async16(&sm.headst[3][j], src.b + sys * n + map.global_row(j));
+                        cp_async16(&sm.headst[3][j], src.b + sysb * n + map.global_row(j));
                     }
                     cp_async_commit();
                 }
@@ -222,6 +277,11 @@ tridiag_pipe_kernel(const __grid_constant__ TensorMaps maps, const __grid_consta
 #pragma unroll
         for (int i = 0; i < kCarry; ++i) ca[i] = cc[i] = pa[i] = pc[i] = 0.0;
         c3[0] = c3[1] = c3[2] = p3[0] = p3[1] = p3[2] = 0.0;
+        // refinement in one pass: solution value of local row j of the system whose solution starts at `us`
+        [[maybe_unused]] auto u_at = [&](const cplx *us, int j) -> cplx {
+            const int64_t g = map.global_row(j);
+            return g >= 0 && g < n ? ldg_cg(us + g) : czero();
+        };
         uint32_t it = 0;
         int64_t prev = -1;
         for (int64_t sys = first_sys;; sys += sys_stride, ++it) {
@@ -269,6 +329,34 @@ tridiag_pipe_kernel(const __grid_constant__ TensorMaps maps, const __grid_consta
                 } else {
                     cplx a[kM], b[kM], c[kM], d[kM];
                     uint32_t tile_addr = 0, tile_x = 0;
+                    // refinement in one pass: the solution values the thread's rows touch (local rows L - 1 .. L + 8).
+                    // A thread's rows are 128 contiguous bytes, so fetching them thread by thread costs a warp ten
+                    // requests of 32 scattered sectors each (measured: 3.7 us per system, as much as the solve).  The
+                    // warp therefore reads its 256 rows with eight coalesced requests (lane l: rows 32 k + l), issued
+                    // before the wait for the tiles, and transposes them in registers (warp_rows_to_threads: 32
+                    // shuffles); the two rows beyond the warp's ends are fetched by its first and last lane.
+                    // rhs_of() turns a row's b into b - A u with the operation order of residual_subset_kernel
+                    // (diagonal, sub-diagonal, super-diagonal of the GLOBAL numbering).
+                    [[maybe_unused]] cplx uo[kM + 2], ur[kM];
+                    [[maybe_unused]] const cplx *uold = nullptr;
+                    [[maybe_unused]] int64_t m_next = -1;
+                    [[maybe_unused]] const int Lrow = map.head + kM * (t - map.first_active);
+                    [[maybe_unused]] auto u_local = [&](int j) -> cplx { return u_at(uold, j); };
+                    [[maybe_unused]] auto rhs_of = [&](int64_t g, cplx ra, cplx rb, cplx rc, cplx rd, cplx um, cplx u0, cplx up) -> cplx {
+                        cplx v = nmsub(rd, rb, u0);
+                        if (g > 0) v = nmsub(v, map.dir > 0 ? ra : rc, map.dir > 0 ? um : up);
+                        if (g < n - 1) v = nmsub(v, map.dir > 0 ? rc : ra, map.dir > 0 ? up : um);
+                        return v;
+                    };
+                    if constexpr (Source::kRefine) {
+                        uold = src.u_old + matrix_of(sys) * n;
+                        if (sys + sys_stride < batch) m_next = src.list[sys + sys_stride];
+                        const int lane = t & 31, Lw = map.head + kM * (32 * warp - map.first_active);
+#pragma unroll
+                        for (int k = 0; k < kM; ++k) ur[k] = u_local(Lw + 32 * k + lane);
+                        uo[0] = lane == 0 ? u_local(Lw - 1) : czero();
+                        uo[kM + 1] = lane == 31 ? u_local(Lw + 32 * kM) : czero();
+                    }
                     if constexpr (Source::kStaged) {
                         mbar_wait(&sm.full_bar, parity);
                         if (map.head > 0 && t == feeder) cp_async_wait_all();
@@ -276,6 +364,14 @@ tridiag_pipe_kernel(const __grid_constant__ TensorMaps maps, const __grid_consta
                         const int r = tt / kPer8;
                         tile_addr = smem_u32(&sm.stage[0][0]) + (uint32_t)r * 128u;
                         tile_x = (uint32_t)(r & 7);
+                    }
+                    if constexpr (Source::kRefine) {
+                        warp_rows_to_threads(ur, t & 31);
+#pragma unroll
+                        for (int i = 0; i < kM; ++i) uo[i + 1] = ur[i];
+                        const cplx up = shfl_up1(ur[kM - 1]), dn = shfl_down1(ur[0]);
+                        if ((t & 31) != 0) uo[0] = up;
+                        if ((t & 31) != 31) uo[kM + 1] = dn;
                     }
                     FH_TRP(warp, 1);
                     // generated rows: mesh row g in the CTA's local orientation (only the threads that own a mesh boundary
@@ -297,6 +393,8 @@ tridiag_pipe_kernel(const __grid_constant__ TensorMaps maps, const __grid_consta
                             const uint32_t ad = tile_addr + ((e ^ tile_x) << 4);
                             a[i] = lds_volatile(ad), b[i] = lds_volatile(ad + kTileBytes);
                             c[i] = lds_volatile(ad + 2 * kTileBytes), d[i] = lds_volatile(ad + 3 * kTileBytes);
+                            if constexpr (Source::kRefine)
+                                d[i] = rhs_of(map.global_row(Lrow + i), a[i], b[i], c[i], d[i], uo[i], uo[i + 1], uo[i + 2]);
                         } else {
                             a[i] = map.dir > 0 ? il : iu, b[i] = id, c[i] = map.dir > 0 ? iu : il, d[i] = ib;
                             // a mesh boundary row can only sit in the first slot of the first active thread (local row 0,
@@ -318,6 +416,8 @@ tridiag_pipe_kernel(const __grid_constant__ TensorMaps maps, const __grid_consta
                             cplx ha, hb, hc, hd;
                             if constexpr (Source::kStaged) {
                                 ha = sm.headst[0][j], hb = sm.headst[1][j], hc = sm.headst[2][j], hd = sm.headst[3][j];
+                                if constexpr (Source::kRefine)
+                                    hd = rhs_of(map.global_row(j), ha, hb, hc, hd, u_local(j - 1), u_local(j), u_local(j + 1));
                             } else {
                                 gen_row(map.global_row(j), ha, hb, hc, hd);
                             }
@@ -347,6 +447,13 @@ tridiag_pipe_kernel(const __grid_constant__ TensorMaps maps, const __grid_consta
                         if (i < kM - 1) b[i] = frecip(b[i]);
                     }
                     FH_TRP(warp, 2);
+                    if constexpr (Source::kRefine) {  // the next system's solution rows on their way into L2 (one line per lane:
+                        if (m_next >= 0) {            // carrying the values themselves across the iteration spilled, and was slower)
+                            const int64_t g = map.global_row(map.head + kM * (t - map.first_active) + (map.dir > 0 ? 0 : kM - 1));
+                            if (g >= 0 && g < n)
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(src.u_old + m_next * n + g) : "memory");
+                        }
+                    }
                     if constexpr (Source::kStaged) {
                         named_bar_sync(kBarEB, kEBThreads);  // every thread has drained the staging tiles ...
                         if (sys + sys_stride < batch) prefetch(sys + sys_stride);  // ... refill them
@@ -400,6 +507,7 @@ tridiag_pipe_kernel(const __grid_constant__ TensorMaps maps, const __grid_consta
             if (prev >= 0) {
                 // ------------------------------------------------------------------------ B: back-substitution of `prev`
                 const uint32_t pp = (it - 1) & 1;
+                const int64_t pm = Source::kRefine ? matrix_of(prev) : prev;  // where the solution and its status live
                 uint32_t pk[kParkCols];
                 if (!have) {  // last system: no elimination ran in this iteration (its waits are made up for here)
                     tmem_wait_st();
@@ -439,13 +547,14 @@ tridiag_pipe_kernel(const __grid_constant__ TensorMaps maps, const __grid_consta
                 }
                 if (map.head > 0 && t == feeder) {
                     cplx xn = x0;
-                    cplx *out = u + prev * n;
+                    cplx *out = u + pm * n;
 #pragma unroll 1
                     for (int j = map.head - 1; j >= 0; --j) {
                         const cplx hcp = sm.headf[pp][0][j], hdp = sm.headf[pp][1][j];
                         xn = (map.chunks == 0 && j == map.head - 1) ? hdp : nmsub(hdp, hcp, xn);
                         bad |= !cfinite(xn);
-                        stg_stream(out + map.global_row(j), xn);
+                        if constexpr (Source::kRefine) red_add(out + map.global_row(j), xn);
+                        else stg_stream(out + map.global_row(j), xn);
                     }
                 }
                 fence_proxy_async();  // make this thread's xs writes visible to the TMA engine
@@ -453,10 +562,12 @@ tridiag_pipe_kernel(const __grid_constant__ TensorMaps maps, const __grid_consta
                 FH_TRP(warp, 8);
                 if (t == kStoreThread) {
                     if (map.chunks > 0) {
-                        tma_store_3d(&umaps.r[rank], 0, 0, (int)prev, sm.xs);
+                        if constexpr (Source::kRefine) tma_reduce_add_3d(&umaps.r[rank], 0, 0, (int)pm, sm.xs);
+                        else tma_store_3d(&umaps.r[rank], 0, 0, (int)pm, sm.xs);
                         tma_store_commit();
                     }
-                    if (status != nullptr && any_nonfinite) atomicOr(&status[prev], 1);
+                    if constexpr (Source::kRefine) atomicAnd(&status[pm], ~2);  // refined: the small-pivot flag goes
+                    if (status != nullptr && any_nonfinite) atomicOr(&status[pm], 1);
                 }
                 {   // probe: defect of the original interface row with the computed solution
                     cplx xn = x_partner;
@@ -466,7 +577,11 @@ tridiag_pipe_kernel(const __grid_constant__ TensorMaps maps, const __grid_consta
                     const bool off = active && abs1(r) > kProbeTol * scale;
                     const bool severe = active && abs1(r) > kSevereTol * scale;
                     const bool any_off = __any_sync(0xffffffffu, off), any_severe = __any_sync(0xffffffffu, severe);
-                    if (any_off && (t & 31) == 0 && status != nullptr) atomicOr(&status[prev], any_severe ? 3 : 2);
+                    if constexpr (Source::kRefine) {  // a correction solve that breaks down again: pivoted re-solve
+                        if (any_severe && (t & 31) == 0) atomicOr(&status[pm], 1);
+                    } else {
+                        if (any_off && (t & 31) == 0 && status != nullptr) atomicOr(&status[pm], any_severe ? 3 : 2);
+                    }
                 }
                 FH_TRP(warp, 9);
             }
@@ -505,7 +620,12 @@ tridiag_pipe_kernel(const __grid_constant__ TensorMaps maps, const __grid_consta
                 if constexpr (Source::kStaged) {
                     const int64_t g = matrix_of(sys) * n + cut_row;
                     cl = ldg_stream(src.dl + g), cb = ldg_stream(src.d + g), ch = ldg_stream(src.du + g);
-                    cd = ldg_stream(src.b + sys * n + cut_row);
+                    if constexpr (Source::kRefine) {
+                        const cplx *uc = src.u_old + g;
+                        cd = nmsub(nmsub(nmsub(ldg_stream(src.b + g), cb, ldg_cg(uc)), cl, ldg_cg(uc - 1)), ch, ldg_cg(uc + 1));
+                    } else {
+                        cd = ldg_stream(src.b + sys * n + cut_row);
+                    }
                 } else {  // uniform mesh: the cut row is an interior row (n >= 2057 here)
                     row_values(src.p, sm.bgeom[2], 1, __ldg(src.ks + sys), __ldg(src.k2s + sys), cl, cb, ch, cd);
                 }
@@ -571,7 +691,10 @@ tridiag_pipe_kernel(const __grid_constant__ TensorMaps maps, const __grid_consta
                     const cplx Y1 = rank == 0 ? Yp : Ym, V1 = rank == 0 ? Vp : Vm;
                     const cplx den = nmsub(nmsub(cb, cl, V0), ch, V1);
                     x_partner = nmsub(nmsub(cd, cl, Y0), ch, Y1) * frecip(den);
-                    if (rank == 0 && j == kH - 1) stg_stream(u + sys * n + cut_row, x_partner);
+                    if (rank == 0 && j == kH - 1) {
+                        if constexpr (Source::kRefine) red_add(u + matrix_of(sys) * n + cut_row, x_partner);
+                        else stg_stream(u + sys * n + cut_row, x_partner);
+                    }
                 } else {
                     const cplx x_me = nmsub(Ym, Vm, Yp) * frecip(nmsub(cone(), Vm, Vp));
                     x_partner = nmsub(Yp, Vp, x_me);

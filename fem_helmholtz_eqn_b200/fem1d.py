@@ -255,12 +255,13 @@ def _refine_workspace(n, batch, device, min_systems=0):
 
 def refine_flagged(dl, d, du, b, u, status, sync=True, ws=None):
     """One step of iterative refinement for exactly the systems whose elimination met a small pivot
-    (``status & STATUS_SMALL_PIVOT``): r = b - A u, solve A e = r, u += e -- all on the device, matrices read in
-    place through an index list that never visits the host (``fh_tridiag_refine_flagged_c128``).  The solver is
+    (``status & STATUS_SMALL_PIVOT``): r = b - A u, solve A e = r, u += e -- all on the device, in one pass over the
+    flagged systems, which are read in place through an index list that never visits the host
+    (``fh_tridiag_refine_flagged_c128``).  The solver is
     unpivoted, so a pivot that cancels to 1e-5 of its scale costs five digits of backward error (seen for ~1 in 10^4
     wavenumbers of a fine sweep); one refinement step restores it.  Returns the number of refined systems; reading it
-    is the only host synchronisation (``sync=False`` skips it and returns None: at most as many systems as the
-    workspace holds -- batch/16 by default -- are then refined; ``ws``: a caller-owned workspace)."""
+    is the only host synchronisation (``sync=False`` skips it and returns None; ``ws``: a caller-owned workspace --
+    since round 2 it holds the index list only, so every flagged system is refined by one call)."""
     lib = _lib.require_cuda()
     batch, n = d.shape
     if n > lib.fh_tridiag_batched_max_n():

@@ -273,10 +273,12 @@ FH_API int fh_tridiag_residual_vector_c128(const fh_c128 *dl, const fh_c128 *d, 
 
 /* Selective iterative refinement on the device (keeps np.linalg.solve's accuracy, nb:204, on the unpivoted fast path):
  * every system whose status carries FH_STATUS_SMALL_PIVOT (2, set by fh_tridiag_solve_batched_c128) gets one step
- * r = b - A u, A e = r, u += e; the flag is cleared, a non-finite correction sets FH_STATUS_NONFINITE (1).  No host
- * synchronisation: the list of flagged systems is built and consumed on the device.  One call refines at most as many
- * systems as the workspace was sized for (max_systems); on return the first two int32 of the workspace hold
- * {flagged, refined}: call again while flagged > refined.  n <= fh_tridiag_batched_max_n(). */
+ * r = b - A u, A e = r, u += e; the flag is cleared, a correction solve that breaks down sets FH_STATUS_NONFINITE (1).
+ * No host synchronisation: the list of flagged systems is built and consumed on the device, and the step itself is ONE
+ * pass over the flagged systems (the residual is formed while the rows are read, the correction is added to u by a TMA
+ * reduce-add: 96 bytes of traffic per refined row).  The workspace holds the list only (8 + 4 * batch bytes, rounded);
+ * max_systems is accepted for compatibility and ignored -- every flagged system is refined by one call.  On return the
+ * first two int32 of the workspace hold {flagged, refined}.  n <= fh_tridiag_batched_max_n(). */
 FH_API size_t fh_tridiag_refine_flagged_workspace_bytes(int64_t n, int64_t batch, int64_t max_systems);
 FH_API int fh_tridiag_refine_flagged_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c128 *du, const fh_c128 *b,
                                    fh_c128 *u, int64_t n, int64_t batch, int32_t *status, void *workspace,

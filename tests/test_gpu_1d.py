@@ -197,6 +197,17 @@ def test_device_side_refinement_of_flagged_subset(n, batch):
     res = fh.tridiagonal_residual(*tens, u_bad)["backward"]
     assert res.max() < 1e-15, res.max()                       # one step repairs a 1e-6 perturbation
     assert rel_err(_np(u_bad), _np(u)) < 1e-12
+    # the one-pass refinement kernel (residual formed while the rows are read, correction added by a TMA reduce-add)
+    # gives the bits of the step spelled out through the C ABI: r = b - A u, A e = r, u + e
+    from fem_helmholtz_eqn_b200 import _lib
+    from fem_helmholtz_eqn_b200._lib import ptr, stream_ptr
+    lib = _lib.require_cuda()
+    r = torch.empty_like(u_ref)
+    assert lib.fh_tridiag_residual_vector_c128(*(ptr(t) for t in tens), ptr(u_ref), n, batch, ptr(r), stream_ptr()) == 0
+    e, st_e = fh.solve_tridiagonal(tens[0], tens[1], tens[2], r, refine=False)
+    assert int((st_e & 1).sum()) == 0
+    fl = torch.as_tensor(flagged, device="cuda")
+    assert torch.equal(u_bad[fl], (u_ref + e)[fl])
 
 
 def test_solver_is_deterministic_run_to_run():
