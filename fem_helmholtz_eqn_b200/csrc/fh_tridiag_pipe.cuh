@@ -725,7 +725,12 @@ tridiag_pipe_kernel(const __grid_constant__ TensorMaps maps, const __grid_consta
             // dependence on the other roles: the stores run ahead of the solves and fill the write bandwidth the
             // latency-bound solver phases leave idle.  (Round 2 first sent tiles of identical rows by TMA stores: they
             // queued in front of the solution store in the SM's one bulk-copy queue, and the E/B warps waited ~5,000
-            // cycles per system for their solution tile to come free.)  Values = fh_assemble_1d_c128's, bit for bit.
+            // cycles per system for their solution tile to come free.  A second attempt paced the queue -- one warp
+            // filling [row 0 | 512 interior rows | row N] tiles and sending contiguous 8 KB bulk copies, at most 3 .. 15
+            // of them pending: the interface warps, whose shared-memory traffic no longer shared the LSU with 1,024 store
+            // instructions per system, ran their PCR levels in 480 instead of 800 cycles, but the bulk-copy engine of an
+            // SM moved no more than ~18 B/cycle: 4.05 ms against 3.68, whatever the queue depth; two bands each way
+            // 3.76 ms.)  Values = fh_assemble_1d_c128's, bit for bit.
             const int ts = t - (kEBThreads + kIThreads);
             const HostMap hm = host_map(n, CLUSTER);
             const int64_t lo = rank == 0 ? 0 : hm.n_loc[0] + hm.cut;                 // first row this CTA writes ...
