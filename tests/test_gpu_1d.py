@@ -166,12 +166,13 @@ def test_random_systems_all_kernel_shapes(n):
     assert res["backward"].max() < 1e-15
 
 
-@pytest.mark.parametrize("n,batch", [(9, 40), (1000, 37), (2057, 21), (3001, 12), (4097, 9), (4112, 7), (300, 600)])
+@pytest.mark.parametrize("n,batch", [(1, 5), (2, 10), (5, 30), (8, 30), (9, 40), (1000, 37), (2056, 11), (2057, 21), (3001, 12), (4096, 9),
+                                     (4097, 9), (4112, 7), (300, 600)])
 def test_device_side_refinement_of_flagged_subset(n, batch):
     """fh_tridiag_refine_flagged_c128: exactly the systems flagged FH_STATUS_SMALL_PIVOT get one refinement step (their
     matrices are read in place through a device-built index list); the others are not touched (bit-for-bit).  Covers
-    the single-CTA kernel, cut rows (odd n), head rows (4112) and a batch that needs several calls (600 flagged systems
-    against a workspace for 256)."""
+    systems of head rows only (n < 8), the single-CTA kernel, even / odd halves (cut rows), head rows (2056, 4112) and
+    a batch in which every system is flagged."""
     rng = np.random.default_rng(1000 * n + batch)
     sh = (batch, n)
     dl = rng.normal(size=sh) + 1j * rng.normal(size=sh)
