@@ -66,6 +66,8 @@ _SIGNATURES = {
     "fh_helmholtz1d_solve_large_fused_c128": (C.c_int, [C.POINTER(Problem1d), C.c_double, C.c_double, _P, _P, _P,
                                                         C.c_size_t, _P]),
     "fh_helmholtz1d_solve_large_fused_kdev_c128": (C.c_int, [C.POINTER(Problem1d), _P, _P, _P, _P, C.c_size_t, _P]),
+    "fh_helmholtz1d_assemble_solve_large_c128": (C.c_int, [C.POINTER(Problem1d), C.c_double, C.c_double, _P, _P, _P, _P,
+                                                           _P, _P, _P, _P, C.c_size_t, _P]),
     "fh_large_uniform_plan": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, _P, C.c_int]),
     "fh_spike_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "fh_spike_reduce_c128": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, _P, C.c_size_t, _P, _P]),

@@ -497,17 +497,32 @@ def assemble_and_solve(N, ks, L=1.0, theta=0.0, *, bc_left="neumann", bc_right="
     ks_h, k2s_h = ks if isinstance(ks, tuple) else _host_k_and_k2(ks)[:2]  # tuple = (ks, k2s) already split
     n_k, n = len(ks_h), int(N) + 1
     dev = _lib.device()
-    if n > lib.fh_tridiag_batched_max_n() or N < 2:
+    if N < 2:
         bands = assemble_bands(N, (ks_h, k2s_h), L / N, theta, bc_left=bc_left, bc_right=bc_right, g_left=g_left,
                                g_right=g_right, out=out_bands)
         U, status = solve_tridiagonal(*bands, out=out, refine=refine)
         return bands, U, status
-    ks_d, k2s_d = _lib.as_device(ks_h, torch.float64), _lib.as_device(k2s_h, torch.float64)
     B = out_bands if out_bands is not None else torch.empty((4, n_k, n), dtype=torch.complex128, device=dev)
     assert B.shape == (4, n_k, n) and B.dtype == torch.complex128 and B.is_contiguous()
     U = out if out is not None else torch.empty((n_k, n), dtype=torch.complex128, device=dev)
     status = torch.empty(n_k, dtype=torch.int32, device=dev)
     prob = _problem(N, L / N, theta, bc_left, bc_right, g_left, g_right, None)
+    if n > lib.fh_tridiag_batched_max_n():
+        # long meshes, one system at a time: the first reduction level of the recursive-partition solver writes the
+        # bands (fh_helmholtz1d_assemble_solve_large_c128: same bits as assembly + solve, 162 instead of 226 B per row)
+        nbytes = lib.fh_tridiag_solve_large_workspace_bytes(n)
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        for i in range(n_k):
+            check(lib.fh_helmholtz1d_assemble_solve_large_c128(
+                C.byref(prob), float(ks_h[i]), float(k2s_h[i]), None, ptr(B[0][i]), ptr(B[1][i]), ptr(B[2][i]),
+                ptr(B[3][i]), ptr(U[i]), ptr(status[i:i + 1]), ptr(ws), nbytes, stream_ptr()),
+                "fh_helmholtz1d_assemble_solve_large_c128")
+        bands = (B[0], B[1], B[2], B[3])
+        if refine:
+            refine_flagged(*bands, U, status)
+            repair_flagged(*bands, U, status, sync=False)
+        return bands, U, status
+    ks_d, k2s_d = _lib.as_device(ks_h, torch.float64), _lib.as_device(k2s_h, torch.float64)
     check(lib.fh_helmholtz1d_sweep_assemble_solve_c128(C.byref(prob), ptr(ks_d), ptr(k2s_d), n_k, ptr(B[0]), ptr(B[1]),
                                                        ptr(B[2]), ptr(B[3]), ptr(U), ptr(status), None, 0, stream_ptr()),
           "fh_helmholtz1d_sweep_assemble_solve_c128")
@@ -545,8 +560,9 @@ class _WavenumberFeed:
 
 class LargeMeshPlan:
     """One long mesh, many solves (BASELINE configs 2 and 5: N = 10^6, a new wavenumber per call).  At that size the
-    work is 0.15 GB -- tens of microseconds of HBM time -- and the path is bound by its nine dependent kernel launches
-    (assembly, three reduction levels, the coarse cluster solve, three back-substitution levels).  The plan owns the
+    work is 0.16 GB -- tens of microseconds of HBM time -- and the path is bound by its eight dependent kernel launches
+    (three reduction levels, the first of which also writes the bands of A; the coarse cluster solve; three
+    back-substitution levels).  The plan owns the
     buffers and a captured CUDA graph of the whole sequence; ``solve(k)`` updates (k, k**2) in device memory and
     replays it.  Results are bit-identical to ``solve_helmholtz_sweep(N, [k])``.
 
@@ -593,6 +609,11 @@ class LargeMeshPlan:
                                                                  ptr(self.status), ptr(self.ws), self.ws.numel(),
                                                                  stream_ptr()),
                   "fh_helmholtz1d_solve_large_fused_kdev_c128")
+            return
+        if self.n > lib.fh_tridiag_batched_max_n():  # A written by the first reduction level of the solver
+            check(lib.fh_helmholtz1d_assemble_solve_large_c128(
+                C.byref(self._prob), 0.0, 0.0, ptr(self.k_dev), ptr(B[0]), ptr(B[1]), ptr(B[2]), ptr(B[3]), ptr(self.U),
+                ptr(self.status), ptr(self.ws), self.ws.numel(), stream_ptr()), "fh_helmholtz1d_assemble_solve_large_c128")
             return
         check(lib.fh_assemble_1d_c128(C.byref(self._prob), ptr(self.k_dev[0:1]), ptr(self.k_dev[1:2]), 1, ptr(B[0]),
                                       ptr(B[1]), ptr(B[2]), ptr(B[3]), stream_ptr()), "fh_assemble_1d_c128")

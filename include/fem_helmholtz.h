@@ -159,6 +159,17 @@ FH_API int fh_helmholtz1d_solve_large_fused_kdev_c128(const fh_problem1d *prob_h
                                                int32_t *status, void *workspace, size_t workspace_bytes,
                                                fh_stream_t stream);
 
+/* assembly() + np.linalg.solve() (nb:134-187, nb:204) for ONE long mesh (n_elem + 1 > fh_tridiag_batched_max_n()) in
+ * one pass that KEEPS A: the first reduction level generates the rows, stores them as the bands fh_assemble_1d_c128
+ * would have stored (bit for bit) and reduces them; the rest is fh_tridiag_solve_large_c128's, so dl/d/du/b and u hold
+ * exactly what the two calls would have produced, for 162 instead of 226 bytes of traffic per row.
+ * k_k2_dev != NULL: (k, k**2) are read from device memory (then k, k2 are ignored), so that a captured CUDA graph serves
+ * every wavenumber.  workspace: fh_tridiag_solve_large_workspace_bytes(n_elem + 1).  status as fh_tridiag_solve_large_c128. */
+FH_API int fh_helmholtz1d_assemble_solve_large_c128(const fh_problem1d *prob_host, double k, double k2,
+                                             const double *k_k2_dev, fh_c128 *dl, fh_c128 *d, fh_c128 *du, fh_c128 *b,
+                                             fh_c128 *u, int32_t *status, void *workspace, size_t workspace_bytes,
+                                             fh_stream_t stream);
+
 /* ---- multi-GPU SPIKE-style partitioned solve (single mesh split into contiguous slabs, one per rank) ------
  * Per rank:  1. *_spike_reduce   : slab [row_begin, row_begin+n_rows) -> its 2 interface rows,
  *                                  iface8 = device complex128[4][2] = (dl, d, du, b) x (first row, last row);

@@ -425,6 +425,26 @@ def test_large_mesh_plan_replays_a_cuda_graph_bit_identically():
     assert torch.equal(eager.solve(10.0), plan.solve(10.0))
 
 
+@pytest.mark.parametrize("bc", [{}, {"bc_left": "dirichlet", "bc_right": "dirichlet", "g_right": 0.5}])
+def test_one_pass_assemble_and_solve_on_a_long_mesh_keeps_identical_bands(bc):
+    """fh_helmholtz1d_assemble_solve_large_c128 (behind assemble_and_solve and LargeMeshPlan for n > 4112): the first
+    reduction level of the recursive-partition solver writes the bands -- bit for bit those of fh_assemble_1d_c128 --
+    and the solution is that of the two-call sequence, status included."""
+    N, ks = 150_001, [10.0, 777.5]
+    bands, U, status = fh.assemble_and_solve(N, ks, refine=False, **bc)
+    ref = fh.assemble_bands(N, ks, 1.0 / N, **bc)
+    for got, want in zip(bands, ref):
+        assert torch.equal(got, want)
+    U2, st2 = fh.solve_tridiagonal(*ref, refine=False)
+    assert torch.equal(U, U2) and torch.equal(status, st2)
+    plan = fh.fem1d.LargeMeshPlan(N, **bc)
+    assert torch.equal(plan.solve(777.5), U[1])
+    for got, want in zip(plan.bands, ref):
+        assert torch.equal(got[0], want[1])
+    res = fh.tridiagonal_residual(*ref, U)["backward"]
+    assert res.max() < 1e-15
+
+
 def test_fused_plans_replay_a_cuda_graph_with_the_wavenumber_in_device_memory():
     """LargeMeshPlan(fused=True) and distributed.PartitionedPlan (one rank): the *_kdev entry points read (k, k**2)
     from device memory, so one captured graph serves every wavenumber -- same bits as the by-value calls."""
