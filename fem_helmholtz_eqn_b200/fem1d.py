@@ -413,13 +413,13 @@ PIPELINES = ("staged", "one_pass", "fused")
 
 def _pick_pipeline(pipeline, fused, N, nodal_h):
     """``pipeline=None`` -> "fused" if the legacy ``fused=True`` switch is set, else the default: the one-pass kernel
-    (A written once, solved from registers: same bits as the staged pair, 80 instead of 144 B/DOF of traffic) wherever
-    it applies -- uniform meshes of 3 .. fh_tridiag_batched_max_n() nodes --, the staged pair elsewhere."""
+    (A written once, solved from registers: same bits as the staged pair, 80 instead of 144 B/DOF of traffic; meshes
+    beyond fh_tridiag_batched_max_n() nodes: A written by the first reduction level of the recursive-partition solver,
+    162 instead of 226 B/DOF) wherever it applies -- uniform meshes of 3 nodes or more --, the staged pair elsewhere."""
     if pipeline is None:
         pipeline = "fused" if fused else "auto"
     if pipeline == "auto":
-        ok = (not nodal_h) and int(N) >= 2 and int(N) + 1 <= _lib.load().fh_tridiag_batched_max_n()
-        pipeline = "one_pass" if ok else "staged"
+        pipeline = "one_pass" if (not nodal_h) and int(N) >= 2 else "staged"
     if pipeline not in PIPELINES:
         raise ValueError(f"pipeline must be one of {PIPELINES} (or None / 'auto'), got {pipeline!r}")
     return pipeline
@@ -444,7 +444,7 @@ def solve_helmholtz_sweep(N, ks, L=1.0, theta=0.0, *, bc_left="neumann", bc_righ
     pipeline = _pick_pipeline(pipeline, fused, N, nodal_h)
     fused = pipeline == "fused"
     nodes_d = _lib.as_device(nodes, torch.float64) if nodal_h else None
-    if pipeline == "one_pass" and (nodal_h or N < 2 or n > lib.fh_tridiag_batched_max_n()):
+    if pipeline == "one_pass" and (nodal_h or N < 2):
         pipeline = "staged"
     if pipeline == "one_pass":
         _, U, status = assemble_and_solve(N, (ks_h, k2s_h), L, theta, bc_left=bc_left, bc_right=bc_right, g_left=g_left,
@@ -491,8 +491,9 @@ def assemble_and_solve(N, ks, L=1.0, theta=0.0, *, bc_left="neumann", bc_right="
     """``A, b = assembly(...)`` followed by ``u = np.linalg.solve(A, b)`` (nb:203-204) for every wavenumber in ``ks``, in
     ONE pass: the kernel generates the rows, stores them as the bands ``assemble_bands`` would have stored (bit for
     bit) and solves from its registers, so ``A`` is written once and never read back.  Returns
-    ``((dl, d, du, b), U, status)`` -- CUDA tensors complex128[n_k, N+1].  Uniform meshes up to the batched solver's
-    size; longer or non-uniform meshes take the two-kernel path."""
+    ``((dl, d, du, b), U, status)`` -- CUDA tensors complex128[n_k, N+1].  Meshes beyond the batched solver's size are
+    taken one system at a time through ``fh_helmholtz1d_assemble_solve_large_c128`` (the solver's first reduction level
+    writes the bands); meshes of fewer than 2 elements take the two-kernel path."""
     lib = _lib.require_cuda()
     ks_h, k2s_h = ks if isinstance(ks, tuple) else _host_k_and_k2(ks)[:2]  # tuple = (ks, k2s) already split
     n_k, n = len(ks_h), int(N) + 1

@@ -70,7 +70,8 @@ def test_round2_entry_points_validate_their_arguments_without_gpu():
 def test_pipeline_choice_is_host_logic():
     from fem_helmholtz_eqn_b200 import fem1d
     assert fem1d._pick_pipeline(None, False, 4096, False) == "one_pass"      # uniform mesh within the batched size
-    assert fem1d._pick_pipeline(None, False, 4112, False) == "staged"        # 4113 nodes: too long for the one-pass kernel
+    assert fem1d._pick_pipeline(None, False, 4112, False) == "one_pass"      # 4113 nodes: the long-mesh one-pass solver
+    assert fem1d._pick_pipeline(None, False, 1, False) == "staged"           # a single element: the two-kernel path
     assert fem1d._pick_pipeline(None, False, 4096, True) == "staged"         # non-uniform mesh
     assert fem1d._pick_pipeline(None, True, 4096, False) == "fused"          # the legacy switch
     assert fem1d._pick_pipeline("staged", True, 4096, False) == "staged"     # an explicit choice wins
