@@ -39,8 +39,10 @@ constexpr uint32_t kParkStride = 128;            // columns between a thread's t
 static_assert(kParkCols == 100 && kParkCols <= (int)kParkStride, "parking layout");
 
 enum : int { kBarEB = 1, kBarI = 2, kBarFullReady = 3, kBarFullFree = 4, kBarX0 = 5, kBarX1 = 6, kBarS = 7 };
-constexpr int kRegsEB = 200, kRegsI = 96;                      // 256 * 200 + 128 * 96 <= 384 * 168 (208 / 96 = all 64 K
-                                                               // registers: setmaxnreg.inc never returns -- measured)
+constexpr int kRegsEB = 200, kRegsI = 96;                      // 256 * 200 + 128 * 96 <= 384 * 168 = what the CTA was
+                                                               // launched with: the pool setmaxnreg re-distributes (a
+                                                               // budget that sums to more, e.g. 208 / 96, makes
+                                                               // setmaxnreg.inc wait for ever -- measured)
 constexpr int kRegsEB1 = 184, kRegsI1 = 88, kRegsS1 = 56;      // 256 * 184 + 128 * 88 + 128 * 56 = 512 * 128
 
 // PCR arrays of the I group: kH rows each, kHalfPad zero rows before and after (the largest PCR stride); the pad behind
