@@ -411,7 +411,19 @@ def run_gpu(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner on stdout when the communicator comes up (NCCL_DEBUG=VERSION on some boxes): the
+        # contract is ONE JSON line on stdout, so stdout points at stderr until the first collective has run
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     lib = fh._lib.require_cuda()
     dev = torch.device("cuda", local_rank)
 
