@@ -1,0 +1,55 @@
+"""Randomised parity of the 1D path (fixed seeds): mesh sizes across every kernel shape (single CTA, cluster of two, head
+rows, long meshes), wavenumbers from 0.1 to 20 points per wavelength and beyond, all boundary-row variants, all three
+pipelines.  Gates: bands bit-exact against the CPU oracle's (nb:134-187 restated in oracle/banded1d.py), the three
+pipelines bit-identical to each other, normwise backward error <= 1e-13 (north-star bar 1e-10), forward error against
+LAPACK zgtsv within what cond(A) allows."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import banded1d
+
+pytestmark = pytest.mark.gpu
+
+fh = pytest.importorskip("fem_helmholtz_eqn_b200")
+
+BCS = [{}, dict(bc_left="dirichlet", bc_right="dirichlet", g_left=1.0, g_right=0.0),
+       dict(bc_left="dirichlet", bc_right="sommerfeld", g_left=0.5), dict(bc_left="neumann", bc_right="dirichlet", g_right=-0.25)]
+
+
+def _cases(seed, count):
+    rng = np.random.default_rng(seed)
+    sizes = [2, 3, 7, 8, 9, 15, 16, 17, 63, 64, 65, 255, 1000, 2047, 2048, 2055, 2056, 2057, 3000, 4095, 4096, 4111, 4112, 4113,
+             5000, 20011]
+    out = []
+    for _ in range(count):
+        N = int(rng.choice(sizes)) if rng.random() < 0.7 else int(rng.integers(2, 6000))
+        L = float(rng.choice([1.0, 2.0, 0.37]))
+        ppw = float(rng.choice([4.0, 10.0, 25.0, 100.0, 1e4]))            # points per wavelength
+        kmax = 2 * np.pi * N / (L * ppw)
+        ks = np.sort(rng.uniform(0.05 * kmax, kmax, size=int(rng.integers(1, 7))))
+        out.append((N, L, ks, BCS[int(rng.integers(0, len(BCS)))], float(rng.uniform(-0.4, 0.4))))
+    return out
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_random_meshes_wavenumbers_and_boundary_rows(seed):
+    for N, L, ks, bc, theta in _cases(seed, 14):
+        tag = (N, L, list(ks), bc, theta)
+        _, U1, st1 = fh.solve_helmholtz_sweep(N, ks, L, theta, pipeline="staged", return_status=True, check_singular=False, **bc)
+        _, U2, st2 = fh.solve_helmholtz_sweep(N, ks, L, theta, pipeline="one_pass", return_status=True, check_singular=False, **bc)
+        _, U3, st3 = fh.solve_helmholtz_sweep(N, ks, L, theta, pipeline="fused", return_status=True, check_singular=False, **bc)
+        assert int(st1.abs().sum()) == 0 and int(st2.abs().sum()) == 0 and int(st3.abs().sum()) == 0, tag
+        assert torch.equal(U1, U2), tag                       # same bands, same arithmetic: identical bits
+        bands, _, _ = fh.assemble_and_solve(N, ks, L, theta, refine=False, **bc)
+        for i, k in enumerate(ks):
+            ref = banded1d.assemble_bands(N, float(k), L / N, theta, **bc)
+            for got, want in zip(bands, ref):
+                assert np.array_equal(got[i].cpu().numpy(), want), tag
+            for U in (U1, U3):
+                u = U[i].cpu().numpy()
+                be, _ = banded1d.residual_metrics(*ref, u)
+                assert be < 1e-13, (tag, i, be)
+            if bc.get("bc_right", "sommerfeld") == "sommerfeld":  # absorbing end: well conditioned, forward error gated too
+                assert rel_err(U1[i].cpu().numpy(), banded1d.solve_bands(*ref)) < 1e-7, (tag, i)
