@@ -437,7 +437,7 @@ def run_gpu(args):
     if os.environ.get("FH_BENCH_EMULATE_SHARD"):  # development: the wavenumbers of rank R of a W-rank job, on one GPU
         w_, r_ = (int(v) for v in os.environ["FH_BENCH_EMULATE_SHARD"].split(","))
         ks_h = np.ascontiguousarray(np.linspace(K_MIN, K_MAX, n_k * w_)[r_::w_])
-    k2s_h = ks_h**2
+    k2s_h = fem1d.squares_like_the_reference(ks_h)  # nb:185: k**2 of a scalar = libm pow, not the rounded square
     ks_d = torch.from_numpy(ks_h).to(dev)
     k2s_d = torch.from_numpy(k2s_h).to(dev)
     bands = torch.empty((4, n_k, n), dtype=torch.complex128, device=dev)

@@ -80,16 +80,31 @@ def boundary_matrices(h, k, theta=0.0):
 # ------------------------------------------------------------------------------------------------
 # helpers
 # ------------------------------------------------------------------------------------------------
+def squares_like_the_reference(ks):
+    """``k**2`` for every entry of a float64 array, evaluated the way the reference evaluates it (nb:185: ``k`` is a Python
+    or numpy SCALAR there, one wavenumber per call, so ``k**2`` is libm's ``pow(k, 2.0)``).  That is not always the
+    correctly rounded square: ``ks**2`` / ``ks*ks`` of an array differ from it by one ulp for about one wavenumber in a
+    thousand (64 of the 65,536 of BASELINE config 3), and with them the assembled diagonals -- found by the randomised
+    parity test.  ``np.float_power`` goes through libm's pow element by element (0.9 ms for 65,536 values); a sample is
+    checked against CPython's own ``**`` and the loop over scalars is the fallback."""
+    ks = np.ascontiguousarray(ks, dtype=np.float64).ravel()
+    out = np.float_power(ks, 2.0)
+    probe = np.unique(np.linspace(0, max(len(ks) - 1, 0), num=min(len(ks), 64)).astype(np.int64)) if len(ks) else []
+    if any(float(ks[i]) ** 2 != out[i] for i in probe):
+        out = np.array([float(v) ** 2 for v in ks], dtype=np.float64)
+    return out
+
+
 def _host_k_and_k2(k):
-    """Return (ks fp64[n_k], k2s fp64[n_k], scalar?) with k**2 evaluated on the host the way
-    nb:185 does (``k**2`` of a Python number goes through CPython's pow, of an array through numpy)."""
+    """Return (ks fp64[n_k], k2s fp64[n_k], scalar?) with k**2 evaluated on the host the way nb:185 does: entry by
+    entry as a scalar power (:func:`squares_like_the_reference`), whatever container the wavenumbers come in."""
     if isinstance(k, torch.Tensor):
         k = k.detach().cpu().numpy()
     if np.isscalar(k) or (isinstance(k, np.ndarray) and k.ndim == 0):
         return np.array([float(k)]), np.array([float(k**2)]), True
     if isinstance(k, np.ndarray):
         ks = np.ascontiguousarray(k, dtype=np.float64).ravel()
-        return ks, ks**2, False
+        return ks, squares_like_the_reference(ks), False
     ks = list(k)
     return (np.array([float(v) for v in ks], dtype=np.float64),
             np.array([float(v**2) for v in ks], dtype=np.float64), False)

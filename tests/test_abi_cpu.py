@@ -79,6 +79,24 @@ def test_pipeline_choice_is_host_logic():
         fem1d._pick_pipeline("fastest", False, 4096, False)
 
 
+def test_wavenumber_squares_follow_the_reference_scalar_power():
+    """nb:185 evaluates ``k**2`` on a scalar: libm's pow, which is not always the correctly rounded square.  The sweep
+    entry points take arrays of wavenumbers and must square them the same way (one ulp of k**2 is one ulp of every
+    assembled diagonal): k = 1252.1780850687405 is a wavenumber where the two differ."""
+    import torch
+    from fem_helmholtz_eqn_b200 import fem1d
+    k = 1252.1780850687405
+    assert (k ** 2).hex() == "0x1.7eccdf4ec05c5p+20" and (k * k).hex() == "0x1.7eccdf4ec05c4p+20"
+    rng = np.random.default_rng(5)
+    ks = np.concatenate([[k], rng.uniform(0.1, 2000.0, 20000), np.linspace(1.0, 1000.0, 65536)])
+    want = np.array([float(v) ** 2 for v in ks])
+    assert np.array_equal(fem1d.squares_like_the_reference(ks), want)
+    assert int((want != ks * ks).sum()) > 0                   # (the distinction is real on this platform)
+    for container in (ks[:50], list(ks[:50]), torch.from_numpy(ks[:50].copy())):
+        assert np.array_equal(fem1d._host_k_and_k2(container)[1], want[:50])
+    assert fem1d._host_k_and_k2(k)[1][0] == k ** 2 and fem1d._host_k_and_k2(np.float64(k))[1][0] == k ** 2
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
