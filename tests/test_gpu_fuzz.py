@@ -57,3 +57,50 @@ def test_random_meshes_wavenumbers_and_boundary_rows(seed):
                 assert be < (1e-13 if absorbing else 1e-12), (tag, i, be)
             if absorbing:  # well conditioned: forward error gated too
                 assert rel_err(U1[i].cpu().numpy(), banded1d.solve_bands(*ref)) < 1e-7, (tag, i)
+
+
+def _permuted_oracle_mesh(ref2d, n_r, n_t, ri, ro, perm):
+    """The oracle's mesh namespace on a re-numbered mesh, boundary lists by the reference's own rules (helmholtz.py:95-118)."""
+    m = ref2d.structured_annulus(n_r, n_t, ri, ro)
+    inv = np.argsort(perm)
+    m.nodes, m.elements = m.nodes[perm], inv[m.elements]
+    dist = np.linalg.norm(m.nodes, axis=1)
+    m.inner_boundary_node_indices = np.where(np.isclose(dist, ri, atol=1e-5))[0]
+    m.outer_boundary_node_indices = np.where(np.isclose(dist, ro, atol=1e-5))[0]
+    ins, outs = set(m.inner_boundary_node_indices.tolist()), set(m.outer_boundary_node_indices.tolist())
+    m.inner_boundary_element_indices = [e for e, c in enumerate(m.elements) if ins.intersection(c.tolist())]
+    m.outer_boundary_element_indices = [e for e, c in enumerate(m.elements) if outs.intersection(c.tolist())]
+    return m
+
+
+@pytest.mark.parametrize("seed", [3, 4])
+def test_random_annuli_against_the_2d_oracle(seed):
+    """The four 2D classes on random annuli (radii, mesh sizes down to one ring of three quads, k**2, Fourier terms, ABC
+    orders, every third mesh with a scrambled numbering) against oracle/ref2d.py, the restatement of src/solvers pinned by
+    tests/golden: pattern and values of K and F bit-exact, solutions within 1e-9."""
+    from fem_helmholtz_eqn_b200.helmholtz import HelmHoltz
+    from fem_helmholtz_eqn_b200.utils import get_solver
+    from oracle import ref2d
+    rng = np.random.default_rng(seed)
+    for trial in range(12):
+        n_r, n_t = int(rng.integers(1, 9)), int(rng.integers(3, 40))
+        ri = float(rng.choice([1.0, 0.5, 2.0]))
+        ro = ri * float(rng.uniform(1.2, 2.5))
+        k2, nf, order = float(rng.uniform(0.5, 60.0)), int(rng.integers(1, 5)), int(rng.integers(0, 4))
+        kind = ref2d.SOLVER_KINDS[trial % 4]
+        perm = rng.permutation((n_r + 1) * n_t) if trial % 3 == 0 else np.arange((n_r + 1) * n_t)
+        m = _permuted_oracle_mesh(ref2d, n_r, n_t, ri, ro, perm)
+        tag = (seed, trial, kind, n_r, n_t, ri, ro, k2, nf, order)
+        Kpre, Fpre = ref2d.assemble(kind, m, k2, nf, order)
+        ur, ui, _, _ = ref2d.solve(kind, m, k2, nf, order, ri, ro)
+        s = get_solver(kind, HelmHoltz.from_arrays(m.nodes, m.elements, ri, ro), k_squared=k2, n_fourier=nf, abc_order=order,
+                       inner_radius=ri, outer_radius=ro)
+        s.assemble()
+        r, c, v = s.K.coo()
+        keep = v != 0
+        order_ = np.lexsort((c[keep], r[keep]))
+        r0, c0 = np.nonzero(Kpre)
+        assert np.array_equal(r[keep][order_], r0) and np.array_equal(c[keep][order_], c0), tag
+        assert np.array_equal(v[keep][order_], Kpre[r0, c0]) and np.array_equal(s.F, Fpre), tag
+        gr, gi = s.solve()
+        assert rel_err(gr + 1j * gi, ur + 1j * ui) < 1e-9, tag
