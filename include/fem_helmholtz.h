@@ -79,7 +79,9 @@ FH_API int fh_element_matrices_1d(double h, double xi, double w, double *Ke4, do
 FH_API int fh_boundary_matrices_1d(double k, double cos_theta, fh_c128 *Ne2, fh_c128 *Se4, fh_stream_t stream);
 
 /* ---- assembly (replaces nb:134-187 `assembly`): A = -K + k^2 M + S as tridiagonal bands ---------
- * ks / k2s: device fp64[n_k]; k2s[i] must be the caller's k**2 (nb:185 evaluates it on the host).
+ * ks / k2s: device fp64[n_k]; k2s[i] must be the caller's k**2 (nb:185 evaluates it on the host -- on a SCALAR k, i.e.
+ * libm's pow(k, 2.0), which differs from the correctly rounded k*k by one ulp for about one k in a thousand: square the
+ * wavenumbers of a sweep one by one, as the reference's loop nb:300-317 does, not as an array).
  * dl, d, du, b: device complex128[n_k][N+1].  Values are bit-identical to the reference's dense A.
  * fh_assemble_1d_c128 allocates nothing and needs no scratch.  On a non-uniform mesh (FH_H_NODAL) with many wavenumbers
  * fh_assemble_1d_ws_c128 is faster (0.97 instead of 0.63 of the HBM write peak): the k-independent geometry of the rows
