@@ -103,6 +103,19 @@ def test_sparse_band_solver_matches_dense_and_numpy(kind):
     assert rel_err(ur + 1j * ui, dr + 1j * di) < 1e-12
 
 
+def test_sparse_band_solver_on_a_cluster_of_ctas_at_4920_nodes():
+    """The banded LU shares its update window over a cluster of CTAs when the window is large (kl (kl + ku) >= 4096):
+    a 120 x 40 annulus (4,920 nodes, bandwidth 239) against the residual of the reference's dense K."""
+    eqn = HelmHoltz(inner_radius=1.0, outer_radius=1.5, n_theta=120, n_r=40, mesher="structured")
+    s = get_solver("dirichlet_sommerfeld", eqn, k_squared=30.25)
+    ur, ui = s.solve()
+    _, kl, ku = s._band_plan()
+    assert kl * (kl + ku) >= 4096
+    K, u = np.asarray(s.K), ur + 1j * ui
+    r = K @ u - s.F
+    assert np.linalg.norm(r) / (np.linalg.norm(K, np.inf) * np.linalg.norm(u) + np.linalg.norm(s.F)) < 1e-15
+
+
 def test_sparse_band_solver_reorders_a_scrambled_mesh():
     """An unstructured numbering (what gmsh hands out) has a band as wide as the matrix: the solver falls back on a
     reverse Cuthill-McKee ordering of the pattern and still returns the solution in the caller's numbering."""
