@@ -180,16 +180,32 @@ class BaseSolver(ABC):
             flags = on_edge.cpu().numpy()
             nodes, elements = np.asarray(self.eqn.nodes), np.asarray(self.eqn.elements)
             g = np.zeros((len(ids), 4, 3), dtype=complex)
+            # The Gauss points of the flagged edges, with the reference's scalar arithmetic (fem2d.py:119-123 and the
+            # r, theta of fem2d.py:12-16: `x**2` of a NumPy scalar is libm's pow, not the square an array would take) ...
+            where, rs, thetas = [], [], []
+            shape = [self.get_shape_fuctions_1d(xi) for xi in gp]
             for q, e in enumerate(ids):
                 coords = nodes[elements[e]]
                 for ed, (p0, p1) in enumerate(_EDGES):
                     if not flags[q, ed]:
                         continue
-                    for gi, xi in enumerate(gp):
-                        N = self.get_shape_fuctions_1d(xi)
-                        x = 0.0 + N[0] * coords[p0, 0] + N[1] * coords[p1, 0]   # fem2d.py:119-123, same rounding
+                    for gi, N in enumerate(shape):
+                        x = 0.0 + N[0] * coords[p0, 0] + N[1] * coords[p1, 0]
                         y = 0.0 + N[0] * coords[p0, 1] + N[1] * coords[p1, 1]
-                        g[q, ed, gi] = self.get_normal_derivative(x, y)
+                        where.append((q, ed, gi))
+                        rs.append(np.sqrt(x**2 + y**2))
+                        thetas.append(np.arctan2(y, x))
+            # ... and the Bessel sum of get_normal_derivative over all of them at once: the same operations in the same
+            # order per point (scipy's jvp and NumPy's complex exp are element-wise loops over the scalar routines), a
+            # few array calls instead of (2 n_fourier + 1) scipy calls per point
+            if where:
+                r_a, th_a = np.array(rs, dtype=np.float64), np.array(thetas, dtype=np.float64)
+                k = np.sqrt(self.k_squared)
+                total = np.zeros(len(where), dtype=complex)
+                for m in range(-self.n_fourier, self.n_fourier + 1):
+                    total += (1j**m) * k * jvp(m, k * r_a) * np.exp(1j * m * th_a)
+                idx = np.array(where)
+                g[idx[:, 0], idx[:, 1], idx[:, 2]] = total
             g_d = _lib.as_device(g, torch.complex128)
         Ne = torch.zeros((len(ids), 4), dtype=torch.complex128, device=g_d.device)
         check(lib.fh_q4_neumann_edge_vectors_c128(ptr(on_edge), ptr(length), len(ids), ptr(g_d), gp_p, gw_p, 3, ptr(Ne),
