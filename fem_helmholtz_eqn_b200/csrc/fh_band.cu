@@ -232,21 +232,19 @@ band_lu_cluster_kernel(cplx *__restrict__ AB, cplx *__restrict__ rhs, cplx *__re
             cplx *p = AB + (j + c) * ld + kv - c;  // A(j, j + c); A(j + i, j + c) is i entries further down
             const cplx a0 = ld_cg(p), ajp = ld_cg(p + jp);
             const cplx top = jp != 0 ? ajp : a0;   // A(j, j + c) after the interchange
-            cplx v[4];
+            __syncwarp();  // (p[0] and p[jp] have been read by every lane before their owners overwrite them)
+            for (int i0 = 1; i0 <= km; i0 += 128) {  // 128 rows at a time: four loads in flight per lane, then four stores
+                cplx v[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int i = 1 + lane + 32 * q;
-                if (i <= km) v[q] = i == jp ? a0 : ld_cg(p + i);
-            }
-            __syncwarp();  // (p[jp] has been read by everybody before its owner overwrites it)
+                for (int q = 0; q < 4; ++q) {
+                    const int i = i0 + lane + 32 * q;
+                    if (i <= km) v[q] = i == jp ? a0 : ld_cg(p + i);
+                }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int i = 1 + lane + 32 * q;
-                if (i <= km) p[i] = nmsub(v[q], lcol[i - 1], top);
-            }
-            for (int i = 129 + lane; i <= km; i += 32) {  // (lower bandwidths beyond 128: the rows the registers do not hold)
-                const cplx vi = i == jp ? a0 : ld_cg(p + i);
-                p[i] = nmsub(vi, lcol[i - 1], top);
+                for (int q = 0; q < 4; ++q) {
+                    const int i = i0 + lane + 32 * q;
+                    if (i <= km) p[i] = nmsub(v[q], lcol[i - 1], top);
+                }
             }
             if (lane == 0 && jp != 0) p[0] = top;
         }
