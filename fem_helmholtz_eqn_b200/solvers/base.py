@@ -79,6 +79,27 @@ class BaseSolver(ABC):
         self.outer_radius = outer_radius
         self._dev = None
         self._pattern = {}
+        self._F_dev = self._F_host = self._N_dev = self._N_host = None
+
+    # ``F`` / ``N_global`` are numpy arrays in the reference; here they live on the device and come to the host when
+    # somebody looks at them (a 10^6-node load vector is 6 ms of pageable D2H copy that solve() never needs)
+    @property
+    def F(self):
+        if self._F_host is None and self._F_dev is not None:
+            self._F_host = self._F_dev.cpu().numpy()
+        return self._F_host
+
+    @F.setter
+    def F(self, value):
+        self._F_host = value
+
+    @property
+    def N_global(self):
+        if self._N_host is None:
+            if self._N_dev is None:
+                raise AttributeError("N_global is set by assemble() of the solver classes with a Neumann boundary")
+            self._N_host = self._N_dev.cpu().numpy()
+        return self._N_host
 
     # ------------------------------------------------------------------ reference helpers (host, 4 numbers)
     def get_shape_functions(self, xi, eta):
@@ -285,9 +306,8 @@ class BaseSolver(ABC):
             vpat = self._segments("N", [inner], False)
             sums = self._segment_sum(Ne, vpat)
             F[vpat["ukeys"]] = sums                       # F += N_global  (0 + x == x)
-            self.N_global = F.cpu().numpy().copy()
-        self._F_dev = F
-        self.F = F.cpu().numpy()
+            self._N_dev, self._N_host = F.clone(), None
+        self._F_dev, self._F_host = F, None
 
     @property
     def S(self):
@@ -300,6 +320,22 @@ class BaseSolver(ABC):
             zeros = torch.zeros(n_ke, dtype=Se.dtype, device=Se.device)
             self._S = CsrMatrix(pat["rowptr"], pat["colidx"], self._segment_sum(torch.cat([zeros, Se]), pat), n)
         return self._S
+
+    def _dirichlet_rows_device(self, tol: float = 1e-10):
+        """apply_boundary_conditions(self.K, self.F) without bringing F to the host (what solve() needs)."""
+        lib, m = _lib.require_cuda(), self._device_mesh()
+        flags = torch.zeros(m["n"], dtype=torch.uint8, device=m["nodes"].device)
+        mask = 0
+        for on, radius, bit in ((self._dirichlet_inner, self.inner_radius, 1), (self._dirichlet_outer, self.outer_radius, 2)):
+            if on:
+                check(lib.fh_q4_boundary_flags(ptr(m["nodes"]), m["n"], float(radius), float(tol), bit, ptr(flags),
+                                               stream_ptr()), "fh_q4_boundary_flags")
+                mask |= bit
+        if mask:
+            check(lib.fh_csr_apply_dirichlet_c128(ptr(self.K.rowptr), ptr(self.K.colidx), ptr(self.K.vals), ptr(self._F_dev),
+                                                  ptr(flags), m["n"], mask, 1.0, 0.0, 0.0, 0.0, stream_ptr()),
+                  "fh_csr_apply_dirichlet_c128")
+            self._F_host = None
 
     def apply_boundary_conditions(self, A=None, b=None, tol: float = 1e-10):
         """Dirichlet row replacement (fem2d_dirichlet.py:11-29, fem2d_dirichlet_sommerfeld.py:12-24,
@@ -321,7 +357,7 @@ class BaseSolver(ABC):
             mask |= 2
         own = A is None or A is getattr(self, "K", None)
         A = self.K if A is None else A
-        if b is None or (own and b is self.F):
+        if b is None or (own and b is self._F_host):
             b_dev, b_own = self._F_dev, True
         else:
             b_dev, b_own = _lib.as_device(b, torch.complex128).clone(), False
@@ -332,6 +368,7 @@ class BaseSolver(ABC):
                                                   m["n"], mask, 1.0, 0.0, 0.0, 0.0, stream_ptr()),
                   "fh_csr_apply_dirichlet_c128")
         else:  # a dense matrix from the caller (the reference's type): same rule, rows picked by the device flags
+            b = self.F if b is None else b
             f = flags.cpu().numpy()
             rows = np.nonzero(f & mask)[0]
             A[rows] = 0
@@ -340,10 +377,11 @@ class BaseSolver(ABC):
             b_host = np.array(b, dtype=complex) if not isinstance(b, np.ndarray) else b
             b_host[rows] = g
             return A, b_host
-        out = b_dev.cpu().numpy()
         if b_own:
-            self.F = out
-        elif isinstance(b, np.ndarray):
+            self._F_host = None        # (the device copy changed; the host view is rebuilt on access)
+            return A, self.F
+        out = b_dev.cpu().numpy()
+        if isinstance(b, np.ndarray):
             b[...] = out
             out = b
         return A, out
@@ -420,7 +458,7 @@ class BaseSolver(ABC):
         """``*.solve()``: assemble -> (Dirichlet rows) -> solve -> ``(u_real, u_imag)`` numpy arrays."""
         self.assemble()
         if self._dirichlet_inner or self._dirichlet_outer:
-            self.K, self.F = self.apply_boundary_conditions(self.K, self.F)
+            self._dirichlet_rows_device()
         u = self._solve_device().cpu().numpy()
         return np.real(u), np.imag(u)
 

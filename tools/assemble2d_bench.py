@@ -15,11 +15,14 @@ for nt, nr in ((60, 20), (256, 64), (1024, 256), (2048, 512)):
     t_mesh = time.perf_counter() - t0
     s = get_solver("dirichlet_sommerfeld", eqn, k_squared=30.25)
     s.assemble()                       # symbolic phase (sort, CSR pattern) is cached after the first call
+    s.assemble()                       # (the second call still grows the allocator's pool)
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    s.assemble()
-    torch.cuda.synchronize()
-    t_num = time.perf_counter() - t0
+    t_num = 1e9
+    for _ in range(3):
+        t0 = time.perf_counter()
+        s.assemble()
+        torch.cuda.synchronize()
+        t_num = min(t_num, time.perf_counter() - t0)
     s2 = get_solver("dirichlet_sommerfeld", eqn, k_squared=30.25)
     t0 = time.perf_counter()
     s2.assemble()
