@@ -387,7 +387,10 @@ FH_API int fh_dense_lu_solve_c128(fh_c128 *A, fh_c128 *b, fh_c128 *x, int64_t n,
  * optional node permutation (perm[i] = new index of node i, NULL = identity), factorised with partial pivoting (the
  * pivot rule and elimination order of zgbtf2 / zgesv, i.e. np.linalg.solve's accuracy) and solved; x comes back in the
  * original numbering.  kl / ku = lower / upper bandwidth under the permutation, from fh_csr_bandwidth (klku: device
- * int32[2]).  status: device int32[1], non-zero = singular to working precision. */
+ * int32[2]).  status: device int32[1], non-zero = singular to working precision.  When the update window of a column
+ * step holds 4,096 entries or more (kl (kl + ku)), the elimination is shared by a thread-block cluster of 16 (8) CTAs --
+ * same pivots, same operations per entry; the workspace (fh_band_lu_workspace_bytes) holds the band, the permuted
+ * right-hand side and the reciprocal pivots. */
 FH_API int fh_csr_bandwidth(const int64_t *rowptr, const int32_t *colidx, const int32_t *perm, int64_t n,
                      int32_t *klku, fh_stream_t stream);
 FH_API size_t fh_band_lu_workspace_bytes(int64_t n, int64_t kl, int64_t ku);
