@@ -222,15 +222,13 @@ extern "C" int fh_helmholtz1d_residual_c128(const fh_problem1d *prob_host, doubl
 //   2. the batched solver as tridiag_pipe_kernel<., BandRefineSource> (fh_tridiag_pipe.cuh): the residual is formed
 //      while the rows of system list[i] are read, the correction is added to u by a TMA reduce-add, status bit 1 is
 //      cleared and bit 0 of the correction solve merged in -- 96 B of traffic per refined row.
-// Round 1 / early round 2 ran this as four launches (compaction, residual_subset_kernel into a compact r, the solver
-// on compact r -> e, correct_subset_kernel: 240 B per refined row, 0.32 ms for the 1,732 flagged systems of the
-// 65,536-wavenumber sweep against 0.19 ms now, tools/refine_probe.py); they remain behind the development switch
-// FH_REFINE=staged -- the two give the same bits (tests/test_gpu_1d.py spells the step out through the C ABI).
+// Round 1 / early round 2 ran this as four launches (compaction, a residual kernel into a compact r, the solver on
+// compact r -> e, an update kernel: 240 B per refined row, 0.32 ms for the 1,732 flagged systems of the 65,536-wavenumber
+// sweep against 0.19 ms now, tools/refine_probe.py) -- the same bits (tests/test_gpu_1d.py spells the step out through
+// the C ABI).
 // Launch sizes depend on the batch only; the kernels read the count from device memory.
 namespace fh {
 
-int batched_solve_subset(const cplx *dl, const cplx *d, const cplx *du, const cplx *r, cplx *e, int64_t n, int64_t batch,
-                         const int32_t *list, const int32_t *count, int64_t cap, int32_t *status, cudaStream_t stream);
 int batched_refine_subset(const cplx *dl, const cplx *d, const cplx *du, const cplx *b, cplx *u, int64_t n, int64_t batch,
                           const int32_t *list, const int32_t *count, int64_t cap, int32_t *status, cudaStream_t stream);
 
@@ -302,73 +300,26 @@ compact_flagged_kernel(const int32_t *__restrict__ status, int64_t batch, int32_
     }
 }
 
-__global__ void __launch_bounds__(kResThreads)
-residual_subset_kernel(const cplx *__restrict__ dl, const cplx *__restrict__ d, const cplx *__restrict__ du,
-                       const cplx *__restrict__ b, const cplx *__restrict__ u, int64_t n,
-                       const int32_t *__restrict__ list, const int32_t *__restrict__ header, cplx *__restrict__ r) {
-    const int64_t total = (int64_t)header[1] * n;
-    for (int64_t o = (int64_t)blockIdx.x * kResThreads + threadIdx.x; o < total; o += (int64_t)gridDim.x * kResThreads) {
-        const int64_t i = o / n, j = o - i * n;
-        const int64_t g = (int64_t)list[i] * n + j;
-        cplx v = nmsub(ldg_stream(b + g), ldg_stream(d + g), u[g]);
-        if (j > 0) v = nmsub(v, ldg_stream(dl + g), u[g - 1]);
-        if (j < n - 1) v = nmsub(v, ldg_stream(du + g), u[g + 1]);
-        r[o] = v;
-    }
-}
-
-__global__ void __launch_bounds__(kResThreads)
-correct_subset_kernel(cplx *__restrict__ u, int64_t n, const int32_t *__restrict__ list,
-                      const int32_t *__restrict__ header, const cplx *__restrict__ e,
-                      const int32_t *__restrict__ status_e, int32_t mask, int32_t *__restrict__ status) {
-    const int64_t m = header[1], total = m * n;
-    for (int64_t o = (int64_t)blockIdx.x * kResThreads + threadIdx.x; o < total; o += (int64_t)gridDim.x * kResThreads) {
-        const int64_t i = o / n, j = o - i * n;
-        const int64_t g = (int64_t)list[i] * n + j;
-        u[g] = u[g] + ldg_stream(e + o);
-        if (j == 0) status[list[i]] = (status[list[i]] & ~mask) | (status_e[i] & 1);
-    }
-}
-
-struct RefinePlan {  // carving of the workspace
+struct RefinePlan {  // carving of the workspace: {flagged, refined} + the list of flagged systems
     int64_t cap;
-    size_t off_header, off_list, off_status, off_r, off_e, total;
+    size_t off_header, off_list, total;
 };
-static bool refine_staged() {  // development switch: the four-launch refinement of round 1
-    static const bool v = [] { const char *e = getenv("FH_REFINE"); return e != nullptr && e[0] == 's'; }();
-    return v;
-}
-static RefinePlan refine_plan(int64_t n, int64_t batch, size_t workspace_bytes) {
+static RefinePlan refine_plan(int64_t batch, size_t workspace_bytes) {
     RefinePlan p;
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     p.off_header = 0;
     p.off_list = up(2 * sizeof(int32_t));
-    p.off_status = p.off_list + up(sizeof(int32_t) * (size_t)batch);
-    if (!refine_staged()) {  // one pass: the header and the list are all there is; every flagged system fits
-        p.cap = workspace_bytes >= p.off_status ? batch : 0;
-        p.off_r = p.off_e = p.total = p.off_status;
-        return p;
-    }
-    const size_t fixed = p.off_status + up(sizeof(int32_t) * (size_t)batch);
-    const size_t per_system = 2 * sizeof(cplx) * (size_t)n;
-    int64_t cap = workspace_bytes > fixed ? (int64_t)((workspace_bytes - fixed) / per_system) : 0;
-    if (cap > batch) cap = batch;
-    p.cap = cap;
-    p.off_r = fixed;
-    p.off_e = fixed + sizeof(cplx) * (size_t)n * (size_t)cap;
-    p.total = fixed + per_system * (size_t)cap;
+    p.total = p.off_list + up(sizeof(int32_t) * (size_t)batch);
+    p.cap = workspace_bytes >= p.total ? batch : 0;  // every flagged system fits
     return p;
 }
 }  // namespace fh
 
 // Workspace for refining up to `max_systems` flagged systems per call.
 extern "C" size_t fh_tridiag_refine_flagged_workspace_bytes(int64_t n, int64_t batch, int64_t max_systems) {
-    if (n <= 0 || batch <= 0) return 0;
-    if (max_systems > batch) max_systems = batch;
-    if (max_systems < 1) max_systems = 1;
-    const fh::RefinePlan p = fh::refine_plan(n, batch, (size_t)0);
-    if (!fh::refine_staged()) return p.total;  // (max_systems: what the four-launch version sized its r / e arrays by)
-    return p.off_r + 2 * sizeof(fh::cplx) * (size_t)n * (size_t)max_systems;
+    (void)n, (void)max_systems;  // (what the four-launch version sized its r / e arrays by)
+    if (batch <= 0) return 0;
+    return fh::refine_plan(batch, (size_t)0).total;
 }
 
 extern "C" int fh_tridiag_refine_flagged_c128(const fh_c128 *dl, const fh_c128 *d, const fh_c128 *du, const fh_c128 *b,
@@ -383,33 +334,18 @@ extern "C" int fh_tridiag_refine_flagged_c128(const fh_c128 *dl, const fh_c128 *
         set_error("refinement is implemented for the batched solver (n <= %lld)", (long long)fh_tridiag_batched_max_n());
         return FH_E_UNSUPPORTED;
     }
-    const RefinePlan p = refine_plan(n, batch, workspace_bytes);
+    const RefinePlan p = refine_plan(batch, workspace_bytes);
     FH_REQUIRE(p.cap >= 1, "workspace too small (see fh_tridiag_refine_flagged_workspace_bytes)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     char *ws = static_cast<char *>(workspace);
     int32_t *header = reinterpret_cast<int32_t *>(ws + p.off_header);
     int32_t *list = reinterpret_cast<int32_t *>(ws + p.off_list);
-    int32_t *status_e = reinterpret_cast<int32_t *>(ws + p.off_status);
-    cplx *r = reinterpret_cast<cplx *>(ws + p.off_r), *e = reinterpret_cast<cplx *>(ws + p.off_e);
     const int32_t mask = 2;  // FH_STATUS_SMALL_PIVOT
     compact_flagged_kernel<<<1, kCompactThreads, 0, st>>>(status, batch, mask, (int32_t)p.cap, list, header);
     FH_LAUNCH_CHECK("compact_flagged_kernel");
-    if (!refine_staged())
-        return batched_refine_subset(reinterpret_cast<const cplx *>(dl), reinterpret_cast<const cplx *>(d),
-                                     reinterpret_cast<const cplx *>(du), reinterpret_cast<const cplx *>(b),
-                                     reinterpret_cast<cplx *>(u), n, batch, list, header + 1, p.cap, status, st);
-    const unsigned grid = (unsigned)(8 * sm_count());
-    residual_subset_kernel<<<grid, kResThreads, 0, st>>>(
-        reinterpret_cast<const cplx *>(dl), reinterpret_cast<const cplx *>(d), reinterpret_cast<const cplx *>(du),
-        reinterpret_cast<const cplx *>(b), reinterpret_cast<const cplx *>(u), n, list, header, r);
-    FH_LAUNCH_CHECK("residual_subset_kernel");
-    int rc = batched_solve_subset(reinterpret_cast<const cplx *>(dl), reinterpret_cast<const cplx *>(d),
-                                  reinterpret_cast<const cplx *>(du), r, e, n, batch, list, header + 1, p.cap, status_e, st);
-    if (rc != FH_OK) return rc;
-    correct_subset_kernel<<<grid, kResThreads, 0, st>>>(reinterpret_cast<cplx *>(u), n, list, header, e, status_e, mask,
-                                                       status);
-    FH_LAUNCH_CHECK("correct_subset_kernel");
-    return FH_OK;
+    return batched_refine_subset(reinterpret_cast<const cplx *>(dl), reinterpret_cast<const cplx *>(d),
+                                 reinterpret_cast<const cplx *>(du), reinterpret_cast<const cplx *>(b),
+                                 reinterpret_cast<cplx *>(u), n, batch, list, header + 1, p.cap, status, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -30,8 +30,8 @@
 //
 // Fused variant: the same kernel with the band loads replaced by the row generator of
 // fh_helm1d.cuh (bit-identical to what fh_assemble_1d_c128 would have stored); 16 B/row written.
-// Subset variant (BandSubsetSource): matrices picked through a device index list -- the correction
-// solve of fh_tridiag_refine_flagged_c128.
+// Refinement variant (BandRefineSource, pipeline kernel only): systems picked through a device index list, the residual
+// formed while the rows are read, the correction added to u -- fh_tridiag_refine_flagged_c128.
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
@@ -805,19 +805,6 @@ int batched_solve_bands(const cplx *dl, const cplx *d, const cplx *du, const cpl
     const cplx *const bands[4] = {dl, d, du, b};
     if (n <= kStageRows) return launch_batched<1>(src, bands, u, n, batch, status, stream);
     return launch_batched<2>(src, bands, u, n, batch, status, stream);
-}
-
-// Solve the systems  A(list[i]) e_i = r_i,  i < min(*count, cap):  matrices picked from a batch of `batch` systems,
-// right-hand sides and solutions compact (cap rows).  Everything the launch needs is known on the host; how many
-// systems there are is read on the device.
-int batched_solve_subset(const cplx *dl, const cplx *d, const cplx *du, const cplx *r, cplx *e, int64_t n, int64_t batch,
-                         const int32_t *list, const int32_t *count, int64_t cap, int32_t *status, cudaStream_t stream) {
-    BandSubsetSource src;
-    src.dl = dl, src.d = d, src.du = du, src.b = r;
-    src.list = list, src.count = count;
-    const cplx *const bands[4] = {dl, d, du, r};
-    if (n <= kStageRows) return launch_batched<1>(src, bands, e, n, cap, status, stream, batch);
-    return launch_batched<2>(src, bands, e, n, cap, status, stream, batch);
 }
 
 // One refinement step  u(list[i]) += A(list[i])^-1 (b - A u)(list[i]),  i < min(*count, cap), in one pass over the

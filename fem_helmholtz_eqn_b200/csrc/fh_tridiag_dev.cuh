@@ -104,18 +104,9 @@ struct BandSource {  // staged pipeline: bands live in global memory
     static constexpr bool kRefine = false;
 };
 
-// Refinement of a SUBSET of a batch (fh_tridiag_refine_flagged_c128): the matrix of compact system i is system
-// list[i] of dl / d / du, its right-hand side and solution are rows i of compact arrays, and the number of systems is
-// read from *count (decided on the device, no host round trip).  A separate type, so that the ordinary solve does not
-// carry the indirection.
-struct BandSubsetSource : BandSource {
-    const int32_t *list;
-    const int32_t *count;
-    static constexpr bool kSubset = true;
-};
-
-// One step of iterative refinement of a subset IN ONE PASS (fh_tridiag_refine_flagged_c128 since round 2): compact
-// system i is system list[i] of ALL five arrays.  The right-hand side of the correction solve, r = b - A u, is formed
+// One step of iterative refinement of a SUBSET of a batch in one pass (fh_tridiag_refine_flagged_c128): compact system i
+// is system list[i] of all five arrays, and the number of systems is read from *count (decided on the device, no host
+// round trip).  A separate type, so that the ordinary solve does not carry the indirection.  The right-hand side of the correction solve, r = b - A u, is formed
 // while the rows are read (each thread fetches the ten solution values its eight rows touch), the correction leaves
 // as a TMA reduce-add onto u (cp.reduce.async.bulk.tensor .add, f64: u += e happens in L2), the small-pivot flag of the
 // system is cleared and a breakdown of the correction solve sets the breakdown bit in the batch's own status array:

@@ -1,6 +1,6 @@
 """Time of the safety nets alone (refinement of the flagged systems, then the repair pass) on the bench's sweep: the
 one-pass kernel runs once, its status flags are restored before every repetition.
-    python tools/refine_probe.py [n_k]        (FH_LIB=... for a variant build, FH_REFINE=staged for the four-launch one)"""
+    python tools/refine_probe.py [n_k]        (FH_LIB=... for a variant build)"""
 import os
 import sys
 
