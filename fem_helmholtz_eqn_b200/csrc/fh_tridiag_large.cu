@@ -366,6 +366,9 @@ struct LevelPtrs {
 };
 
 constexpr int kDeepThreads = 256;
+__device__ __forceinline__ void named_bar_sync_large(int id, int threads) {  // hardware barrier `id` over `threads` threads
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 constexpr int kDeepSpecialMax = 2;        // special chunks per level: one at the front, one at the back (tests/test_large_plan_cpu.py)
 constexpr int kDeepSmallLevelsMax = 8;    // levels the single-CTA back-substitution stages at once (2^14 rows down to 4: five)
 constexpr int64_t kDeepSmall = 1 << 14;   // levels up to this many rows are back-substituted inside the single-CTA kernel
@@ -429,12 +432,13 @@ struct DeepStage {
 // first_thread: the thread that takes entry 0 (several levels staged back to back use different threads).
 __device__ __forceinline__ void deep_stage(const UniformRows &u, const DeepPlan &dp, const DeepConsts *cs,
                                            const DeepCarry *carry, int l, bool with_plain, DeepStage &sg,
-                                           int first_thread = 0) {
+                                           int first_thread = 0, int tid = -1, int nthreads = 0) {
     const DeepLevel &L = dp.lv[l];
     const int ns = deep_special_count(L);
     const int total = (ns + (with_plain ? 1 : 0)) * (kLM + 1);
-    const int nt = (int)blockDim.x;
-    for (int idx = ((int)threadIdx.x + nt - first_thread % nt) % nt; idx < total; idx += nt) {
+    const int nt = nthreads > 0 ? nthreads : (int)blockDim.x;  // (a subset of the CTA's threads: tid in [0, nthreads))
+    if (tid < 0) tid = (int)threadIdx.x;
+    for (int idx = (tid + nt - first_thread % nt) % nt; idx < total; idx += nt) {
         const int s = idx / (kLM + 1), i = idx - s * (kLM + 1);
         cplx a, b, c, d;
         if (s == ns) {
@@ -457,61 +461,88 @@ __device__ __forceinline__ void deep_stage(const UniformRows &u, const DeepPlan 
 // cs: per-level constants in global memory (visible to the whole CTA after each level's barrier).
 __device__ void deep_reduce_levels(const UniformRows &u, const DeepPlan &dp, DeepConsts *cs, DeepStage &sg,
                                    DeepCarry carry[2]) {
+    // The symbolic Thomas sweep of a level's plain chunk (forward + backward: 28 dependent steps, ~3,000 cycles) is
+    // longer than the two reductions (14 steps, ~2,100) and nothing below a level depends on its tables: it runs on
+    // its own warp, one lane, DECOUPLED from the level barriers -- it starts level l as soon as the constants (E_l, O_l)
+    // are published and may trail the reductions by a level or two; two such warps take the even and the odd levels (the
+    // round-2 start had the sweep inside the level barrier: 2.4 us per level, 19.7 us for the eight levels of a 2^24-row
+    // slab).
+    __shared__ int levels_published;  // cs[l].eo is valid for l <= levels_published
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    constexpr int kTableWarp = 2, kTableWarps = 2, kOthers = kDeepThreads - 32 * kTableWarps, kBarLevels = 1;
     if (t == 0) {
         cplx in[4];
         u.interior(in[0], in[1], in[2], in[3]);
         for (int q = 0; q < 4; ++q) cs[0].eo[0][q] = cs[0].eo[1][q] = carry[0].eo[0][q] = carry[0].eo[1][q] = in[q];
+        levels_published = 0;
     }
     __syncthreads();
-    for (int l = 0; l < dp.levels; ++l) {
-        const DeepLevel &L = dp.lv[l];
-        const int ns = deep_special_count(L);
-        const DeepCarry &now = carry[l & 1];
-        DeepCarry &next = carry[(l + 1) & 1];
-        deep_stage(u, dp, cs, &now, l, true, sg);
-        __syncthreads();
-        if (warp < 2 && lane <= ns) {
-            cplx out[4];
-            const DeepRows &R = sg.rows[lane];
-            auto rowfn = [&](int i, cplx &a, cplx &b, cplx &c, cplx &d) { a = R[i][0], b = R[i][1], c = R[i][2], d = R[i][3]; };
-            if (warp == 0) reduce_chunk_down(rowfn, sg.len[lane], out);
-            else reduce_chunk_up(rowfn, sg.len[lane], out);
-            const int which = warp == 0 ? 1 : 0;  // downward sweep -> the row in the LAST unknown
-            if (lane == ns) {
-                for (int q = 0; q < 4; ++q) cs[l + 1].eo[which][q] = next.eo[which][q] = out[q];
-            } else {  // (to global memory for the back-substitution, to shared memory for the next level)
-                const LevelPtrs &p = dp.ptr[l + 1];
-                const int64_t o = 2 * deep_special_chunk(L, lane) + which;
-                p.a[o] = out[0], p.b[o] = out[1], p.c[o] = out[2], p.d[o] = out[3];
-                for (int q = 0; q < 4; ++q) next.spec[2 * lane + which][q] = out[q];
+    if (warp >= kTableWarp && warp < kTableWarp + kTableWarps) {
+        if (lane == 0) {
+            for (int l = warp - kTableWarp; l < dp.levels; l += kTableWarps) {
+                while (*(volatile int *)&levels_published < l) __nanosleep(40);
+                __threadfence_block();
+                cplx R[2][4];  // the plain rows of the level: E (even positions), O (odd positions)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const volatile double *e0 = &cs[l].eo[0][q].re, *e1 = &cs[l].eo[1][q].re;
+                    R[0][q] = mk(e0[0], e0[1]), R[1][q] = mk(e1[0], e1[1]);
+                }
+                // x_i = alpha_i x_first + beta_i x_last + gamma_i for a plain chunk of this level
+                cplx fc[kLM], fP[kLM], fG[kLM];
+                cplx cp = czero(), Pp = cone(), Gp = czero();
+#pragma unroll
+                for (int i = 1; i <= kLM - 2; ++i) {  // forward sweep with x_first as a symbol: dp_i = P_i x_first + G_i
+                    const cplx *r = R[i & 1];
+                    const cplx inv = frecip(nmsub(r[1], r[0], cp));
+                    Pp = -((r[0] * Pp) * inv);
+                    Gp = nmsub(r[3], r[0], Gp) * inv;
+                    cp = r[2] * inv;
+                    fc[i] = cp, fP[i] = Pp, fG[i] = Gp;
+                }
+                cplx al = czero(), be = cone(), ga = czero();  // backward sweep with x_last as a symbol
+                cs[l].tab[0][kLM - 1] = al, cs[l].tab[1][kLM - 1] = be, cs[l].tab[2][kLM - 1] = ga;  // x_15 = x_last
+#pragma unroll
+                for (int i = kLM - 2; i >= 1; --i) {
+                    al = nmsub(fP[i], fc[i], al);
+                    be = -(fc[i] * be);
+                    ga = nmsub(fG[i], fc[i], ga);
+                    cs[l].tab[0][i] = al, cs[l].tab[1][i] = be, cs[l].tab[2][i] = ga;
+                }
+                cs[l].tab[0][0] = cone(), cs[l].tab[1][0] = czero(), cs[l].tab[2][0] = czero();  // x_0 = x_first
             }
         }
-        if (t == 64) {  // x_i = alpha_i x_first + beta_i x_last + gamma_i for a plain chunk of this level
-            const DeepRows &R = sg.rows[ns];
-            cplx fc[kLM], fP[kLM], fG[kLM];
-            cplx cp = czero(), Pp = cone(), Gp = czero();
-#pragma unroll
-            for (int i = 1; i <= kLM - 2; ++i) {  // forward sweep with x_first as a symbol: dp_i = P_i x_first + G_i
-                const cplx inv = frecip(nmsub(R[i][1], R[i][0], cp));
-                Pp = -((R[i][0] * Pp) * inv);
-                Gp = nmsub(R[i][3], R[i][0], Gp) * inv;
-                cp = R[i][2] * inv;
-                fc[i] = cp, fP[i] = Pp, fG[i] = Gp;
+    } else {
+        const int tid = t < 32 * kTableWarp ? t : t - 32 * kTableWarps;  // the other 192 threads, numbered 0 .. 191
+        for (int l = 0; l < dp.levels; ++l) {
+            const DeepLevel &L = dp.lv[l];
+            const int ns = deep_special_count(L);
+            const DeepCarry &now = carry[l & 1];
+            DeepCarry &next = carry[(l + 1) & 1];
+            deep_stage(u, dp, cs, &now, l, true, sg, 0, tid, kOthers);
+            named_bar_sync_large(kBarLevels, kOthers);
+            if (warp < 2 && lane <= ns) {
+                cplx out[4];
+                const DeepRows &R = sg.rows[lane];
+                auto rowfn = [&](int i, cplx &a, cplx &b, cplx &c, cplx &d) { a = R[i][0], b = R[i][1], c = R[i][2], d = R[i][3]; };
+                if (warp == 0) reduce_chunk_down(rowfn, sg.len[lane], out);
+                else reduce_chunk_up(rowfn, sg.len[lane], out);
+                const int which = warp == 0 ? 1 : 0;  // downward sweep -> the row in the LAST unknown
+                if (lane == ns) {
+                    for (int q = 0; q < 4; ++q) cs[l + 1].eo[which][q] = next.eo[which][q] = out[q];
+                } else {  // (to global memory for the back-substitution, to shared memory for the next level)
+                    const LevelPtrs &p = dp.ptr[l + 1];
+                    const int64_t o = 2 * deep_special_chunk(L, lane) + which;
+                    p.a[o] = out[0], p.b[o] = out[1], p.c[o] = out[2], p.d[o] = out[3];
+                    for (int q = 0; q < 4; ++q) next.spec[2 * lane + which][q] = out[q];
+                }
+                __threadfence_block();
             }
-            cplx al = czero(), be = cone(), ga = czero();  // backward sweep with x_last as a symbol
-            cs[l].tab[0][kLM - 1] = al, cs[l].tab[1][kLM - 1] = be, cs[l].tab[2][kLM - 1] = ga;  // x_15 = x_last
-#pragma unroll
-            for (int i = kLM - 2; i >= 1; --i) {
-                al = nmsub(fP[i], fc[i], al);
-                be = -(fc[i] * be);
-                ga = nmsub(fG[i], fc[i], ga);
-                cs[l].tab[0][i] = al, cs[l].tab[1][i] = be, cs[l].tab[2][i] = ga;
-            }
-            cs[l].tab[0][0] = cone(), cs[l].tab[1][0] = czero(), cs[l].tab[2][0] = czero();  // x_0 = x_first
+            named_bar_sync_large(kBarLevels, kOthers);
+            if (t == 0) *(volatile int *)&levels_published = l + 1;  // (E, O) of level l + 1 are in cs[l + 1].eo
         }
-        __syncthreads();
     }
+    __syncthreads();  // the tables of every level are complete
     // the 2-row level in full: plain positions are filled in, so that its four arrays (a[2] b[2] c[2] d[2], contiguous)
     // are the slab's interface rows
     const DeepLevel &T = dp.lv[dp.levels];
