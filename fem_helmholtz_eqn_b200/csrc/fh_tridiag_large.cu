@@ -365,6 +365,12 @@ struct LevelPtrs {
     cplx *a, *b, *c, *d, *x;
 };
 
+#ifdef FH_DEEP_TRACE
+__device__ long long g_deep_trace[64];
+#define FH_DT(k) do { if (threadIdx.x == 0) g_deep_trace[k] = clock64(); } while (0)
+#else
+#define FH_DT(k) do { } while (0)
+#endif
 constexpr int kDeepThreads = 256;
 __device__ __forceinline__ void named_bar_sync_large(int id, int threads) {  // hardware barrier `id` over `threads` threads
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
@@ -519,8 +525,10 @@ __device__ void deep_reduce_levels(const UniformRows &u, const DeepPlan &dp, Dee
             const int ns = deep_special_count(L);
             const DeepCarry &now = carry[l & 1];
             DeepCarry &next = carry[(l + 1) & 1];
+            FH_DT(3 * l);
             deep_stage(u, dp, cs, &now, l, true, sg, 0, tid, kOthers);
             named_bar_sync_large(kBarLevels, kOthers);
+            FH_DT(3 * l + 1);
             if (warp < 2 && lane <= ns) {
                 cplx out[4];
                 const DeepRows &R = sg.rows[lane];
@@ -539,10 +547,13 @@ __device__ void deep_reduce_levels(const UniformRows &u, const DeepPlan &dp, Dee
                 __threadfence_block();
             }
             named_bar_sync_large(kBarLevels, kOthers);
+            FH_DT(3 * l + 2);
             if (t == 0) *(volatile int *)&levels_published = l + 1;  // (E, O) of level l + 1 are in cs[l + 1].eo
         }
     }
+    FH_DT(60);
     __syncthreads();  // the tables of every level are complete
+    FH_DT(61);
     // the 2-row level in full: plain positions are filled in, so that its four arrays (a[2] b[2] c[2] d[2], contiguous)
     // are the slab's interface rows
     const DeepLevel &T = dp.lv[dp.levels];
@@ -1180,6 +1191,11 @@ static int kdev_unsupported() {
 
 extern "C" {
 
+#ifdef FH_DEEP_TRACE
+__attribute__((visibility("default"))) int fh_debug_deep_trace(long long *out64) {
+    return (int)cudaMemcpyFromSymbol(out64, fh::g_deep_trace, sizeof(long long) * 64);
+}
+#endif
 #ifdef FH_PROBE_STAT
 __attribute__((visibility("default"))) double fh_debug_probe_max(int reset) {
     unsigned long long v = 0ull, z = 0ull;
